@@ -1,0 +1,101 @@
+"""Mint the golden fixtures by running the REAL reference (read-only, /root/reference) on CPU.
+
+Run in the build container only (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+Outputs (committed): tests/golden/forward_identity.npz, forward_randombn.npz,
+panostretch_small.npz, panostretch_rows.npz.  The two shims are the ones SURVEY.md section 8c
+describes: torchvision.resnet50 is forced to weights=None (no network), nothing else is patched.
+Weights/inputs come from horizonnet_b200.weights (numpy RandomState => reproducible on any box).
+"""
+import os
+import sys
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+REF = '/root/reference'
+sys.path.insert(0, REF)
+
+import torchvision.models as tvm            # noqa: E402
+_orig = tvm.resnet50
+tvm.resnet50 = lambda *a, **k: _orig(weights=None)     # shim 1: no network
+import model as ref_model                    # noqa: E402  (reference model.py)
+from misc import panostretch as ref_ps       # noqa: E402  (reference misc/panostretch.py)
+
+from horizonnet_b200.weights import synthetic_state_dict, synthetic_panoramas   # noqa: E402
+
+N_SAMPLES = 4096
+KGRID = (0.5, 0.75, 1.0, 1.25, 1.5, 1.75, 2.0)
+# the 12-point example label of README_PREPARE_DATASET.md:53-64 (x, y): ceiling/floor pairs
+CORNERS = np.array([[158, 186], [158, 329], [353, 185], [353, 330], [594, 154], [594, 363],
+                    [713, 100], [713, 415], [692, 77], [692, 438], [965, 150], [965, 367]], np.float32)
+
+
+def sample(t):
+    flat = t.detach().reshape(-1).double().numpy()
+    stride = max(1, flat.size // N_SAMPLES)
+    return flat[::stride][:N_SAMPLES].astype(np.float32), np.float64(np.abs(flat).mean()), np.float64(np.abs(flat).max())
+
+
+def golden_forward(name, seed, bn, batch):
+    torch.manual_seed(0)
+    net = ref_model.HorizonNet('resnet50', True).eval()
+    sd = synthetic_state_dict(seed, bn)
+    net.load_state_dict(sd, strict=True)          # proves the 448-key layout is the reference's
+    x = synthetic_panoramas(batch, seed=100 + seed)
+    stages = {}
+    net.feature_extractor.register_forward_hook(
+        lambda m, i, o: stages.update({f'layer{j + 1}': o[j] for j in range(4)}))
+    net.reduce_height_module.register_forward_hook(lambda m, i, o: stages.update(feature=o))
+    net.bi_rnn.register_forward_hook(lambda m, i, o: stages.update(rnn_out=o[0]))
+    with torch.no_grad():
+        bon, cor = net(x)
+    out = dict(bon=bon.numpy(), cor=cor.numpy(), seed=seed, batch=batch, x_seed=100 + seed)
+    for k, v in stages.items():
+        s, mean_abs, max_abs = sample(v)
+        out[k + '_sample'] = s
+        out[k + '_meanabs'] = mean_abs
+        out[k + '_maxabs'] = max_abs
+        out[k + '_shape'] = np.array(v.shape)
+    np.savez_compressed(os.path.join(HERE, f'forward_{name}.npz'), **out)
+    print(name, 'bon', float(bon.abs().max()), 'cor', float(cor.abs().max()),
+          {k: float(v.abs().max()) for k, v in stages.items()})
+
+
+def golden_panostretch():
+    small = {}
+    rs = np.random.RandomState(7)
+    img_s = rs.random_sample((32, 64, 3)).astype(np.float32)
+    small['img'] = img_s
+    cs = CORNERS * np.array([64 / 1024, 32 / 512], np.float32)
+    for kx in KGRID:
+        for ky in KGRID:
+            o, c = ref_ps.pano_stretch(img_s, cs, kx, ky)
+            small[f'out_{kx}_{ky}'] = o
+            small[f'cor_{kx}_{ky}'] = c
+    o0, _ = ref_ps.pano_stretch(img_s, cs, 1.5, 0.75, order=0)
+    small['out0_1.5_0.75'] = o0
+    np.savez_compressed(os.path.join(HERE, 'panostretch_small.npz'), **small)
+
+    rows = {}
+    img = np.random.RandomState(0).random_sample((512, 1024, 3)).astype(np.float32)
+    sel = np.array([0, 1, 2, 130, 255, 256, 381, 509, 510, 511])
+    rows['rows'] = sel
+    for kx in KGRID:
+        for ky in KGRID:
+            o, c = ref_ps.pano_stretch(img, CORNERS, kx, ky)
+            rows[f'sum_{kx}_{ky}'] = np.float64(o.astype(np.float64).sum())
+            rows[f'sq_{kx}_{ky}'] = np.float64((o.astype(np.float64) ** 2).sum())
+            rows[f'cor_{kx}_{ky}'] = c
+            if (kx, ky) in ((2.0, 1.0), (0.5, 2.0), (1.0, 1.0), (1.25, 0.75), (2.0, 0.5), (0.75, 1.75)):
+                rows[f'out_{kx}_{ky}'] = o[sel]
+    np.savez_compressed(os.path.join(HERE, 'panostretch_rows.npz'), **rows)
+    print('panostretch fixtures written')
+
+
+if __name__ == '__main__':
+    golden_panostretch()
+    golden_forward('identity', seed=0, bn='identity', batch=2)
+    golden_forward('randombn', seed=1, bn='random', batch=1)

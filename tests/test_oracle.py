@@ -1,0 +1,94 @@
+"""CPU: pin the oracle (oracle/) against golden outputs minted from the REAL reference
+(tests/golden/make_golden.py).  Tolerances: forward 2e-5 max-abs on O(1) outputs (fp32 CPU
+summation order differs between the functional restatement / machines; fp32-vs-fp64 noise floor
+of the model is ~7e-7); pano_stretch 1.2e-7 (one fp32 ulp at values in [0,1))."""
+import json
+import os
+import numpy as np
+import pytest
+import torch
+
+from horizonnet_b200._spec import state_dict_spec
+from horizonnet_b200.weights import synthetic_state_dict, synthetic_panoramas
+from oracle import horizonnet_ref, panostretch_ref
+
+KGRID = (0.5, 0.75, 1.0, 1.25, 1.5, 1.75, 2.0)
+
+
+def test_spec_matches_reference_checkpoint_layout(golden_dir):
+    ref = json.load(open(os.path.join(golden_dir, 'state_dict_keys.json')))
+    spec = state_dict_spec()
+    assert len(spec) == 448
+    for (k, shape, dt), (k2, (s2, _)) in zip(ref, spec.items()):
+        assert k == k2 and tuple(shape) == tuple(s2)
+    n_params = sum(int(np.prod(s)) for k, (s, kind) in spec.items()
+                   if kind not in ('bn_mean', 'bn_var', 'bn_count'))
+    assert n_params == 81570348
+
+
+def _sample(t, n=4096):
+    flat = t.detach().reshape(-1).double().numpy()
+    stride = max(1, flat.size // n)
+    return flat[::stride][:n].astype(np.float32)
+
+
+@pytest.mark.parametrize('name,bn', [('identity', 'identity'), ('randombn', 'random')])
+def test_forward_oracle_matches_reference(golden_dir, name, bn):
+    g = np.load(os.path.join(golden_dir, f'forward_{name}.npz'))
+    sd = synthetic_state_dict(int(g['seed']), bn)
+    x = synthetic_panoramas(int(g['batch']), seed=int(g['x_seed']))
+    with torch.no_grad():
+        bon, cor, stages = horizonnet_ref.forward(sd, x, return_stages=True)
+    assert bon.shape == (x.shape[0], 2, 1024) and cor.shape == (x.shape[0], 1, 1024)
+    assert np.abs(bon.numpy() - g['bon']).max() < 2e-5
+    assert np.abs(cor.numpy() - g['cor']).max() < 2e-5
+    for k, v in stages.items():
+        ref = g[k + '_sample']
+        scale = float(g[k + '_maxabs'])
+        assert tuple(v.shape) == tuple(g[k + '_shape'])
+        assert np.abs(_sample(v) - ref).max() <= 2e-6 * scale + 1e-6, k
+
+
+def test_forward_oracle_rejects_other_sizes():
+    sd = {}
+    with pytest.raises(NotImplementedError):
+        horizonnet_ref.forward(sd, torch.zeros(1, 3, 256, 512))
+
+
+def test_panostretch_oracle_small_full_grid(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'panostretch_small.npz'))
+    img = g['img']
+    for kx in KGRID:
+        for ky in KGRID:
+            out, _ = panostretch_ref.pano_stretch(img, np.zeros((1, 2), np.float32), kx, ky)
+            assert out.dtype == np.float32 and out.shape == img.shape
+            assert np.abs(out - g[f'out_{kx}_{ky}']).max() <= 1.2e-7, (kx, ky)
+    out0, _ = panostretch_ref.pano_stretch(img, np.zeros((1, 2), np.float32), 1.5, 0.75, order=0)
+    assert np.array_equal(out0, g['out0_1.5_0.75'])
+
+
+def test_panostretch_oracle_full_size_rows_and_corners(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'panostretch_rows.npz'))
+    img = np.random.RandomState(0).random_sample((512, 1024, 3)).astype(np.float32)
+    corners = np.array([[158, 186], [158, 329], [353, 185], [353, 330], [594, 154], [594, 363],
+                        [713, 100], [713, 415], [692, 77], [692, 438], [965, 150], [965, 367]], np.float32)
+    rows = g['rows']
+    for key in g.files:
+        if not key.startswith('out_'):
+            continue
+        _, kx, ky = key.split('_')
+        out, cor = panostretch_ref.pano_stretch(img, corners, float(kx), float(ky))
+        assert np.abs(out[rows] - g[key]).max() <= 1.2e-7, key
+        assert abs(out.astype(np.float64).sum() - float(g[f'sum_{kx}_{ky}'])) < 1e-3
+        assert np.abs(cor - g[f'cor_{kx}_{ky}']).max() < 1e-9
+    # identity property: kx = ky = 1 reproduces the image
+    out, cor = panostretch_ref.pano_stretch(img, corners, 1.0, 1.0)
+    assert np.abs(out - img).max() <= 1.2e-7
+    assert np.abs(cor - corners).max() < 1e-4
+
+
+def test_legacy_wrap_rule():
+    # SURVEY hard-part 5: scipy's legacy 'wrap' has period n-1: [10,20,30,40,50] at -0.3 -> 47.0
+    a = np.array([[10., 20., 30., 40., 50.]])
+    v = panostretch_ref.map_coordinates_wrap(a, np.array([[0.0]]), np.array([[-0.3]]))
+    assert abs(float(v[0, 0]) - 47.0) < 1e-12
