@@ -1,0 +1,74 @@
+"""ctypes binding of libhorizonnet_b200.so (include/horizonnet_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a call fails, a
+RuntimeError is raised (the product path never routes through torch ops or the CPU oracle)."""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libhorizonnet_b200.so')
+ABI_VERSION = 1
+
+_lib = None
+_lock = threading.Lock()
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+vp = ctypes.c_void_p
+
+# name -> (restype, argtypes); mirrors include/horizonnet_b200.h one to one
+SIGNATURES = {
+    'hn_last_error': (ctypes.c_char_p, []),
+    'hn_abi_version': (ctypes.c_int, []),
+    'hn_kernel_launches': (ctypes.c_longlong, []),
+    'hn_model_create': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]),
+    'hn_model_num_tensors': (ctypes.c_int, [vp]),
+    'hn_model_tensor_info': (ctypes.c_int, [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_char_p),
+                                            ctypes.POINTER(ctypes.c_longlong)]),
+    'hn_model_set_tensor': (ctypes.c_int, [vp, ctypes.c_char_p, vp, ctypes.c_longlong, ctypes.c_int]),
+    'hn_model_finalize': (ctypes.c_int, [vp]),
+    'hn_model_forward': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
+    'hn_model_forward_host': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp]),
+    'hn_model_stage': (ctypes.c_int, [vp, ctypes.c_char_p, vp, ctypes.c_longlong, c_int_p, vp]),
+    'hn_model_set_option': (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.c_int]),
+    'hn_model_check': (ctypes.c_int, [vp]),
+    'hn_model_destroy': (None, [vp]),
+    'hn_pano_stretch': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                       c_double_p, c_double_p, ctypes.c_int, vp]),
+    'hn_pano_stretch_host': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                            c_double_p, c_double_p, ctypes.c_int]),
+    'hn_conv2d': (ctypes.c_int, [vp] + [ctypes.c_int] * 5 + [vp, vp, vp, vp] + [ctypes.c_int] * 8 +
+                  [vp, ctypes.c_int, ctypes.c_int, vp]),
+    'hn_lstm_layer': (ctypes.c_int, [vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]),
+}
+
+
+def lib():
+    """Loads the library once; raises RuntimeError (never falls back) when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f'{LIB_PATH} is missing: run `python -c "import __graft_entry__ as g; g.build()"` '
+                '(horizonnet_b200 has no CPU / PyTorch fallback)')
+        l = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)          # AttributeError here = header/library mismatch
+            fn.restype = res
+            fn.argtypes = args
+        if l.hn_abi_version() != ABI_VERSION:
+            raise RuntimeError('libhorizonnet_b200 ABI version mismatch; rebuild')
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().hn_last_error().decode('utf-8', 'replace')
+        raise RuntimeError(f'{what} failed: {msg}')

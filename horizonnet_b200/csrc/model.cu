@@ -1,0 +1,600 @@
+// hn_model: weight registry (reference checkpoint layout, misc/utils.py:49-65), BN folding and
+// weight packing, activation workspace, and the forward schedule of HorizonNet('resnet50', rnn)
+// (reference model.py:254-281), plus the C ABI (include/horizonnet_b200.h).
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+#include <atomic>
+
+#include "hn_common.cuh"
+#include "../../include/horizonnet_b200.h"
+
+namespace hn {
+
+// ---- error / launch accounting -----------------------------------------------------------------
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+void set_error(const std::string& m) { g_err = m; }
+int fail(const std::string& m) { g_err = m; return -1; }
+void count_launch(int n) { g_launches += n; }
+
+int ghc_to_sequence(const Act ghc[4], float* seq, cudaStream_t st);
+int linear_head(const float* rnn, const float* w, const float* bias, float* bon, float* cor, int T, int B,
+                cudaStream_t st);
+int lstm_layer(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, float* out, int T, int B,
+               unsigned int* counters, int* error_flag, cudaStream_t st);
+int pano_stretch_device(const float* img, float* out, int n, int H, int W, int C, const double* kx_dev,
+                        const double* ky_dev, double* scratch, int order, cudaStream_t st);
+int conv_tc(const ConvDesc& d, const Act& in, const Act& out, const float* residual, cudaStream_t st);
+bool conv_tc_supported(const ConvDesc& d, const Act& in, const Act& out);
+
+namespace {
+
+// ---- packing kernels ---------------------------------------------------------------------------
+// OIHW [Cout][Cin][kh][kw] -> [K = (dy*kw+dx)*Cin + c][Cout]
+__global__ void pack_oihw_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kh,
+                                 int kw) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)Cout * Cin * kh * kw;
+    if (i >= total) return;
+    const int n = (int)(i % Cout);
+    const size_t k = i / Cout;
+    const int c = (int)(k % Cin);
+    const int tap = (int)(k / Cin);
+    const int dy = tap / kw, dx = tap % kw;
+    out[i] = w[(((size_t)n * Cin + c) * kh + dy) * kw + dx];
+}
+
+// eval-mode BN (+ optional conv bias) -> scale/shift:  y = conv*scale + shift
+__global__ void fold_bn_kernel(const float* __restrict__ gamma, const float* __restrict__ beta,
+                               const float* __restrict__ mean, const float* __restrict__ var,
+                               const float* __restrict__ bias, float* __restrict__ scale,
+                               float* __restrict__ shift, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C) return;
+    const double s = (double)gamma[i] / sqrt((double)var[i] + 1e-5);      // BatchNorm2d eps (model.py:130)
+    const double b = bias ? (double)bias[i] : 0.0;
+    scale[i] = (float)s;
+    shift[i] = (float)((double)beta[i] + (b - (double)mean[i]) * s);
+}
+
+__global__ void lstm_bias_kernel(const float* __restrict__ bih_f, const float* __restrict__ bhh_f,
+                                 const float* __restrict__ bih_b, const float* __restrict__ bhh_b,
+                                 float* __restrict__ scale, float* __restrict__ shift) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 4096) return;
+    scale[i] = 1.f;
+    shift[i] = i < 2048 ? bih_f[i] + bhh_f[i] : bih_b[i - 2048] + bhh_b[i - 2048];
+}
+
+// halo-NHWC interior -> NCHW (test hook)
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, float* __restrict__ out, int B, int H, int W,
+                                    int C, int halo) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)B * C * H * W;
+    if (i >= total) return;
+    const int w = (int)(i % W);
+    size_t t = i / W;
+    const int h = (int)(t % H); t /= H;
+    const int c = (int)(t % C);
+    const int b = (int)(t / C);
+    out[i] = in[(((size_t)b * H + h) * (W + 2 * halo) + w + halo) * C + c];
+}
+
+// seq [T][B][1024] -> feature [B][1024][T]
+__global__ void seq_to_feature_kernel(const float* __restrict__ seq, float* __restrict__ out, int T, int B) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)T * B * 1024;
+    if (i >= total) return;
+    const int t = (int)(i % T);
+    const int ch = (int)((i / T) % 1024);
+    const int b = (int)(i / T / 1024);
+    out[i] = seq[((size_t)t * B + b) * 1024 + ch];
+}
+
+struct TensorSlot {
+    std::string key;
+    long long numel = 0;
+    float* dev = nullptr;     // staging copy in the reference layout
+    bool set = false;
+    bool ignored = false;     // num_batches_tracked
+};
+
+struct ConvLayer {
+    ConvDesc d;
+    std::string wkey, bnprefix, biaskey;
+    float* w = nullptr;
+    float* scale = nullptr;
+    float* shift = nullptr;
+};
+
+}  // namespace
+}  // namespace hn
+
+using namespace hn;
+
+struct hn_model {
+    int device = 0;
+    int max_batch = 0;
+    bool finalized = false;
+    int use_tc = 0;                                  // 1: route supported convs through tcgen05 kernels
+    std::vector<TensorSlot> slots;
+    std::map<std::string, int> index;
+    std::vector<void*> allocs;
+
+    // graph
+    ConvLayer stem;                                  // weights packed [147][64]
+    struct Block { ConvLayer c1, c2, c3, ds; bool has_ds = false; };
+    std::vector<Block> blocks[4];
+    ConvLayer ghc[4][4];
+    ConvLayer xproj[2];                              // LSTM input projections as 1x1 convs, N = 4096
+    float* head_w = nullptr;
+    float* head_b = nullptr;
+    const float* whh[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+
+    // workspace (sized for max_batch)
+    float *S0 = nullptr, *S1 = nullptr, *X[2] = {nullptr, nullptr}, *IDN = nullptr, *T1 = nullptr, *T2 = nullptr;
+    float* F[4] = {nullptr, nullptr, nullptr, nullptr};
+    float* G[2] = {nullptr, nullptr};
+    float* GO[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *SEQ = nullptr, *XP = nullptr, *R1 = nullptr, *R2 = nullptr;
+    unsigned int* counters = nullptr;
+    int* error_flag = nullptr;
+    float *x_in = nullptr, *bon_out = nullptr, *cor_out = nullptr;    // for forward_host
+    int last_batch = 0;
+
+    ~hn_model() {
+        cudaSetDevice(device);
+        for (void* p : allocs) cudaFree(p);
+    }
+    int alloc(void** p, size_t bytes) {
+        HN_CUDA_OK(cudaMalloc(p, bytes ? bytes : 4));
+        allocs.push_back(*p);
+        return 0;
+    }
+    template <typename T>
+    int alloc_t(T** p, size_t n) { return alloc(reinterpret_cast<void**>(p), n * sizeof(T)); }
+
+    int add_slot(const std::string& key, long long numel, bool ignored = false) {
+        TensorSlot s;
+        s.key = key; s.numel = numel; s.ignored = ignored;
+        index[key] = (int)slots.size();
+        slots.push_back(s);
+        return 0;
+    }
+    void add_bn(const std::string& p, int c) {
+        add_slot(p + ".weight", c); add_slot(p + ".bias", c);
+        add_slot(p + ".running_mean", c); add_slot(p + ".running_var", c);
+        add_slot(p + ".num_batches_tracked", 1, true);
+    }
+    const float* T(const std::string& key) const { return slots[index.at(key)].dev; }
+};
+
+namespace {
+
+ConvLayer make_conv(hn_model* m, const std::string& wkey, const std::string& bn, const std::string& biaskey, int cin,
+                    int cout, int k, int sh, int sw, int relu) {
+    ConvLayer c;
+    c.d.Cin = cin; c.d.Cout = cout; c.d.kh = k; c.d.kw = k; c.d.sh = sh; c.d.sw = sw;
+    c.d.ph = k / 2; c.d.pw = k / 2; c.d.relu = relu;
+    c.wkey = wkey; c.bnprefix = bn; c.biaskey = biaskey;
+    m->add_slot(wkey, (long long)cout * cin * k * k);
+    if (!biaskey.empty()) m->add_slot(biaskey, cout);
+    m->add_bn(bn, cout);
+    return c;
+}
+
+// Builds the key list in the reference's own order (tests/golden/state_dict_keys.json) and the graph.
+void build_graph(hn_model* m) {
+    const std::string enc = "feature_extractor.encoder.";
+    m->stem = make_conv(m, enc + "conv1.1.weight", enc + "bn1", "", 3, 64, 7, 2, 2, 1);
+    const int nblk[4] = {3, 4, 6, 3};
+    const int planes[4] = {64, 128, 256, 512};
+    int inpl = 64;
+    for (int l = 0; l < 4; ++l) {
+        for (int b = 0; b < nblk[l]; ++b) {
+            const std::string p = enc + "layer" + std::to_string(l + 1) + "." + std::to_string(b) + ".";
+            const int stride = (b == 0 && l > 0) ? 2 : 1;
+            hn_model::Block blk;
+            blk.c1 = make_conv(m, p + "conv1.weight", p + "bn1", "", inpl, planes[l], 1, 1, 1, 1);
+            blk.c2 = make_conv(m, p + "conv2.1.weight", p + "bn2", "", planes[l], planes[l], 3, stride, stride, 1);
+            blk.c3 = make_conv(m, p + "conv3.weight", p + "bn3", "", planes[l], planes[l] * 4, 1, 1, 1, 1);
+            blk.has_ds = (b == 0);
+            if (blk.has_ds)
+                blk.ds = make_conv(m, p + "downsample.0.weight", p + "downsample.1", "", inpl, planes[l] * 4, 1, stride,
+                                   stride, 0);
+            inpl = planes[l] * 4;
+            m->blocks[l].push_back(blk);
+        }
+    }
+    for (int s = 0; s < 4; ++s) {
+        const int c = planes[s] * 4;
+        const int ch[5] = {c, c / 2, c / 2, c / 4, c / 8};
+        for (int j = 0; j < 4; ++j) {
+            const std::string p =
+                "reduce_height_module.ghc_lst." + std::to_string(s) + ".layer." + std::to_string(j) + ".layers.";
+            m->ghc[s][j] = make_conv(m, p + "0.1.weight", p + "1", p + "0.1.bias", ch[j], ch[j + 1], 3, 2, 1, 1);
+        }
+    }
+    for (int layer = 0; layer < 2; ++layer)
+        for (int dir = 0; dir < 2; ++dir) {
+            const std::string sfx = "_l" + std::to_string(layer) + (dir ? "_reverse" : "");
+            m->add_slot("bi_rnn.weight_ih" + sfx, 2048ll * 1024);
+            m->add_slot("bi_rnn.weight_hh" + sfx, 2048ll * 512);
+            m->add_slot("bi_rnn.bias_ih" + sfx, 2048);
+            m->add_slot("bi_rnn.bias_hh" + sfx, 2048);
+        }
+    m->add_slot("linear.weight", 12 * 1024);
+    m->add_slot("linear.bias", 12);
+    for (int layer = 0; layer < 2; ++layer) {
+        ConvLayer& c = m->xproj[layer];
+        c.d.Cin = 1024; c.d.Cout = 4096; c.d.kh = c.d.kw = 1; c.d.sh = c.d.sw = 1; c.d.ph = c.d.pw = 0; c.d.relu = 0;
+    }
+}
+
+int pack_conv(hn_model* m, ConvLayer& c, cudaStream_t st) {
+    const size_t nw = (size_t)c.d.Cout * c.d.Cin * c.d.kh * c.d.kw;
+    if (!c.w) {
+        if (m->alloc_t(&c.w, nw)) return -1;
+        if (m->alloc_t(&c.scale, c.d.Cout)) return -1;
+        if (m->alloc_t(&c.shift, c.d.Cout)) return -1;
+    }
+    pack_oihw_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(m->T(c.wkey), c.w, c.d.Cout, c.d.Cin, c.d.kh, c.d.kw);
+    HN_LAUNCH_OK();
+    fold_bn_kernel<<<(c.d.Cout + 255) / 256, 256, 0, st>>>(
+        m->T(c.bnprefix + ".weight"), m->T(c.bnprefix + ".bias"), m->T(c.bnprefix + ".running_mean"),
+        m->T(c.bnprefix + ".running_var"), c.biaskey.empty() ? nullptr : m->T(c.biaskey), c.scale, c.shift, c.d.Cout);
+    HN_LAUNCH_OK();
+    c.d.w = c.w; c.d.scale = c.scale; c.d.shift = c.shift;
+    return 0;
+}
+
+Act mk(float* p, int B, int H, int W, int C, int halo = 1) {
+    Act a; a.p = p; a.B = B; a.H = H; a.W = W; a.C = C; a.halo = halo; return a;
+}
+
+int run_conv(hn_model* m, const ConvLayer& c, const Act& in, const Act& out, const float* res, cudaStream_t st) {
+    if (m->use_tc && conv_tc_supported(c.d, in, out)) return conv_tc(c.d, in, out, res, st);
+    return conv_f32(c.d, in, out, res, st);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* hn_last_error(void) { return g_err.c_str(); }
+int hn_abi_version(void) { return 1; }
+long long hn_kernel_launches(void) { return g_launches.load(); }
+
+int hn_model_create(int device, int max_batch, hn_model** out) {
+    HN_CHECK(out != nullptr, "hn_model_create: out is NULL");
+    HN_CHECK(max_batch >= 1 && max_batch <= 1024, "hn_model_create: max_batch must be in 1..1024");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("hn_model_create: no CUDA device -- libhorizonnet_b200 has no CPU path");
+    HN_CHECK(device >= 0 && device < ndev, "hn_model_create: bad device index");
+    HN_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    HN_CHECK(prop.major == 10, "hn_model_create: this library is built for sm_100a (B200) only");
+    std::unique_ptr<hn_model> m(new hn_model());
+    m->device = device;
+    m->max_batch = max_batch;
+    build_graph(m.get());
+    for (auto& s : m->slots)
+        if (!s.ignored && m->alloc_t(&s.dev, (size_t)s.numel)) return -1;
+    const size_t B = (size_t)max_batch;
+    struct { float** p; size_t n; } bufs[] = {
+        {&m->S0, B * 256 * 514 * 64},   {&m->S1, B * 128 * 258 * 64},  {&m->X[0], B * 128 * 258 * 256},
+        {&m->X[1], B * 128 * 258 * 256}, {&m->IDN, B * 128 * 258 * 256}, {&m->T1, B * 128 * 258 * 128},
+        {&m->T2, B * 128 * 258 * 64},   {&m->F[0], B * 128 * 258 * 256}, {&m->F[1], B * 64 * 130 * 512},
+        {&m->F[2], B * 32 * 66 * 1024}, {&m->F[3], B * 16 * 34 * 2048}, {&m->G[0], B * 64 * 258 * 128},
+        {&m->G[1], B * 64 * 258 * 128}, {&m->GO[0], B * 8 * 258 * 32},  {&m->GO[1], B * 4 * 130 * 64},
+        {&m->GO[2], B * 2 * 66 * 128},  {&m->GO[3], B * 1 * 34 * 256},  {&m->SEQ, 256 * B * 1024},
+        {&m->XP, (256 * B * 4096 > (size_t)4096 * 1024) ? 256 * B * 4096 : (size_t)4096 * 1024},       {&m->R1, 256 * B * 1024},       {&m->R2, 256 * B * 1024},
+        {&m->x_in, B * 3 * 512 * 1024}, {&m->bon_out, B * 2 * 1024},    {&m->cor_out, B * 1024},
+        {&m->head_w, 12 * 1024},        {&m->head_b, 12},
+    };
+    for (auto& b : bufs)
+        if (m->alloc_t(b.p, b.n)) return -1;
+    if (m->alloc_t(&m->counters, 4)) return -1;
+    if (m->alloc_t(&m->error_flag, 1)) return -1;
+    HN_CUDA_OK(cudaMemset(m->error_flag, 0, sizeof(int)));
+    *out = m.release();
+    return 0;
+}
+
+int hn_model_num_tensors(const hn_model* m) { return m ? (int)m->slots.size() : 0; }
+
+int hn_model_tensor_info(const hn_model* m, int i, const char** key, long long* numel) {
+    HN_CHECK(m && i >= 0 && i < (int)m->slots.size(), "hn_model_tensor_info: bad index");
+    if (key) *key = m->slots[i].key.c_str();
+    if (numel) *numel = m->slots[i].numel;
+    return 0;
+}
+
+int hn_model_set_tensor(hn_model* m, const char* key, const float* data, long long numel, int on_device) {
+    HN_CHECK(m && key, "hn_model_set_tensor: NULL argument");
+    auto it = m->index.find(key);
+    if (it == m->index.end()) return fail(std::string("hn_model_set_tensor: unexpected key '") + key + "'");
+    TensorSlot& s = m->slots[it->second];
+    if (s.ignored) { s.set = true; return 0; }
+    HN_CHECK(data != nullptr, "hn_model_set_tensor: data is NULL");
+    if (numel != s.numel)
+        return fail(std::string("hn_model_set_tensor: size mismatch for '") + key + "': got " + std::to_string(numel) +
+                    ", expected " + std::to_string(s.numel));
+    HN_CUDA_OK(cudaSetDevice(m->device));
+    HN_CUDA_OK(cudaMemcpy(s.dev, data, (size_t)numel * sizeof(float),
+                          on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+    s.set = true;
+    m->finalized = false;
+    return 0;
+}
+
+int hn_model_set_option(hn_model* m, const char* name, int value) {
+    HN_CHECK(m && name, "hn_model_set_option: NULL argument");
+    if (std::strcmp(name, "tensor_cores") == 0) { m->use_tc = value; return 0; }
+    return fail(std::string("hn_model_set_option: unknown option '") + name + "'");
+}
+
+int hn_model_finalize(hn_model* m) {
+    HN_CHECK(m, "hn_model_finalize: NULL model");
+    for (auto& s : m->slots)
+        if (!s.set && !s.ignored) return fail("hn_model_finalize: missing key '" + s.key + "' (strict load, utils.py:64)");
+    HN_CUDA_OK(cudaSetDevice(m->device));
+    cudaStream_t st = 0;
+    if (pack_conv(m, m->stem, st)) return -1;
+    for (int l = 0; l < 4; ++l)
+        for (auto& b : m->blocks[l]) {
+            if (pack_conv(m, b.c1, st) || pack_conv(m, b.c2, st) || pack_conv(m, b.c3, st)) return -1;
+            if (b.has_ds && pack_conv(m, b.ds, st)) return -1;
+        }
+    for (int s = 0; s < 4; ++s)
+        for (int j = 0; j < 4; ++j)
+            if (pack_conv(m, m->ghc[s][j], st)) return -1;
+    for (int layer = 0; layer < 2; ++layer) {
+        ConvLayer& c = m->xproj[layer];
+        if (!c.w) {
+            if (m->alloc_t(&c.w, (size_t)4096 * 1024) || m->alloc_t(&c.scale, 4096) || m->alloc_t(&c.shift, 4096)) return -1;
+        }
+        const std::string l = "_l" + std::to_string(layer);
+        // [4096][1024] (fwd rows then reverse rows) -> [K=1024][N=4096]
+        for (int dir = 0; dir < 2; ++dir) {
+            const float* w = m->T("bi_rnn.weight_ih" + l + (dir ? "_reverse" : ""));
+            HN_CUDA_OK(cudaMemcpyAsync(m->XP + (size_t)dir * 2048 * 1024, w, (size_t)2048 * 1024 * sizeof(float),
+                                       cudaMemcpyDeviceToDevice, st));
+            m->whh[layer][dir] = m->T("bi_rnn.weight_hh" + l + (dir ? "_reverse" : ""));
+        }
+        pack_oihw_kernel<<<(4096 * 1024 + 255) / 256, 256, 0, st>>>(m->XP, c.w, 4096, 1024, 1, 1);
+        HN_LAUNCH_OK();
+        lstm_bias_kernel<<<16, 256, 0, st>>>(m->T("bi_rnn.bias_ih" + l), m->T("bi_rnn.bias_hh" + l),
+                                             m->T("bi_rnn.bias_ih" + l + "_reverse"),
+                                             m->T("bi_rnn.bias_hh" + l + "_reverse"), c.scale, c.shift);
+        HN_LAUNCH_OK();
+        c.d.w = c.w; c.d.scale = c.scale; c.d.shift = c.shift;
+    }
+    HN_CUDA_OK(cudaMemcpyAsync(m->head_w, m->T("linear.weight"), 12 * 1024 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    HN_CUDA_OK(cudaMemcpyAsync(m->head_b, m->T("linear.bias"), 12 * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    HN_CUDA_OK(cudaStreamSynchronize(st));
+    m->finalized = true;
+    return 0;
+}
+
+int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float* bon, float* cor, void* stream) {
+    HN_CHECK(m && x && bon && cor, "hn_model_forward: NULL argument");
+    HN_CHECK(m->finalized, "hn_model_forward: call hn_model_finalize after setting all tensors");
+    HN_CHECK(B >= 1 && B <= m->max_batch, "hn_model_forward: batch exceeds max_batch given at create");
+    HN_CUDA_OK(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    m->last_batch = B;
+
+    // model.py:248-252 + :73-76: normalise, stem conv/BN/ReLU, max-pool
+    Act s0 = mk(m->S0, B, 256, 512, 64);
+    if (stem_f32(x, B, in_channels, m->stem.w, m->stem.scale, m->stem.shift, s0, st)) return -1;
+    Act cur = mk(m->S1, B, 128, 256, 64);
+    if (maxpool3x3s2(s0, cur, st)) return -1;
+
+    // model.py:78-81: layer1..layer4 (torchvision Bottleneck v1.5)
+    Act feats[4];
+    for (int l = 0; l < 4; ++l) {
+        const int nb = (int)m->blocks[l].size();
+        for (int b = 0; b < nb; ++b) {
+            const hn_model::Block& blk = m->blocks[l][b];
+            const int s = blk.c2.d.sh;
+            const int Ho = cur.H / s, Wo = cur.W / s;
+            Act t1 = mk(m->T1, B, cur.H, cur.W, blk.c1.d.Cout);
+            Act t2 = mk(m->T2, B, Ho, Wo, blk.c2.d.Cout);
+            Act y = mk(b == nb - 1 ? m->F[l] : m->X[b & 1], B, Ho, Wo, blk.c3.d.Cout);
+            if (run_conv(m, blk.c1, cur, t1, nullptr, st)) return -1;
+            if (run_conv(m, blk.c2, t1, t2, nullptr, st)) return -1;
+            const float* idn = cur.p;
+            if (blk.has_ds) {
+                Act d = mk(m->IDN, B, Ho, Wo, blk.ds.d.Cout);
+                if (run_conv(m, blk.ds, cur, d, nullptr, st)) return -1;
+                idn = d.p;
+            }
+            if (run_conv(m, blk.c3, t2, y, idn, st)) return -1;      // + identity, ReLU
+            cur = y;
+        }
+        feats[l] = cur;
+    }
+
+    // model.py:148-151: 4 x (3x3 stride (2,1) conv + bias + BN + ReLU) per scale
+    Act gout[4];
+    for (int s = 0; s < 4; ++s) {
+        Act g = feats[s];
+        for (int j = 0; j < 4; ++j) {
+            const ConvLayer& c = m->ghc[s][j];
+            Act o = mk(j == 3 ? m->GO[s] : m->G[j & 1], B, g.H / 2, g.W, c.d.Cout);
+            if (run_conv(m, c, g, o, nullptr, st)) return -1;
+            g = o;
+        }
+        gout[s] = g;
+    }
+    // model.py:152-155 + :175-178 + :263 -> [T=256][B][1024]
+    if (ghc_to_sequence(gout, m->SEQ, st)) return -1;
+
+    // model.py:264: 2-layer bidirectional LSTM (eval: dropout = identity)
+    const float* lin = m->SEQ;
+    float* louts[2] = {m->R1, m->R2};
+    for (int layer = 0; layer < 2; ++layer) {
+        Act a = mk(const_cast<float*>(lin), 1, 1, 256 * B, 1024, 0);
+        Act xp = mk(m->XP, 1, 1, 256 * B, 4096, 0);
+        if (run_conv(m, m->xproj[layer], a, xp, nullptr, st)) return -1;
+        if (lstm_layer(m->XP, m->whh[layer][0], m->whh[layer][1], louts[layer], 256, B, m->counters, m->error_flag, st))
+            return -1;
+        lin = louts[layer];
+    }
+    // model.py:265-281: dropout (id), linear, reshape, split
+    if (linear_head(m->R2, m->head_w, m->head_b, bon, cor, 256, B, st)) return -1;
+    return 0;
+}
+
+int hn_model_check(hn_model* m) {
+    // surfaces device-side failures (LSTM spin timeout) after a synchronisation point
+    HN_CHECK(m, "hn_model_check: NULL model");
+    int flag = 0;
+    HN_CUDA_OK(cudaMemcpy(&flag, m->error_flag, sizeof(int), cudaMemcpyDeviceToHost));
+    if (flag) {
+        cudaMemset(m->error_flag, 0, sizeof(int));
+        return fail("hn_model: the persistent LSTM kernel timed out waiting for a peer CTA");
+    }
+    return 0;
+}
+
+int hn_model_forward_host(hn_model* m, const float* x, int B, int in_channels, float* bon, float* cor) {
+    HN_CHECK(m && x && bon && cor, "hn_model_forward_host: NULL argument");
+    HN_CHECK(B >= 1 && B <= m->max_batch, "hn_model_forward_host: batch exceeds max_batch");
+    HN_CHECK(in_channels >= 3, "hn_model_forward_host: need >= 3 channels");
+    HN_CUDA_OK(cudaSetDevice(m->device));
+    cudaStream_t st = 0;
+    // only the first 3 channels are used (model.py:252): copy them image by image
+    for (int b = 0; b < B; ++b)
+        HN_CUDA_OK(cudaMemcpyAsync(m->x_in + (size_t)b * 3 * 512 * 1024, x + (size_t)b * in_channels * 512 * 1024,
+                                   (size_t)3 * 512 * 1024 * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (hn_model_forward(m, m->x_in, B, 3, m->bon_out, m->cor_out, st)) return -1;
+    HN_CUDA_OK(cudaMemcpyAsync(bon, m->bon_out, (size_t)B * 2 * 1024 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HN_CUDA_OK(cudaMemcpyAsync(cor, m->cor_out, (size_t)B * 1024 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HN_CUDA_OK(cudaStreamSynchronize(st));
+    return hn_model_check(m);
+}
+
+int hn_model_stage(hn_model* m, const char* stage, float* out, long long capacity, int dims[4], void* stream) {
+    HN_CHECK(m && stage && out && dims, "hn_model_stage: NULL argument");
+    HN_CHECK(m->last_batch > 0, "hn_model_stage: no forward has run yet");
+    HN_CUDA_OK(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int B = m->last_batch;
+    const std::string s(stage);
+    for (int l = 0; l < 4; ++l)
+        if (s == "layer" + std::to_string(l + 1)) {
+            const int C = 256 << l, H = 128 >> l, W = 256 >> l;
+            const size_t total = (size_t)B * C * H * W;
+            HN_CHECK((long long)total <= capacity, "hn_model_stage: output buffer too small");
+            nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m->F[l], out, B, H, W, C, 1);
+            HN_LAUNCH_OK();
+            dims[0] = B; dims[1] = C; dims[2] = H; dims[3] = W;
+            return 0;
+        }
+    const size_t total = (size_t)256 * B * 1024;
+    HN_CHECK((long long)total <= capacity, "hn_model_stage: output buffer too small");
+    if (s == "feature") {
+        seq_to_feature_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m->SEQ, out, 256, B);
+        HN_LAUNCH_OK();
+        dims[0] = B; dims[1] = 1024; dims[2] = 256; dims[3] = 0;
+        return 0;
+    }
+    if (s == "rnn_out") {
+        HN_CUDA_OK(cudaMemcpyAsync(out, m->R2, total * sizeof(float), cudaMemcpyDeviceToDevice, st));
+        dims[0] = 256; dims[1] = B; dims[2] = 1024; dims[3] = 0;
+        return 0;
+    }
+    return fail("hn_model_stage: unknown stage '" + s + "'");
+}
+
+void hn_model_destroy(hn_model* m) { delete m; }
+
+// ---- pano_stretch ------------------------------------------------------------------------------
+int hn_pano_stretch(const float* img, float* out, int n, int h, int w, int c, const double* kx, const double* ky,
+                    int order, void* stream) {
+    HN_CHECK(img && out && kx && ky, "hn_pano_stretch: NULL argument");
+    HN_CHECK(n >= 0 && h >= 1 && w >= 1, "hn_pano_stretch: bad geometry");
+    if (n == 0) return 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("hn_pano_stretch: no CUDA device -- libhorizonnet_b200 has no CPU path");
+    for (int i = 0; i < n; ++i) HN_CHECK(kx[i] > 0 && ky[i] > 0, "hn_pano_stretch: kx, ky must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    double* scratch = nullptr;
+    const size_t nd = (size_t)2 * n + (size_t)2 * n * w + h;
+    HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&scratch), nd * sizeof(double), st));
+    HN_CUDA_OK(cudaMemcpyAsync(scratch, kx, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    HN_CUDA_OK(cudaMemcpyAsync(scratch + n, ky, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    int rc = pano_stretch_device(img, out, n, h, w, c, scratch, scratch + n, scratch + 2 * (size_t)n, order, st);
+    cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+int hn_pano_stretch_host(const float* img, float* out, int n, int h, int w, int c, const double* kx,
+                         const double* ky, int order) {
+    HN_CHECK(img && out && kx && ky, "hn_pano_stretch_host: NULL argument");
+    if (n == 0) return 0;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("hn_pano_stretch_host: no CUDA device -- libhorizonnet_b200 has no CPU path");
+    const size_t bytes = (size_t)n * h * w * c * sizeof(float);
+    float *d_in = nullptr, *d_out = nullptr;
+    HN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d_in), bytes));
+    if (cudaMalloc(reinterpret_cast<void**>(&d_out), bytes) != cudaSuccess) { cudaFree(d_in); return fail("hn_pano_stretch_host: out of memory"); }
+    int rc = 0;
+    if (cudaMemcpy(d_in, img, bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail("hn_pano_stretch_host: H2D failed");
+    if (!rc) rc = hn_pano_stretch(d_in, d_out, n, h, w, c, kx, ky, order, nullptr);
+    if (!rc && cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("hn_pano_stretch_host: D2H failed");
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}
+
+// ---- kernel-level entry points -----------------------------------------------------------------
+int hn_conv2d(const float* in, int B, int H, int W, int Cin, int in_halo, const float* w, const float* scale,
+              const float* shift, const float* residual, int Cout, int kh, int kw, int sh, int sw, int ph, int pw,
+              int relu, float* out, int out_halo, int impl, void* stream) {
+    HN_CHECK(in && w && scale && shift && out, "hn_conv2d: NULL argument");
+    ConvDesc d;
+    d.Cin = Cin; d.Cout = Cout; d.kh = kh; d.kw = kw; d.sh = sh; d.sw = sw; d.ph = ph; d.pw = pw; d.relu = relu;
+    d.w = w; d.scale = scale; d.shift = shift;
+    Act a = mk(const_cast<float*>(in), B, H, W, Cin, in_halo);
+    const int Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
+    Act o = mk(out, B, Ho, Wo, Cout, out_halo);
+    if (impl == 1) {
+        if (!conv_tc_supported(d, a, o)) return fail("hn_conv2d: shape not supported by the tcgen05 kernel");
+        return conv_tc(d, a, o, residual, (cudaStream_t)stream);
+    }
+    return conv_f32(d, a, o, residual, (cudaStream_t)stream);
+}
+
+int hn_lstm_layer(const float* xproj, const float* whf, const float* whb, float* out, int T, int B, void* stream) {
+    HN_CHECK(xproj && whf && whb && out && T >= 1 && B >= 1, "hn_lstm_layer: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    unsigned int* ctr = nullptr;
+    HN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ctr), 4 * sizeof(unsigned int)));
+    int* flag = reinterpret_cast<int*>(ctr + 2);
+    cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), st);
+    int rc = lstm_layer(xproj, whf, whb, out, T, B, ctr, flag, st);
+    int h = 0;
+    if (!rc) {
+        if (cudaStreamSynchronize(st) != cudaSuccess) rc = fail("hn_lstm_layer: kernel failed");
+        else {
+            cudaMemcpy(&h, flag, sizeof(int), cudaMemcpyDeviceToHost);
+            if (h) rc = fail("hn_lstm_layer: persistent kernel timed out waiting for a peer CTA");
+        }
+    }
+    cudaFree(ctr);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,257 @@
+"""Drop-in ``HorizonNet`` (reference model.py:185-281) backed by libhorizonnet_b200 (sm_100a CUDA).
+
+Boundary kept from the reference:
+  * ``HorizonNet(backbone, use_rnn)`` is an ``nn.Module`` whose parameters/buffers carry exactly
+    the reference's 448 ``state_dict`` keys, so ``misc/utils.py:49-65`` (``save_model`` /
+    ``load_trained_model``) work unchanged with this class;
+  * ``forward(x[B, C>=3, 512, 1024]) -> (bon[B,2,1024], cor[B,1,1024])`` raw fp32 outputs,
+    ``NotImplementedError`` for any other H x W (model.py:255-256);
+  * ``.backbone``, ``.use_rnn``, ``.feature_extractor.list_blocks()``, ``.x_mean``, ``.x_std``.
+Only the path BASELINE.json names is built: ``backbone='resnet50'``, ``use_rnn=True``, inference
+(eval) forward.  The modules below are parameter containers with the reference's names; none of
+their torch ``forward`` methods is ever called -- all arithmetic runs in the CUDA library, and there
+is no CPU fallback: a CPU tensor or a missing library raises.
+"""
+import ctypes
+import threading
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._spec import HEAD_BIAS, RNN_HIDDEN, STEP_COLS, PANO_H, PANO_W, state_dict_spec
+
+
+class CircularPadW(nn.Module):
+    """Index-0 placeholder of the ``Sequential(LR_PAD, conv)`` pairs the reference creates in
+    wrap_lr_pad (model.py:42-55); it is why wrapped convs are keyed ``...conv2.1.weight``.  The
+    circular padding itself is realised by the halo columns of the device activation layout."""
+
+    def __init__(self, padding):
+        super().__init__()
+        self.padding = padding
+
+    def forward(self, x):
+        raise RuntimeError('horizonnet_b200 modules are parameter containers; call HorizonNet.forward')
+
+
+def _wrapped_conv(cin, cout, k, stride, bias):
+    return nn.Sequential(CircularPadW(k // 2),
+                         nn.Conv2d(cin, cout, k, stride=stride, padding=(k // 2, 0), bias=bias))
+
+
+class _Bottleneck(nn.Module):
+    def __init__(self, inplanes, planes, stride, downsample):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, 1, bias=False)
+        self.bn1 = nn.BatchNorm2d(planes)
+        self.conv2 = _wrapped_conv(planes, planes, 3, stride, False)
+        self.bn2 = nn.BatchNorm2d(planes)
+        self.conv3 = nn.Conv2d(planes, planes * 4, 1, bias=False)
+        self.bn3 = nn.BatchNorm2d(planes * 4)
+        self.relu = nn.ReLU(inplace=True)
+        if downsample:
+            self.downsample = nn.Sequential(nn.Conv2d(inplanes, planes * 4, 1, stride=stride, bias=False),
+                                            nn.BatchNorm2d(planes * 4))
+
+
+class _ResNet50(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv1 = _wrapped_conv(3, 64, 7, 2, False)
+        self.bn1 = nn.BatchNorm2d(64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(3, 2, 1)
+        inplanes = 64
+        for li, (nblk, planes) in enumerate(zip((3, 4, 6, 3), (64, 128, 256, 512)), start=1):
+            blocks = []
+            for b in range(nblk):
+                blocks.append(_Bottleneck(inplanes, planes, 2 if (b == 0 and li > 1) else 1, b == 0))
+                inplanes = planes * 4
+            setattr(self, f'layer{li}', nn.Sequential(*blocks))
+        for m in self.modules():            # torchvision resnet.py:208-213 initialisation
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode='fan_out', nonlinearity='relu')
+
+
+class _Encoder(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.encoder = _ResNet50()
+
+    def list_blocks(self):
+        """Same grouping as reference model.py:84-91 (used by train.py --freeze_earlier_blocks)."""
+        lst = list(self.encoder.children())
+        return lst[:4], lst[4:5], lst[5:6], lst[6:7], lst[7:8]
+
+
+class _CompressH(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.layers = nn.Sequential(_wrapped_conv(cin, cout, 3, (2, 1), True), nn.BatchNorm2d(cout),
+                                    nn.ReLU(inplace=True))
+
+
+class _HeightConv(nn.Module):
+    def __init__(self, cin, cout):
+        super().__init__()
+        self.layer = nn.Sequential(_CompressH(cin, cin // 2), _CompressH(cin // 2, cin // 2),
+                                   _CompressH(cin // 2, cin // 4), _CompressH(cin // 4, cout))
+
+
+class _HeightStage(nn.Module):
+    def __init__(self, cs, out_scale):
+        super().__init__()
+        self.cs = cs
+        self.out_scale = out_scale
+        self.ghc_lst = nn.ModuleList([_HeightConv(c, c // out_scale) for c in cs])
+
+
+class HorizonNet(nn.Module):
+    x_mean = torch.FloatTensor(np.array([0.485, 0.456, 0.406])[None, :, None, None])
+    x_std = torch.FloatTensor(np.array([0.229, 0.224, 0.225])[None, :, None, None])
+
+    def __init__(self, backbone, use_rnn):
+        super().__init__()
+        if backbone != 'resnet50' or not use_rnn:
+            raise NotImplementedError(
+                "horizonnet_b200 implements the BASELINE path only: HorizonNet('resnet50', use_rnn=True)")
+        self.backbone = backbone
+        self.use_rnn = use_rnn
+        self.out_scale = 8
+        self.step_cols = STEP_COLS
+        self.rnn_hidden_size = RNN_HIDDEN
+        self.feature_extractor = _Encoder()
+        self.reduce_height_module = _HeightStage((256, 512, 1024, 2048), self.out_scale)
+        self.bi_rnn = nn.LSTM(input_size=1024, hidden_size=RNN_HIDDEN, num_layers=2, dropout=0.5,
+                              batch_first=False, bidirectional=True)
+        self.drop_out = nn.Dropout(0.5)
+        self.linear = nn.Linear(2 * RNN_HIDDEN, 3 * STEP_COLS)
+        with torch.no_grad():
+            self.linear.bias.copy_(torch.tensor(HEAD_BIAS))          # model.py:231-233
+        # bypass nn.Module.__setattr__: runtime state must not become sub-modules / parameters
+        object.__setattr__(self, '_handles', {})
+        object.__setattr__(self, '_lock', threading.Lock())
+        object.__setattr__(self, '_tensor_cores', 1)
+        self._slots = None
+
+    # ---- weights -> device library --------------------------------------------------------------
+    def _state_tensors(self):
+        if self._slots is None:
+            slots = []
+            spec = state_dict_spec()
+            for key in spec:
+                *path, leaf = key.split('.')
+                mod = self
+                for p in path:
+                    mod = getattr(mod, p)
+                slots.append((key, mod, leaf))
+            self._slots = slots
+        for key, mod, leaf in self._slots:
+            t = mod._parameters.get(leaf)
+            if t is None:
+                t = mod._buffers[leaf]
+            yield key, t
+
+    def use_tensor_cores(self, enabled=True):
+        """True (default): split-bf16 tcgen05 kernels where supported; False: exact fp32 kernels."""
+        object.__setattr__(self, '_tensor_cores', 1 if enabled else 0)
+        for h in self._handles.values():
+            h['sig'] = None
+        return self
+
+    def _handle(self, device, batch):
+        lib = _lib.lib()
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        with self._lock:
+            h = self._handles.get(key)
+            if h is not None and h['max_batch'] < batch:
+                lib.hn_model_destroy(h['ptr'])
+                h = None
+            if h is None:
+                ptr = ctypes.c_void_p()
+                max_batch = max(batch, 1)
+                _lib.check(lib.hn_model_create(key, max_batch, ctypes.byref(ptr)), 'hn_model_create')
+                h = {'ptr': ptr, 'max_batch': max_batch, 'sig': None}
+                self._handles[key] = h
+            tensors = list(self._state_tensors())
+            sig = tuple((t.data_ptr(), t._version) for _, t in tensors) + (self._tensor_cores,)
+            if h['sig'] != sig:
+                for k, t in tensors:
+                    if not t.is_floating_point():
+                        _lib.check(lib.hn_model_set_tensor(h['ptr'], k.encode(), None, 1, 1), k)
+                        continue
+                    d = t.detach().to(device=device, dtype=torch.float32).contiguous()
+                    _lib.check(lib.hn_model_set_tensor(h['ptr'], k.encode(), d.data_ptr(), d.numel(), 1), k)
+                _lib.check(lib.hn_model_set_option(h['ptr'], b'tensor_cores', self._tensor_cores), 'set_option')
+                _lib.check(lib.hn_model_finalize(h['ptr']), 'hn_model_finalize')
+                h['sig'] = sig
+        return h
+
+    def _prepare_x(self, x):          # kept for API parity (model.py:248-252); fused into the stem kernel
+        raise RuntimeError('input normalisation is fused into the stem kernel; call forward()')
+
+    def forward(self, x):
+        if x.shape[2] != PANO_H or x.shape[3] != PANO_W:
+            raise NotImplementedError()                                   # model.py:255-256
+        if not x.is_cuda:
+            raise RuntimeError('horizonnet_b200.HorizonNet has no CPU path: move the input to a B200 (cuda) device')
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError('horizonnet_b200 implements the inference forward (eval / no_grad) only')
+        if x.shape[1] < 3:
+            raise RuntimeError('input needs at least 3 channels (model.py:252 reads x[:, :3])')
+        x = x.detach().to(torch.float32).contiguous()
+        B, C = x.shape[0], x.shape[1]
+        h = self._handle(x.device, B)
+        bon = torch.empty(B, 2, PANO_W, device=x.device, dtype=torch.float32)
+        cor = torch.empty(B, 1, PANO_W, device=x.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(_lib.lib().hn_model_forward(h['ptr'], x.data_ptr(), B, C, bon.data_ptr(), cor.data_ptr(), stream),
+                   'hn_model_forward')
+        return bon, cor
+
+    def forward_host(self, x_host, device=0):
+        """End-to-end call on HOST arrays through the C ABI (H2D + forward + D2H inside the
+        library): the equivalent of inference.py:78-79.  x_host: contiguous fp32 [B,C,512,1024]
+        numpy array or CPU tensor (pinned memory makes the copies asynchronous-capable)."""
+        xt = torch.as_tensor(x_host)
+        if xt.is_cuda or xt.dtype != torch.float32 or not xt.is_contiguous():
+            raise RuntimeError('forward_host expects a contiguous fp32 host array')
+        if xt.shape[2] != PANO_H or xt.shape[3] != PANO_W:
+            raise NotImplementedError()
+        B, C = xt.shape[0], xt.shape[1]
+        dev = torch.device('cuda', device)
+        h = self._handle(dev, B)
+        bon = torch.empty(B, 2, PANO_W, dtype=torch.float32)
+        cor = torch.empty(B, 1, PANO_W, dtype=torch.float32)
+        _lib.check(_lib.lib().hn_model_forward_host(h['ptr'], xt.data_ptr(), B, C, bon.data_ptr(), cor.data_ptr()),
+                   'hn_model_forward_host')
+        return bon, cor
+
+    def debug_stage(self, name, device=None):
+        """Intermediate result of the last forward in the reference's layout (test hook)."""
+        lib = _lib.lib()
+        key = next(iter(self._handles)) if device is None else device
+        h = self._handles[key]
+        dev = torch.device('cuda', key)
+        dims = (ctypes.c_int * 4)()
+        cap = h['max_batch'] * 256 * 128 * 256
+        out = torch.empty(cap, device=dev, dtype=torch.float32)
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        _lib.check(lib.hn_model_stage(h['ptr'], name.encode(), out.data_ptr(), cap, dims, stream), 'hn_model_stage')
+        shape = [d for d in dims if d > 0]
+        return out[:int(np.prod(shape))].view(*shape)
+
+    def check(self):
+        """Synchronise and raise if an asynchronous forward failed on the device."""
+        for h in self._handles.values():
+            _lib.check(_lib.lib().hn_model_check(h['ptr']), 'hn_model_check')
+
+    def __del__(self):
+        try:
+            for h in self._handles.values():
+                _lib.lib().hn_model_destroy(h['ptr'])
+            self._handles.clear()
+        except Exception:
+            pass

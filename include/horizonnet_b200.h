@@ -1,0 +1,114 @@
+/* libhorizonnet_b200 -- C ABI of the B200-native HorizonNet hot path.
+ *
+ * The reference (sunset1995/HorizonNet @ c9a7df9) is pure Python and has no FFI of its own, so this
+ * ABI sits *beneath* the two Python entry points it keeps drop-in compatible:
+ *
+ *   model.HorizonNet('resnet50', use_rnn=True).forward(x)        reference model.py:254-281
+ *   misc.panostretch.pano_stretch(img, corners, kx, ky, order)   reference misc/panostretch.py:81-117
+ *
+ * Conventions: plain pointers and sizes only (no torch types); the caller owns every buffer;
+ * device entry points are asynchronous on the CUstream/cudaStream_t passed as `void* stream`
+ * (NULL = legacy default stream); every function returns 0 on success and a negative value on
+ * failure, with the message available from hn_last_error() (thread-local).  A handle is bound to
+ * one device and is not thread-safe; use one handle per replica (reference train.py:190-192
+ * replicates the module per device).  There is no CPU path: without a CUDA device every compute
+ * entry point fails.
+ */
+#ifndef HORIZONNET_B200_H
+#define HORIZONNET_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct hn_model hn_model;
+
+/* Last error message of the calling thread ("" if none). */
+const char* hn_last_error(void);
+/* ABI version (bumped on any signature change). */
+int hn_abi_version(void);
+/* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
+long long hn_kernel_launches(void);
+
+/* ---- model.HorizonNet (reference model.py:185-281), resnet50 + bi-LSTM head only ------------- */
+
+/* Creates the model on CUDA device `device`, with activation workspace for up to `max_batch`
+ * panoramas per forward.  Replaces HorizonNet.__init__ (model.py:189-246) minus the ImageNet
+ * download. */
+int hn_model_create(int device, int max_batch, hn_model** out);
+
+/* Number of tensors of the reference checkpoint layout (448, misc/utils.py:49-58) and the i-th key
+ * with its element count; lets a binding iterate the state_dict without knowing the topology. */
+int hn_model_num_tensors(const hn_model* m);
+int hn_model_tensor_info(const hn_model* m, int index, const char** key, long long* numel);
+
+/* Uploads one fp32 tensor of the reference state_dict (same key names and PyTorch layouts:
+ * conv OIHW, LSTM [4H, in], linear [out, in]).  `data` may be a host (on_device=0) or a device
+ * pointer (on_device=1).  `*.num_batches_tracked` keys are accepted and ignored.
+ * Replaces nn.Module.load_state_dict for this module (misc/utils.py:64). */
+int hn_model_set_tensor(hn_model* m, const char* key, const float* data, long long numel, int on_device);
+
+/* Folds eval-mode BN / conv bias and re-packs all weights into the kernels' layouts.  Fails if a
+ * tensor was never set.  Must be called after the last hn_model_set_tensor and before forward. */
+int hn_model_finalize(hn_model* m);
+
+/* HorizonNet.forward (model.py:254-281), eval mode.  x: [batch][in_channels >= 3][512][1024] fp32
+ * NCHW in [0,1] on the device (only the first 3 channels are read, model.py:252);
+ * bon: [batch][2][1024], cor: [batch][1][1024] fp32 on the device (raw: cor is a logit). */
+int hn_model_forward(hn_model* m, const float* x_nchw_dev, int batch, int in_channels,
+                     float* bon_dev, float* cor_dev, void* stream);
+
+/* Same call with HOST buffers: H2D of x, forward, D2H of bon/cor, synchronous.  This is what
+ * inference.py:78-79 (`net(x.to(device))` + `.cpu()`) amounts to. */
+int hn_model_forward_host(hn_model* m, const float* x_nchw_host, int batch, int in_channels,
+                          float* bon_host, float* cor_host);
+
+/* Test hook: copies an intermediate result of the LAST forward, converted to the reference's
+ * layout, into `out_dev` (fp32).  Stages: "layer1".."layer4" (NCHW [B,C,H,W], model.py:78-81),
+ * "feature" ([B,1024,256], model.py:175-178), "rnn_out" ([256,B,1024], model.py:264).
+ * dims receives the 4 (or 3, last = 0) extents. */
+int hn_model_stage(hn_model* m, const char* stage, float* out_dev, long long capacity, int dims[4],
+                   void* stream);
+
+/* Options: "tensor_cores" = 1 routes every conv / projection GEMM the tcgen05 kernel supports
+ * through the split-bf16 tensor-core path (default), 0 = exact fp32 CUDA-core kernels everywhere. */
+int hn_model_set_option(hn_model* m, const char* name, int value);
+
+/* Synchronises the device and reports device-side failures recorded by earlier asynchronous
+ * forwards (e.g. the persistent LSTM kernel's peer-wait timeout). */
+int hn_model_check(hn_model* m);
+
+void hn_model_destroy(hn_model* m);
+
+/* ---- misc.panostretch.pano_stretch, image part (reference misc/panostretch.py:81-102) -------- */
+
+/* n images [h][w][c] fp32 (HWC, c in 1..4) on the device, one (kx[i], ky[i]) pair per image
+ * (host arrays of n doubles); order 0 (nearest) or 1 (bilinear); scipy legacy 'wrap' semantics. */
+int hn_pano_stretch(const float* img_dev, float* out_dev, int n, int h, int w, int c,
+                    const double* kx_host, const double* ky_host, int order, void* stream);
+/* Same with host images (H2D + kernel + D2H inside), i.e. the numpy-in / numpy-out call of
+ * dataset.py:82. */
+int hn_pano_stretch_host(const float* img_host, float* out_host, int n, int h, int w, int c,
+                         const double* kx_host, const double* ky_host, int order);
+
+/* ---- kernel-level entry points (unit tests; halo-NHWC activations) ------------ */
+
+/* One convolution + folded BN/bias + optional residual + optional ReLU.
+ * in:  [B][H][W + 2*in_halo][Cin]   out: [B][Ho][Wo + 2*out_halo][Cout]   (fp32, device)
+ * w_packed: [kh*kw*Cin][Cout], k = (dy*kw + dx)*Cin + c;  scale/shift: [Cout];
+ * ph = zero padding along H, pw = circular padding along W (<= in_halo).
+ * impl: 0 = exact fp32 CUDA-core kernel, 1 = split-bf16 tcgen05 tensor-core kernel. */
+int hn_conv2d(const float* in_dev, int B, int H, int W, int Cin, int in_halo,
+              const float* w_packed_dev, const float* scale_dev, const float* shift_dev,
+              const float* residual_dev, int Cout, int kh, int kw, int sh, int sw, int ph, int pw,
+              int relu, float* out_dev, int out_halo, int impl, void* stream);
+
+/* One bidirectional LSTM layer recurrence: xproj [T][B][4096] (input projection + both biases,
+ * column = dir*2048 + gate*512 + unit), w_hh_* [2048][512] (PyTorch layout), out [T][B][1024]. */
+int hn_lstm_layer(const float* xproj_dev, const float* w_hh_fwd_dev, const float* w_hh_bwd_dev,
+                  float* out_dev, int T, int B, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HORIZONNET_B200_H */

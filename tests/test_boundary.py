@@ -1,0 +1,91 @@
+"""CPU: the drop-in boundary -- C ABI exports, checkpoint layout, loud failure without a GPU."""
+import ctypes
+import io
+import os
+import re
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+import torch
+
+import __graft_entry__ as entry
+from horizonnet_b200 import _lib
+from horizonnet_b200.model import HorizonNet
+from horizonnet_b200.weights import synthetic_state_dict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    entry.build()
+    return _lib.lib()
+
+
+def test_library_exports_every_symbol_of_the_header(lib):
+    header = open(os.path.join(ROOT, 'include', 'horizonnet_b200.h')).read()
+    declared = set(re.findall(r'\b(hn_[a-z0-9_]+)\s*\(', header))
+    assert declared, 'no declarations found'
+    for name in declared:
+        assert hasattr(lib, name), f'{name} declared in include/horizonnet_b200.h but not exported'
+    assert declared == set(_lib.SIGNATURES), 'ctypes signature table out of sync with the header'
+
+
+def test_checkpoint_layout_round_trip():
+    """reference misc/utils.py:49-65 save_model/load_trained_model, restated, on our class."""
+    sd = synthetic_state_dict(3, 'random')
+    net = HorizonNet('resnet50', True)
+    net.load_state_dict(sd, strict=True)
+    blob = io.BytesIO()
+    torch.save(OrderedDict({'args': {}, 'kwargs': {'backbone': net.backbone, 'use_rnn': net.use_rnn},
+                            'state_dict': net.state_dict()}), blob)
+    blob.seek(0)
+    ck = torch.load(blob, map_location='cpu')
+    net2 = HorizonNet(**ck['kwargs'])
+    net2.load_state_dict(ck['state_dict'])
+    assert list(net2.state_dict().keys()) == list(sd.keys())
+    for k, v in net2.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_module_surface_used_by_reference_callers():
+    net = HorizonNet('resnet50', True)
+    blocks = net.feature_extractor.list_blocks()            # train.py:202-208
+    assert len(blocks) == 5 and len(blocks[0]) == 4
+    assert sum(p.numel() for p in net.parameters()) == 81570348
+    assert any(isinstance(m, torch.nn.BatchNorm2d) for m in net.modules())     # train.py:210-213
+    assert any(isinstance(m, torch.nn.RNNBase) for m in net.modules())         # train.py:39-42
+    assert net.linear.bias.tolist() == pytest.approx([-1] * 4 + [-0.478] * 4 + [0.425] * 4)
+    with pytest.raises(NotImplementedError):
+        HorizonNet('densenet169', True)                     # out of scope, fails loudly
+
+
+def test_no_cpu_fallback():
+    net = HorizonNet('resnet50', True).eval()
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 3, 256, 512))                    # model.py:255-256
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError):
+            net(torch.zeros(1, 3, 512, 1024))
+        from horizonnet_b200.misc.panostretch import pano_stretch
+        with pytest.raises(RuntimeError):
+            pano_stretch(np.zeros((8, 16, 3), np.float32), np.zeros((1, 2)), 1.0, 1.0)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, 'horizonnet_b200')
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(('.py', '.cu', '.cuh')):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r'^\s*(from|import)\s+oracle', src, re.M), f
+                assert '/root/reference' not in src, f
+
+
+def test_missing_device_is_reported_not_hidden(lib):
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    p = ctypes.c_void_p()
+    assert lib.hn_model_create(0, 1, ctypes.byref(p)) != 0
+    assert b'no CUDA device' in lib.hn_last_error()

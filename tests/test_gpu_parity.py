@@ -1,0 +1,258 @@
+"""-m gpu: parity of the CUDA path (through the C ABI) against the CPU oracle, the committed
+golden fixtures (minted from the real reference) and size-independent properties.
+
+Tolerances: forward outputs 1e-4 max-abs (BASELINE north_star), kernel unit tests relative to the
+output scale; pano_stretch 1.2e-7 (one fp32 ulp in [0,1): 'pixel-exact to bilinear rounding')."""
+import os
+import numpy as np
+import pytest
+import torch
+
+import __graft_entry__ as entry
+from horizonnet_b200 import _lib
+from horizonnet_b200.model import HorizonNet
+from horizonnet_b200.misc.panostretch import pano_stretch, pano_stretch_batch
+from horizonnet_b200.weights import synthetic_state_dict, synthetic_panoramas
+from oracle import horizonnet_ref, panostretch_ref
+import gpu_utils as gu
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda:0'
+KGRID = (0.5, 0.75, 1.0, 1.25, 1.5, 1.75, 2.0)
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _built():
+    entry.build()
+    _lib.lib()
+
+
+def _net(sd, tensor_cores):
+    net = HorizonNet('resnet50', True).eval()
+    net.load_state_dict(sd, strict=True)
+    net.use_tensor_cores(tensor_cores)
+    return net.to(DEV)
+
+
+# ------------------------------------------------------------------------------- conv kernels
+CONV_CASES = [
+    # B, Cin, H, W, Cout, k, stride, bias/bn, residual, relu
+    (2, 64, 8, 32, 64, 1, (1, 1), False, True),
+    (1, 64, 16, 32, 256, 1, (1, 1), True, True),       # conv3 + identity + relu
+    (2, 32, 9, 32, 48, 3, (1, 1), False, True),        # odd H, Cout not a multiple of 64
+    (2, 128, 16, 64, 128, 3, (2, 2), False, True),     # stride-2 3x3 (layer2.0.conv2)
+    (1, 256, 16, 32, 512, 1, (2, 2), False, False),    # stride-2 downsample
+    (2, 64, 16, 32, 32, 3, (2, 1), False, True),       # GHC conv, stride (2,1)
+    (3, 512, 2, 32, 256, 3, (2, 1), False, True),      # H 2 -> 1
+    (1, 1024, 4, 32, 4096, 1, (1, 1), False, False),   # LSTM projection shape family
+]
+
+
+@pytest.mark.parametrize('impl', [0, 1])
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_kernel_vs_torch(case, impl):
+    B, Ci, H, W, Co, k, stride, residual, relu = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(B, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5
+    scale = torch.rand(Co, generator=g) + 0.5
+    shift = torch.randn(Co, generator=g) * 0.1
+    Ho = (H + 2 * (k // 2) - k) // stride[0] + 1
+    Wo = (W + 2 * (k // 2) - k) // stride[1] + 1
+    res = torch.randn(B, Co, Ho, Wo, generator=g) if residual else None
+    ref = gu.conv2d_reference(x, w, scale, shift, stride, k // 2, k // 2, relu, res)
+    try:
+        y, raw = gu.conv2d(x.to(DEV), w.to(DEV), scale.to(DEV), shift.to(DEV), stride, k // 2, k // 2, relu,
+                           res.to(DEV) if res is not None else None, impl=impl)
+    except RuntimeError as e:
+        if impl == 1 and 'not supported by the tcgen05 kernel' in str(e):
+            pytest.skip('shape not covered by the tensor-core kernel (fp32 kernel covers it)')
+        raise
+    tol = 2e-5 if impl == 0 else 1e-4       # fp32 exact path / split-bf16 3-product path
+    err = (y.cpu().double() - ref).abs().max().item()
+    assert err <= tol * max(1.0, ref.abs().max().item()), err
+    # halo columns must be the circular wrap of the interior
+    assert torch.equal(raw[:, :, 0], raw[:, :, -2]) and torch.equal(raw[:, :, -1], raw[:, :, 1])
+
+
+# ------------------------------------------------------------------------------- LSTM kernel
+@pytest.mark.parametrize('T,B', [(5, 1), (24, 7), (16, 32), (12, 40)])
+def test_lstm_layer_vs_oracle(T, B):
+    g = torch.Generator().manual_seed(T * 100 + B)
+    xproj = torch.randn(T, B, 4096, generator=g) * 0.5
+    whh = [torch.rand(2048, 512, generator=g) * 0.08 - 0.04 for _ in range(2)]
+    zero = torch.zeros(2048)
+    ref = []
+    for d in range(2):
+        # oracle recurrence with the projection already applied: feed identity input weights
+        xp = xproj[:, :, d * 2048:(d + 1) * 2048]
+        h = torch.zeros(B, 512); c = torch.zeros(B, 512)
+        out = torch.empty(T, B, 512)
+        for t in (range(T - 1, -1, -1) if d else range(T)):
+            gates = xp[t] + h @ whh[d].t()
+            i, f, gg, o = gates.chunk(4, dim=1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            out[t] = h
+        ref.append(out)
+    ref = torch.cat(ref, dim=2)
+    out = torch.full((T, B, 1024), float('nan'), device=DEV)
+    xd, w0, w1 = xproj.to(DEV), whh[0].to(DEV), whh[1].to(DEV)
+    rc = _lib.lib().hn_lstm_layer(xd.data_ptr(), w0.data_ptr(), w1.data_ptr(), out.data_ptr(), T, B,
+                                  torch.cuda.current_stream().cuda_stream)
+    _lib.check(rc, 'hn_lstm_layer')
+    torch.cuda.synchronize()
+    assert (out.cpu() - ref).abs().max().item() < 2e-6
+
+
+def test_lstm_layer_matches_oracle_function():
+    """The oracle's own lstm_layer_dir (incl. input projection) against GEMM-free kernel input."""
+    g = torch.Generator().manual_seed(11)
+    T, B = 9, 3
+    x = torch.randn(T, B, 64, generator=g)
+    wih = [torch.randn(2048, 64, generator=g) * 0.1 for _ in range(2)]
+    whh = [torch.randn(2048, 512, generator=g) * 0.04 for _ in range(2)]
+    bih = [torch.randn(2048, generator=g) * 0.1 for _ in range(2)]
+    bhh = [torch.randn(2048, generator=g) * 0.1 for _ in range(2)]
+    ref = torch.cat([horizonnet_ref.lstm_layer_dir(x, wih[d], whh[d], bih[d], bhh[d], bool(d)) for d in range(2)], 2)
+    xproj = torch.cat([x @ wih[d].t() + bih[d] + bhh[d] for d in range(2)], dim=2).to(DEV)
+    out = torch.empty(T, B, 1024, device=DEV)
+    w0, w1 = whh[0].to(DEV), whh[1].to(DEV)
+    _lib.check(_lib.lib().hn_lstm_layer(xproj.data_ptr(), w0.data_ptr(), w1.data_ptr(), out.data_ptr(), T, B, None),
+               'hn_lstm_layer')
+    torch.cuda.synchronize()
+    assert (out.cpu() - ref).abs().max().item() < 2e-6
+
+
+# ------------------------------------------------------------------------------- forward
+@pytest.mark.parametrize('tensor_cores', [False, True])
+@pytest.mark.parametrize('name,bn', [('identity', 'identity'), ('randombn', 'random')])
+def test_forward_matches_reference_golden(golden_dir, name, bn, tensor_cores):
+    g = np.load(os.path.join(golden_dir, f'forward_{name}.npz'))
+    sd = synthetic_state_dict(int(g['seed']), bn)
+    net = _net(sd, tensor_cores)
+    x = synthetic_panoramas(int(g['batch']), seed=int(g['x_seed']))
+    with torch.no_grad():
+        bon, cor = net(x.to(DEV))
+    bon, cor = bon.cpu().numpy(), cor.cpu().numpy()
+    net.check()
+    # per-stage samples first: they localise a failure
+    for stage in ('layer1', 'layer2', 'layer3', 'layer4', 'feature', 'rnn_out'):
+        v = net.debug_stage(stage).cpu()
+        assert tuple(v.shape) == tuple(g[stage + '_shape']), stage
+        flat = v.reshape(-1).numpy()
+        stride = max(1, flat.size // 4096)
+        got = flat[::stride][:4096]
+        scale = float(g[stage + '_maxabs'])
+        tol = (2e-5 if not tensor_cores else 2e-4) * scale + 1e-6
+        assert np.abs(got - g[stage + '_sample']).max() <= tol, stage
+    assert np.abs(bon - g['bon']).max() < 1e-4
+    assert np.abs(cor - g['cor']).max() < 1e-4
+
+
+@pytest.mark.parametrize('tensor_cores', [False, True])
+def test_forward_matches_oracle_and_is_batch_invariant(tensor_cores):
+    sd = synthetic_state_dict(7, 'random')
+    net = _net(sd, tensor_cores)
+    x = synthetic_panoramas(3, seed=21, channels=4)          # extra channel must be ignored (model.py:252)
+    with torch.no_grad():
+        bon3, cor3 = net(x.to(DEV))
+        bon1, cor1 = net(x[1:2].to(DEV))
+        rbon, rcor = horizonnet_ref.forward(sd, x[1:2])
+    net.check()
+    assert (bon1.cpu() - rbon).abs().max().item() < 1e-4
+    assert (cor1.cpu() - rcor).abs().max().item() < 1e-4
+    # shard invariance: a panorama's result does not depend on its batch
+    assert torch.equal(bon3[1:2], bon1) and torch.equal(cor3[1:2], cor1)
+
+
+def test_forward_host_equals_device_forward():
+    sd = synthetic_state_dict(2, 'identity')
+    net = _net(sd, True)
+    x = synthetic_panoramas(2, seed=9)
+    with torch.no_grad():
+        bon, cor = net(x.to(DEV))
+    hb, hc = net.forward_host(x.pin_memory())
+    assert torch.equal(hb, bon.cpu()) and torch.equal(hc, cor.cpu())
+
+
+def test_zero_head_weight_gives_bias_exactly():
+    """Known answer: linear.weight = 0 => cor = -1, bon = (-0.478, 0.425)."""
+    sd = synthetic_state_dict(4, 'identity')
+    sd['linear.weight'] = torch.zeros_like(sd['linear.weight'])
+    net = _net(sd, True)
+    with torch.no_grad():
+        bon, cor = net(synthetic_panoramas(1, seed=3).to(DEV))
+    assert torch.all(cor == -1.0)
+    assert torch.all(bon[:, 0] == torch.tensor(-0.478)) and torch.all(bon[:, 1] == torch.tensor(0.425))
+
+
+def test_forward_rejects_wrong_size_and_reloads_weights():
+    sd = synthetic_state_dict(5, 'identity')
+    net = _net(sd, True)
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 3, 256, 512, device=DEV))
+    x = synthetic_panoramas(1, seed=1).to(DEV)
+    with torch.no_grad():
+        b0, _ = net(x)
+        net.load_state_dict(synthetic_state_dict(6, 'identity'))       # in-place update must be picked up
+        b1, _ = net(x)
+    assert not torch.equal(b0, b1)
+
+
+# ------------------------------------------------------------------------------- pano_stretch
+def test_pano_stretch_small_grid_vs_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'panostretch_small.npz'))
+    img = g['img']
+    for kx in KGRID:
+        for ky in KGRID:
+            out, _ = pano_stretch(img, np.zeros((1, 2), np.float32), kx, ky)
+            assert out.dtype == np.float32 and out.shape == img.shape
+            assert np.abs(out - g[f'out_{kx}_{ky}']).max() <= 1.2e-7, (kx, ky)
+    out0, _ = pano_stretch(img, np.zeros((1, 2), np.float32), 1.5, 0.75, order=0)
+    assert np.mean(out0 != g['out0_1.5_0.75']) < 1e-3          # nearest: ties may round differently
+
+
+def test_pano_stretch_full_size_vs_golden_and_oracle(golden_dir):
+    g = np.load(os.path.join(golden_dir, 'panostretch_rows.npz'))
+    img = np.random.RandomState(0).random_sample((512, 1024, 3)).astype(np.float32)
+    corners = np.array([[158, 186], [158, 329], [353, 185], [353, 330], [594, 154], [594, 363],
+                        [713, 100], [713, 415], [692, 77], [692, 438], [965, 150], [965, 367]], np.float32)
+    rows = g['rows']
+    pairs = [(kx, ky) for kx in KGRID for ky in KGRID]
+    dev_img = torch.from_numpy(img).to(DEV)
+    batch = dev_img.unsqueeze(0).expand(len(pairs), -1, -1, -1).contiguous()
+    outs = pano_stretch_batch(batch, [p[0] for p in pairs], [p[1] for p in pairs]).cpu().numpy()
+    for i, (kx, ky) in enumerate(pairs):
+        o = outs[i]
+        assert abs(o.astype(np.float64).sum() - float(g[f'sum_{kx}_{ky}'])) < 1e-3 * 1.0, (kx, ky)
+        assert abs((o.astype(np.float64) ** 2).sum() - float(g[f'sq_{kx}_{ky}'])) < 1e-3, (kx, ky)
+        if f'out_{kx}_{ky}' in g.files:
+            assert np.abs(o[rows] - g[f'out_{kx}_{ky}']).max() <= 1.2e-7, (kx, ky)
+    # one full image against the oracle, plus the host (numpy) entry point and corners
+    out, cor = pano_stretch(img, corners, 2.0, 0.5)
+    rout, rcor = panostretch_ref.pano_stretch(img, corners, 2.0, 0.5)
+    assert np.abs(out - rout).max() <= 1.2e-7
+    assert np.abs(cor - rcor).max() < 1e-9 and cor.dtype == np.float64
+    assert np.array_equal(out, outs[pairs.index((2.0, 0.5))])
+    # identity
+    ident, icor = pano_stretch(img, corners, 1.0, 1.0)
+    assert np.abs(ident - img).max() <= 1.2e-7 and np.abs(icor - corners).max() < 1e-4
+
+
+@pytest.mark.parametrize('shape', [(7, 10, 1), (33, 130, 3), (64, 257, 4), (1, 8, 2)])
+def test_pano_stretch_ragged_shapes_vs_oracle(shape):
+    img = np.random.RandomState(sum(shape)).random_sample(shape).astype(np.float32)
+    for kx, ky in ((0.6, 1.9), (1.8, 0.7), (1.0, 1.0)):
+        out, _ = pano_stretch(img, np.zeros((1, 2)), kx, ky)
+        rout, _ = panostretch_ref.pano_stretch(img, np.zeros((1, 2)), kx, ky)
+        assert np.abs(out - rout).max() <= 1.2e-7, (shape, kx, ky)
+
+
+def test_pano_stretch_rejects_bad_arguments():
+    with pytest.raises(TypeError):
+        pano_stretch(np.zeros((8, 16, 3), np.float64), np.zeros((1, 2)), 1.0, 1.0)
+    with pytest.raises(RuntimeError):
+        pano_stretch(np.zeros((8, 16, 3), np.float32), np.zeros((1, 2)), -1.0, 1.0)
+    empty = pano_stretch_batch(torch.zeros(0, 8, 16, 3, device=DEV), [], [])
+    assert empty.shape == (0, 8, 16, 3)
