@@ -34,6 +34,7 @@ SIGNATURES = {
     'hn_model_stage': (ctypes.c_int, [vp, ctypes.c_char_p, vp, ctypes.c_longlong, c_int_p, vp]),
     'hn_model_set_option': (ctypes.c_int, [vp, ctypes.c_char_p, ctypes.c_int]),
     'hn_model_check': (ctypes.c_int, [vp]),
+    'hn_model_profile_read': (ctypes.c_int, [vp, c_double_p, c_double_p, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]),
     'hn_model_destroy': (None, [vp]),
     'hn_pano_stretch': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                        c_double_p, c_double_p, ctypes.c_int, vp]),

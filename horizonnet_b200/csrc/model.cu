@@ -12,6 +12,8 @@
 #include "hn_common.cuh"
 #include "../../include/horizonnet_b200.h"
 
+#define HN_NUM_CLASSES 8
+
 namespace hn {
 
 // ---- error / launch accounting -----------------------------------------------------------------
@@ -95,6 +97,8 @@ __global__ void seq_to_feature_kernel(const float* __restrict__ seq, float* __re
     out[i] = seq[((size_t)t * B + b) * 1024 + ch];
 }
 
+enum { CLS_STEM = 0, CLS_POOL, CLS_ENC_CONV, CLS_GHC_CONV, CLS_TAIL, CLS_XPROJ, CLS_LSTM, CLS_HEAD };
+
 struct TensorSlot {
     std::string key;
     long long numel = 0;
@@ -146,9 +150,24 @@ struct hn_model {
     float *x_in = nullptr, *bon_out = nullptr, *cor_out = nullptr;    // for forward_host
     int last_batch = 0;
 
+    // optional per-op-class timing (bench.py roofline): CUDA event pairs around every launch
+    int profile = 0;
+    struct Span { int cls; double flops; cudaEvent_t a, b; };
+    std::vector<Span> spans;                       // pending (recorded, not yet read)
+    std::vector<cudaEvent_t> free_events;
+    double prof_ms[HN_NUM_CLASSES] = {0};
+    double prof_flops[HN_NUM_CLASSES] = {0};
+    long long prof_launches[HN_NUM_CLASSES] = {0};
+
     ~hn_model() {
         cudaSetDevice(device);
+        for (auto& sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+        for (auto e : free_events) cudaEventDestroy(e);
         for (void* p : allocs) cudaFree(p);
+    }
+    cudaEvent_t get_event() {
+        if (!free_events.empty()) { cudaEvent_t e = free_events.back(); free_events.pop_back(); return e; }
+        cudaEvent_t e; cudaEventCreate(&e); return e;
     }
     int alloc(void** p, size_t bytes) {
         HN_CUDA_OK(cudaMalloc(p, bytes ? bytes : 4));
@@ -256,7 +275,25 @@ Act mk(float* p, int B, int H, int W, int C, int halo = 1) {
     Act a; a.p = p; a.B = B; a.H = H; a.W = W; a.C = C; a.halo = halo; return a;
 }
 
-int run_conv(hn_model* m, const ConvLayer& c, const Act& in, const Act& out, const float* res, cudaStream_t st) {
+// RAII span: records an event pair around the launches issued in its scope when profiling is on
+struct Scope {
+    hn_model* m; cudaStream_t st; hn_model::Span sp; bool on;
+    Scope(hn_model* m_, int cls, double flops, cudaStream_t st_) : m(m_), st(st_), on(m_->profile != 0) {
+        if (!on) return;
+        sp.cls = cls; sp.flops = flops; sp.a = m->get_event(); sp.b = m->get_event();
+        cudaEventRecord(sp.a, st);
+    }
+    ~Scope() {
+        if (!on) return;
+        cudaEventRecord(sp.b, st);
+        m->spans.push_back(sp);
+    }
+};
+
+int run_conv(hn_model* m, const ConvLayer& c, const Act& in, const Act& out, const float* res, cudaStream_t st,
+             int cls) {
+    const double flops = 2.0 * (double)out.B * out.H * out.W * c.d.Cout * c.d.kh * c.d.kw * c.d.Cin;
+    Scope sc(m, cls, flops, st);
     if (m->use_tc && conv_tc_supported(c.d, in, out)) return conv_tc(c.d, in, out, res, st);
     return conv_f32(c.d, in, out, res, st);
 }
@@ -338,6 +375,7 @@ int hn_model_set_tensor(hn_model* m, const char* key, const float* data, long lo
 int hn_model_set_option(hn_model* m, const char* name, int value) {
     HN_CHECK(m && name, "hn_model_set_option: NULL argument");
     if (std::strcmp(name, "tensor_cores") == 0) { m->use_tc = value; return 0; }
+    if (std::strcmp(name, "profile") == 0) { m->profile = value; return 0; }
     return fail(std::string("hn_model_set_option: unknown option '") + name + "'");
 }
 
@@ -394,9 +432,15 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
 
     // model.py:248-252 + :73-76: normalise, stem conv/BN/ReLU, max-pool
     Act s0 = mk(m->S0, B, 256, 512, 64);
-    if (stem_f32(x, B, in_channels, m->stem.w, m->stem.scale, m->stem.shift, s0, st)) return -1;
+    {
+        Scope sc(m, CLS_STEM, 2.0 * B * 256 * 512 * 64 * 147, st);
+        if (stem_f32(x, B, in_channels, m->stem.w, m->stem.scale, m->stem.shift, s0, st)) return -1;
+    }
     Act cur = mk(m->S1, B, 128, 256, 64);
-    if (maxpool3x3s2(s0, cur, st)) return -1;
+    {
+        Scope sc(m, CLS_POOL, 0.0, st);
+        if (maxpool3x3s2(s0, cur, st)) return -1;
+    }
 
     // model.py:78-81: layer1..layer4 (torchvision Bottleneck v1.5)
     Act feats[4];
@@ -409,15 +453,15 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
             Act t1 = mk(m->T1, B, cur.H, cur.W, blk.c1.d.Cout);
             Act t2 = mk(m->T2, B, Ho, Wo, blk.c2.d.Cout);
             Act y = mk(b == nb - 1 ? m->F[l] : m->X[b & 1], B, Ho, Wo, blk.c3.d.Cout);
-            if (run_conv(m, blk.c1, cur, t1, nullptr, st)) return -1;
-            if (run_conv(m, blk.c2, t1, t2, nullptr, st)) return -1;
+            if (run_conv(m, blk.c1, cur, t1, nullptr, st, CLS_ENC_CONV)) return -1;
+            if (run_conv(m, blk.c2, t1, t2, nullptr, st, CLS_ENC_CONV)) return -1;
             const float* idn = cur.p;
             if (blk.has_ds) {
                 Act d = mk(m->IDN, B, Ho, Wo, blk.ds.d.Cout);
-                if (run_conv(m, blk.ds, cur, d, nullptr, st)) return -1;
+                if (run_conv(m, blk.ds, cur, d, nullptr, st, CLS_ENC_CONV)) return -1;
                 idn = d.p;
             }
-            if (run_conv(m, blk.c3, t2, y, idn, st)) return -1;      // + identity, ReLU
+            if (run_conv(m, blk.c3, t2, y, idn, st, CLS_ENC_CONV)) return -1;      // + identity, ReLU
             cur = y;
         }
         feats[l] = cur;
@@ -430,13 +474,16 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
         for (int j = 0; j < 4; ++j) {
             const ConvLayer& c = m->ghc[s][j];
             Act o = mk(j == 3 ? m->GO[s] : m->G[j & 1], B, g.H / 2, g.W, c.d.Cout);
-            if (run_conv(m, c, g, o, nullptr, st)) return -1;
+            if (run_conv(m, c, g, o, nullptr, st, CLS_GHC_CONV)) return -1;
             g = o;
         }
         gout[s] = g;
     }
     // model.py:152-155 + :175-178 + :263 -> [T=256][B][1024]
-    if (ghc_to_sequence(gout, m->SEQ, st)) return -1;
+    {
+        Scope sc(m, CLS_TAIL, 0.0, st);
+        if (ghc_to_sequence(gout, m->SEQ, st)) return -1;
+    }
 
     // model.py:264: 2-layer bidirectional LSTM (eval: dropout = identity)
     const float* lin = m->SEQ;
@@ -444,13 +491,40 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
     for (int layer = 0; layer < 2; ++layer) {
         Act a = mk(const_cast<float*>(lin), 1, 1, 256 * B, 1024, 0);
         Act xp = mk(m->XP, 1, 1, 256 * B, 4096, 0);
-        if (run_conv(m, m->xproj[layer], a, xp, nullptr, st)) return -1;
-        if (lstm_layer(m->XP, m->whh[layer][0], m->whh[layer][1], louts[layer], 256, B, m->counters, m->error_flag, st))
-            return -1;
+        if (run_conv(m, m->xproj[layer], a, xp, nullptr, st, CLS_XPROJ)) return -1;
+        {
+            Scope sc(m, CLS_LSTM, 2.0 * 256 * B * 2 * 2048 * 512, st);
+            if (lstm_layer(m->XP, m->whh[layer][0], m->whh[layer][1], louts[layer], 256, B, m->counters,
+                           m->error_flag, st))
+                return -1;
+        }
         lin = louts[layer];
     }
     // model.py:265-281: dropout (id), linear, reshape, split
-    if (linear_head(m->R2, m->head_w, m->head_b, bon, cor, 256, B, st)) return -1;
+    {
+        Scope sc(m, CLS_HEAD, 2.0 * 256 * B * 12 * 1024, st);
+        if (linear_head(m->R2, m->head_w, m->head_b, bon, cor, 256, B, st)) return -1;
+    }
+    return 0;
+}
+
+int hn_model_profile_read(hn_model* m, double* ms, double* flops, long long* launches, int reset) {
+    HN_CHECK(m, "hn_model_profile_read: NULL model");
+    HN_CUDA_OK(cudaSetDevice(m->device));
+    for (auto& sp : m->spans) {
+        HN_CUDA_OK(cudaEventSynchronize(sp.b));
+        float t = 0.f;
+        HN_CUDA_OK(cudaEventElapsedTime(&t, sp.a, sp.b));
+        m->prof_ms[sp.cls] += t; m->prof_flops[sp.cls] += sp.flops; m->prof_launches[sp.cls] += 1;
+        m->free_events.push_back(sp.a); m->free_events.push_back(sp.b);
+    }
+    m->spans.clear();
+    for (int i = 0; i < HN_NUM_CLASSES; ++i) {
+        if (ms) ms[i] = m->prof_ms[i];
+        if (flops) flops[i] = m->prof_flops[i];
+        if (launches) launches[i] = m->prof_launches[i];
+        if (reset) { m->prof_ms[i] = 0; m->prof_flops[i] = 0; m->prof_launches[i] = 0; }
+    }
     return 0;
 }
 

@@ -243,6 +243,27 @@ class HorizonNet(nn.Module):
         shape = [d for d in dims if d > 0]
         return out[:int(np.prod(shape))].view(*shape)
 
+    PROFILE_CLASSES = ('stem', 'maxpool', 'encoder_convs', 'height_reduction_convs', 'upsample_concat',
+                       'lstm_input_projection', 'lstm_recurrence', 'linear_head')
+
+    def set_profile(self, enabled=True):
+        """Per-launch CUDA-event timing inside the library (used by bench.py for the roofline)."""
+        for h in self._handles.values():
+            _lib.check(_lib.lib().hn_model_set_option(h['ptr'], b'profile', 1 if enabled else 0), 'set_option')
+
+    def read_profile(self, reset=True):
+        """{class: (device ms, algorithmic FLOPs, launches)} accumulated since the last reset."""
+        out = {}
+        for h in self._handles.values():
+            ms = (ctypes.c_double * 8)()
+            fl = (ctypes.c_double * 8)()
+            n = (ctypes.c_longlong * 8)()
+            _lib.check(_lib.lib().hn_model_profile_read(h['ptr'], ms, fl, n, 1 if reset else 0), 'profile_read')
+            for i, name in enumerate(self.PROFILE_CLASSES):
+                a = out.get(name, (0.0, 0.0, 0))
+                out[name] = (a[0] + ms[i], a[1] + fl[i], a[2] + n[i])
+        return out
+
     def check(self):
         """Synchronise and raise if an asynchronous forward failed on the device."""
         for h in self._handles.values():

@@ -71,8 +71,16 @@ int hn_model_stage(hn_model* m, const char* stage, float* out_dev, long long cap
                    void* stream);
 
 /* Options: "tensor_cores" = 1 routes every conv / projection GEMM the tcgen05 kernel supports
- * through the split-bf16 tensor-core path (default), 0 = exact fp32 CUDA-core kernels everywhere. */
+ * through the split-bf16 tensor-core path (default), 0 = exact fp32 CUDA-core kernels everywhere;
+ * "profile" = 1 turns on per-launch CUDA-event timing (see hn_model_profile_read). */
 int hn_model_set_option(hn_model* m, const char* name, int value);
+
+/* With option "profile" = 1 every forward records CUDA-event pairs (on the forward's stream)
+ * around each launch; this call waits for them and returns, per op class
+ * {0 stem, 1 maxpool, 2 encoder convs, 3 height-reduction convs, 4 upsample/concat tail,
+ *  5 LSTM input-projection GEMMs, 6 LSTM recurrence, 7 linear head},
+ * the accumulated device milliseconds, algorithmic FLOPs and launch counts (arrays of 8). */
+int hn_model_profile_read(hn_model* m, double* ms, double* flops, long long* launches, int reset);
 
 /* Synchronises the device and reports device-side failures recorded by earlier asynchronous
  * forwards (e.g. the persistent LSTM kernel's peer-wait timeout). */
