@@ -10,6 +10,7 @@
 // stem_f32: 7x7 stride-2 conv on the NCHW fp32 input with the input normalisation
 //   (model.py:248-252), BN and ReLU fused (model.py:73-75).
 // maxpool3x3s2: model.py:76 (padding is -inf on both axes -- NOT circular).
+#include <cuda_bf16.h>
 #include "hn_common.cuh"
 
 namespace hn {
@@ -301,6 +302,18 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
     }
 }
 
+__device__ __forceinline__ uint2 split4(const float4 m, bool lo) {
+    const float f[4] = {m.x, m.y, m.z, m.w};
+    unsigned short u[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
+        u[j] = __bfloat16_as_ushort(lo ? __float2bfloat16_rn(f[j] - __bfloat162float(h)) : h);
+    }
+    return make_uint2((unsigned)u[0] | ((unsigned)u[1] << 16), (unsigned)u[2] | ((unsigned)u[3] << 16));
+}
+
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                       int B, int H, int W, int C, int Ho, int Wo) {
     // one thread = one output pixel x 4 channels; input/output halo = 1
@@ -329,9 +342,23 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ 
         }
     }
     const size_t row = ((size_t)b * Ho + ho) * Wop;
-    reinterpret_cast<float4*>(out + (row + wo + 1) * C)[c4] = m;
-    if (wo == 0) reinterpret_cast<float4*>(out + (row + Wo + 1) * C)[c4] = m;
-    if (wo == Wo - 1) reinterpret_cast<float4*>(out + row * C)[c4] = m;
+    if (!SPLIT) {
+        reinterpret_cast<float4*>(out + (row + wo + 1) * C)[c4] = m;
+        if (wo == 0) reinterpret_cast<float4*>(out + (row + Wo + 1) * C)[c4] = m;
+        if (wo == Wo - 1) reinterpret_cast<float4*>(out + row * C)[c4] = m;
+    } else {
+        // bf16 hi/lo planes for the tensor-core convs (plane = B*Ho*Wop*C elements)
+        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out);
+        const size_t plane = (size_t)B * Ho * Wop * C;
+        const uint2 hi = split4(m, false), lo = split4(m, true);
+        auto put = [&](size_t pix) {
+            reinterpret_cast<uint2*>(ob + pix * C)[c4] = hi;
+            reinterpret_cast<uint2*>(ob + plane + pix * C)[c4] = lo;
+        };
+        put(row + wo + 1);
+        if (wo == 0) put(row + Wo + 1);
+        if (wo == Wo - 1) put(row);
+    }
 }
 
 }  // namespace
@@ -348,11 +375,14 @@ int stem_f32(const float* x_nchw, int B, int in_channels, const float* w_packed,
     return 0;
 }
 
-int maxpool3x3s2(const Act& in, const Act& out, cudaStream_t st) {
+int maxpool3x3s2(const Act& in, const Act& out, cudaStream_t st, bool out_split) {
     HN_CHECK(in.halo == 1 && out.halo == 1 && in.C == out.C && in.C % 4 == 0, "maxpool: bad tensors");
     HN_CHECK(out.H == (in.H + 2 - 3) / 2 + 1 && out.W == (in.W + 2 - 3) / 2 + 1 && in.B == out.B, "maxpool: geometry");
     const size_t total = (size_t)out.B * out.H * out.W * (out.C / 4);
-    maxpool_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in.p, out.p, in.B, in.H, in.W, in.C, out.H, out.W);
+    if (out_split)
+        maxpool_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in.p, out.p, in.B, in.H, in.W, in.C, out.H, out.W);
+    else
+        maxpool_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in.p, out.p, in.B, in.H, in.W, in.C, out.H, out.W);
     HN_LAUNCH_OK();
     return 0;
 }

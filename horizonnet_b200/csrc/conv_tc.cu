@@ -1,8 +1,650 @@
-// tcgen05 tensor-core convolution (split-bf16, 3 products) -- placeholder until the kernel lands.
+// tcgen05 tensor-core convolution / GEMM for sm_100a: split-bf16, three products, fp32 accumulate.
+//
+// Why split precision: the contract is <= 1e-4 max-abs against the fp32 reference on random-init
+// weights; single-pass bf16 (1.4e-2) or tf32 (1.5e-3) miss it (SURVEY hard-part 1).  Every fp32
+// value v is carried as two bf16 planes  hi = bf16(v), lo = bf16(v - hi)  (same 4 B/element as
+// fp32), and the product is evaluated as  Ahi*Bhi + Ahi*Blo + Alo*Bhi  with the fp32 accumulator
+// in tensor memory.  The planes are written by the producing kernel's epilogue, so every operand
+// tile is MMA-ready when TMA drops it into shared memory (no in-kernel conversion pass).
+//
+// Kernel shape (persistent, warp-specialised, one CTA per SM):
+//   warp 0     TMA producer: per 64-channel K chunk it loads A (hi, lo: 128 pixels x 64 ch, 128B
+//              swizzle) with one box per output row of the tile from the halo-NHWC planes -- the
+//              3x3 taps are just shifted box coordinates, zero H padding is TMA out-of-bounds
+//              fill, circular W padding is the halo column, stride-2 in W reads a parity view --
+//              and B (hi, lo: BN x 64 weights, K-major);   3-stage mbarrier ring (64 KB / stage)
+//   warp 1     MMA issuer: one thread issues 12 tcgen05.mma (3 products x 4 K-steps of 16) per
+//              chunk into one of two TMEM accumulators; tcgen05.commit frees the smem stage and,
+//              at the end of the tile, publishes the accumulator
+//   warp 2     TMEM allocator
+//   warps 4-11 epilogue: tcgen05.ld (lane quarter = warp%4, column half = (warp-4)/4), folded
+//              BN scale/shift, residual add, ReLU, re-split into bf16 planes (or fp32), vector
+//              stores incl. the circular halo columns; overlaps the next tile's MMAs.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <mutex>
+
 #include "hn_common.cuh"
+#include "conv_tc.cuh"
+
 namespace hn {
-bool conv_tc_supported(const ConvDesc&, const Act&, const Act&) { return false; }
-int conv_tc(const ConvDesc&, const Act&, const Act&, const float*, cudaStream_t) {
-    return fail("conv_tc: not built");
+
+namespace {
+
+constexpr int BM = 128;            // pixels per tile = UMMA M
+constexpr int BKC = 64;            // bf16 channels per K chunk = one 128-byte swizzle row
+constexpr int STAGES = 3;
+constexpr int NTHREADS = 384;
+constexpr int EPI_WARP0 = 4;
+constexpr long long WAIT_LIMIT = 3000000000ll;     // cycles; a stuck barrier traps instead of hanging
+
+// ------------------------------------------------------------------------------------ PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > WAIT_LIMIT) {
+            printf("conv_tc: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+            asm volatile("trap;");
+        }
+    }
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3),
+        "r"(c4)
+        : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory operand descriptor (rows of 128 B, 8-row atoms 1024 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address        bits [0,14)
+    d |= (uint64_t)0 << 16;                               // leading byte offset  bits [16,30) (unused: one atom along K)
+    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset   bits [32,46)
+    d |= (uint64_t)1 << 46;                               // descriptor version 1 (sm_100)
+    d |= (uint64_t)2 << 61;                               // layout type: SWIZZLE_128B
+    return d;
+}
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
+    return (1u << 4)                    // c_format  = F32
+           | (1u << 7)                  // a_format  = BF16
+           | (1u << 10)                 // b_format  = BF16
+           | ((uint32_t)(n >> 3) << 17) // n_dim
+           | ((uint32_t)(BM >> 4) << 24);  // m_dim
+}
+
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+struct TcArgs {
+    int mode;                 // 0: GEMM rows (1x1 stride-1 conv over all halo-NHWC pixels, or plain GEMM); 1: conv rows
+    int M;                    // mode 0: rows; mode 1: B*Ho output rows
+    int Ho, Wo, Wop;          // mode 1 output geometry (Wop = Wo + 2*out_halo)
+    int out_halo;
+    int tw, rows_per_tile, wsegs;
+    int sh, ph, parity, woff; // parity = 1: stride 2 along W through the [Wp/2][2] view; woff = in_halo - pw
+    int kw, kc_per_tap, num_kc;
+    int Bimg;                 // images per plane (plane p of image b sits at index p*Bimg + b of the outer TMA dim)
+    int Cout, n_tiles, num_tiles;
+    const float* scale;
+    const float* shift;
+    const __nv_bfloat16* res; // residual planes in the OUTPUT geometry (hi at res, lo at res + out_plane), or null
+    __nv_bfloat16* out;       // split output planes (hi at out, lo at out + out_plane)
+    float* out_f32;           // fp32 output instead of planes (LSTM projections)
+    size_t out_plane;         // elements per plane
+    int relu;
+};
+
+template <int BN>
+struct Smem {
+    static constexpr int A_PLANE = BM * BKC * 2;          // 16 KB
+    static constexpr int B_PLANE = BN * BKC * 2;
+    static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
+    static constexpr int BAR_OFF = STAGES * STAGE;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;    // barriers + alignment slack
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(NTHREADS, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
+    using S = Smem<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;       // [2] accumulator ready
+    uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+                const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+                int valid_rows = 1, row0 = 0, wo0 = 0;
+                if (a.mode == 1) {
+                    const int rg = mt / a.wsegs;
+                    wo0 = (mt - rg * a.wsegs) * a.tw;
+                    row0 = rg * a.rows_per_tile;
+                    valid_rows = min(a.rows_per_tile, a.M - row0);
+                }
+                const uint32_t a_bytes = (a.mode == 0) ? 2u * S::A_PLANE : (uint32_t)(2 * valid_rows * a.tw * BKC * 2);
+                for (int kc = 0; kc < a.num_kc; ++kc) {
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t* sA = smem + stage * S::STAGE;
+                    uint8_t* sB = sA + 2 * S::A_PLANE;
+                    mbar_expect_tx(full_bar + stage, a_bytes + 2u * S::B_PLANE);
+                    const int tap = kc / a.kc_per_tap;
+                    const int c0 = (kc - tap * a.kc_per_tap) * BKC;
+                    if (a.mode == 0) {
+                        tma_load_3d(sA, &tmA, full_bar + stage, c0, mt * BM, 0);
+                        tma_load_3d(sA + S::A_PLANE, &tmA, full_bar + stage, c0, mt * BM, 1);
+                    } else {
+                        const int dy = tap / a.kw, dx = tap - dy * a.kw;
+                        for (int rr = 0; rr < valid_rows; ++rr) {
+                            const int R = row0 + rr;
+                            const int b = R / a.Ho, ho = R - b * a.Ho;
+                            const int hin = ho * a.sh + dy - a.ph;
+                            uint8_t* dst = sA + rr * a.tw * (BKC * 2);
+                            if (a.parity) {
+                                const int p = dx + a.woff;
+                                tma_load_5d(dst, &tmA, full_bar + stage, c0, p & 1, wo0 + (p >> 1), hin, b);
+                                tma_load_5d(dst + S::A_PLANE, &tmA, full_bar + stage, c0, p & 1, wo0 + (p >> 1), hin,
+                                            a.Bimg + b);
+                            } else {
+                                tma_load_4d(dst, &tmA, full_bar + stage, c0, wo0 + dx + a.woff, hin, b);
+                                tma_load_4d(dst + S::A_PLANE, &tmA, full_bar + stage, c0, wo0 + dx + a.woff, hin,
+                                            a.Bimg + b);
+                            }
+                        }
+                    }
+                    tma_load_3d(sB, &tmB, full_bar + stage, kc * BKC, nt * BN, 0);
+                    tma_load_3d(sB + S::B_PLANE, &tmB, full_bar + stage, kc * BKC, nt * BN, 1);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(BN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1;
+                mbar_wait(tempty_bar + acc, acc_phase ^ 1);        // epilogue drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kc = 0; kc < a.num_kc; ++kc) {
+                    mbar_wait(full_bar + stage, phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_u32(smem + stage * S::STAGE);
+                    const uint32_t sB = sA + 2 * S::A_PLANE;
+                    const uint64_t a_hi = umma_desc_sw128(sA), a_lo = umma_desc_sw128(sA + S::A_PLANE);
+                    const uint64_t b_hi = umma_desc_sw128(sB), b_lo = umma_desc_sw128(sB + S::B_PLANE);
+#pragma unroll
+                    for (int k = 0; k < BKC / 16; ++k) {
+                        const uint64_t ko = (uint64_t)((k * 16 * 2) >> 4);     // advance 32 B inside the swizzle row
+                        umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, (kc | k) != 0);
+                        umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1);
+                        umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1);
+                    }
+                    umma_commit(empty_bar + stage);                  // frees the smem stage when the MMAs retire
+                    if (kc == a.num_kc - 1) umma_commit(tfull_bar + acc);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // =============================== epilogue ===============================
+        const int q = warp & 3;                          // TMEM lane quarter this warp may access
+        const int half = (warp - EPI_WARP0) >> 2;        // column half
+        // BN >= 64: the two warps of a lane quarter split the columns; BN == 32: warp of half 0 takes all 32
+        constexpr int COLS_PER_WARP = (BN >= 64) ? BN / 2 : BN;
+        constexpr int NCHUNK = COLS_PER_WARP / 32;
+        constexpr int CW = 32;                                           // columns per tcgen05.ld chunk
+        const bool works = (BN >= 64) || half == 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+            const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1;
+            const int r = q * 32 + lane;                 // accumulator row = pixel of the tile
+            // ---- where does this row live in the output?
+            bool valid;
+            size_t pix;                                  // pixel index in the output tensor (incl. halo columns)
+            size_t halo_pix = 0;
+            bool has_halo = false;
+            if (a.mode == 0) {
+                const long long m = (long long)mt * BM + r;
+                valid = m < a.M;
+                pix = (size_t)m;
+            } else {
+                const int rg = mt / a.wsegs;
+                const int wo = (mt - rg * a.wsegs) * a.tw + (r % a.tw);
+                const int R = rg * a.rows_per_tile + r / a.tw;
+                valid = R < a.M;
+                pix = (size_t)R * a.Wop + wo + a.out_halo;
+                if (a.out_halo) {
+                    if (wo == 0) { has_halo = true; halo_pix = (size_t)R * a.Wop + a.Wo + 1; }
+                    else if (wo == a.Wo - 1) { has_halo = true; halo_pix = (size_t)R * a.Wop; }
+                }
+            }
+            mbar_wait(tfull_bar + acc, acc_phase);
+            tc_fence_after();
+#pragma unroll
+            for (int ch = 0; ch < (works ? NCHUNK : 0); ++ch) {
+                const int col0 = half * COLS_PER_WARP + ch * 32;          // column inside the tile
+                uint32_t v[32];
+                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col0), v);
+                if (!valid) continue;
+                const int n0 = nt * BN + col0;                            // output channel of v[0]
+                float y[32];
+#pragma unroll
+                for (int j = 0; j < CW; j += 4) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + n0 + j));
+                    const float4 sf = __ldg(reinterpret_cast<const float4*>(a.shift + n0 + j));
+                    y[j + 0] = fmaf(__uint_as_float(v[j + 0]), sc.x, sf.x);
+                    y[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sf.y);
+                    y[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sf.z);
+                    y[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sf.w);
+                }
+                if (a.res) {
+                    const uint4* rh = reinterpret_cast<const uint4*>(a.res + pix * a.Cout + n0);
+                    const uint4* rl = reinterpret_cast<const uint4*>(a.res + a.out_plane + pix * a.Cout + n0);
+#pragma unroll
+                    for (int j = 0; j < CW / 8; ++j) {
+                        const uint4 h = __ldg(rh + j), l = __ldg(rl + j);
+                        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            // bf16 -> fp32 is a 16-bit shift
+                            y[j * 8 + 2 * e + 0] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
+                            y[j * 8 + 2 * e + 1] += __uint_as_float(hw[e] & 0xFFFF0000u) + __uint_as_float(lw[e] & 0xFFFF0000u);
+                        }
+                    }
+                }
+                if (a.relu) {
+#pragma unroll
+                    for (int j = 0; j < CW; ++j) y[j] = fmaxf(y[j], 0.f);
+                }
+                if (a.out_f32) {
+                    float4* o = reinterpret_cast<float4*>(a.out_f32 + pix * a.Cout + n0);
+#pragma unroll
+                    for (int j = 0; j < CW / 4; ++j) o[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                } else {
+                    uint32_t ph[16], pl[16];
+#pragma unroll
+                    for (int j = 0; j < CW / 2; ++j) {
+                        const __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * j]), h1 = __float2bfloat16_rn(y[2 * j + 1]);
+                        const __nv_bfloat16 l0 = __float2bfloat16_rn(y[2 * j] - __bfloat162float(h0));
+                        const __nv_bfloat16 l1 = __float2bfloat16_rn(y[2 * j + 1] - __bfloat162float(h1));
+                        ph[j] = pack_bf16x2(h0, h1);
+                        pl[j] = pack_bf16x2(l0, l1);
+                    }
+                    uint4* oh = reinterpret_cast<uint4*>(a.out + pix * a.Cout + n0);
+                    uint4* ol = reinterpret_cast<uint4*>(a.out + a.out_plane + pix * a.Cout + n0);
+#pragma unroll
+                    for (int j = 0; j < CW / 8; ++j) {
+                        oh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+                        ol[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                    }
+                    if (has_halo) {
+                        uint4* hh = reinterpret_cast<uint4*>(a.out + halo_pix * a.Cout + n0);
+                        uint4* hl = reinterpret_cast<uint4*>(a.out + a.out_plane + halo_pix * a.Cout + n0);
+#pragma unroll
+                        for (int j = 0; j < CW / 8; ++j) {
+                            hh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
+                            hl[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
+                        }
+                    }
+                }
+            }
+            // accumulator drained: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar + acc);
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// -------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+             const cuuint32_t* box) {
+    EncodeTiledFn fn = encode_fn();
+    HN_CHECK(fn != nullptr, "conv_tc: cuTensorMapEncodeTiled unavailable");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail("conv_tc: cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return 0;
+}
+
+template <int BN>
+int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
+    using S = Smem<BN>;
+    HN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    int dev = 0, sms = 0;
+    HN_CUDA_OK(cudaGetDevice(&dev));
+    HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = a.num_tiles < sms ? a.num_tiles : sms;
+    conv_tc_kernel<BN><<<grid, NTHREADS, S::TOTAL, st>>>(tmA, tmB, a);
+    HN_LAUNCH_OK();
+    return 0;
+}
+
+}  // namespace
+
+bool conv_tc_supported(const ConvDesc& d, const Act& in, const Act& out) {
+    if (d.Cin % 64 != 0 || d.Cout % 32 != 0) return false;
+    if (d.Cout > 64 && d.Cout % 128 != 0) return false;
+    if (d.Cout < 64 && d.Cout != 32) return false;
+    if (d.pw > in.halo) return false;
+    const bool gemm = (d.kh == 1 && d.kw == 1 && d.sh == 1 && d.sw == 1 && in.halo == out.halo);
+    if (gemm) return true;
+    if (d.sw != 1 && d.sw != 2) return false;
+    if (d.sw == 2 && (in.Wp() % 2) != 0) return false;
+    const int tw = out.W < 128 ? out.W : 128;
+    if (tw < 8 || (tw & (tw - 1)) != 0 || out.W % tw != 0) return false;       // 8-row swizzle atoms, exact W tiling
+    return true;
+}
+
+// in / out / residual are split-bf16 plane pairs in halo-NHWC geometry (hi plane, then lo plane).
+// wq: [2][Cout][K] bf16 (hi, lo), K = (dy*kw+dx)*Cin + c.
+int conv_tc_planes(const ConvDesc& d, const __nv_bfloat16* wq, const Act& in, const __nv_bfloat16* in_planes,
+                   const Act& out, __nv_bfloat16* out_planes, float* out_f32, const __nv_bfloat16* res_planes,
+                   cudaStream_t st) {
+    HN_CHECK(conv_tc_supported(d, in, out), "conv_tc: unsupported shape");
+    const int K = d.kh * d.kw * d.Cin;
+    TcArgs a;
+    memset(&a, 0, sizeof(a));
+    const bool gemm = (d.kh == 1 && d.kw == 1 && d.sh == 1 && d.sw == 1 && in.halo == out.halo);
+    const int BN = d.Cout >= 128 ? 128 : d.Cout;
+    const size_t in_plane = in.numel(), out_plane = out.numel();
+    CUtensorMap tmA, tmB;
+    {   // weights: {K, Cout, 2}
+        cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)d.Cout, 2};
+        cuuint64_t str[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * d.Cout * 2};
+        cuuint32_t box[3] = {BKC, (cuuint32_t)BN, 1};
+        if (make_map(&tmB, wq, 3, dims, str, box)) return -1;
+    }
+    a.Cout = d.Cout;
+    a.n_tiles = d.Cout / BN;
+    a.kw = d.kw;
+    a.kc_per_tap = d.Cin / BKC;
+    a.num_kc = d.kh * d.kw * a.kc_per_tap;
+    a.scale = d.scale; a.shift = d.shift;
+    a.res = res_planes; a.out = out_planes; a.out_f32 = out_f32; a.out_plane = out_plane; a.relu = d.relu;
+    a.Bimg = in.B;
+    long long m_tiles;
+    if (gemm) {
+        const long long Mtot = (long long)in.B * in.H * in.Wp();
+        a.mode = 0;
+        a.M = (int)Mtot;
+        cuuint64_t dims[3] = {(cuuint64_t)d.Cin, (cuuint64_t)Mtot, 2};
+        cuuint64_t str[2] = {(cuuint64_t)d.Cin * 2, (cuuint64_t)in_plane * 2};
+        cuuint32_t box[3] = {BKC, BM, 1};
+        if (make_map(&tmA, in_planes, 3, dims, str, box)) return -1;
+        m_tiles = (Mtot + BM - 1) / BM;
+    } else {
+        a.mode = 1;
+        a.Ho = out.H; a.Wo = out.W; a.Wop = out.Wp(); a.out_halo = out.halo;
+        a.M = out.B * out.H;
+        a.tw = out.W < 128 ? out.W : 128;
+        a.rows_per_tile = BM / a.tw;
+        a.wsegs = out.W / a.tw;
+        a.sh = d.sh; a.ph = d.ph; a.woff = in.halo - d.pw;
+        a.parity = (d.sw == 2);
+        const cuuint64_t C2 = (cuuint64_t)d.Cin * 2, Wp = in.Wp();
+        if (!a.parity) {
+            cuuint64_t dims[4] = {(cuuint64_t)d.Cin, Wp, (cuuint64_t)in.H, (cuuint64_t)2 * in.B};
+            cuuint64_t str[3] = {C2, C2 * Wp, C2 * Wp * in.H};
+            cuuint32_t box[4] = {BKC, (cuuint32_t)a.tw, 1, 1};
+            if (make_map(&tmA, in_planes, 4, dims, str, box)) return -1;
+        } else {
+            cuuint64_t dims[5] = {(cuuint64_t)d.Cin, 2, Wp / 2, (cuuint64_t)in.H, (cuuint64_t)2 * in.B};
+            cuuint64_t str[4] = {C2, 2 * C2, C2 * Wp, C2 * Wp * in.H};
+            cuuint32_t box[5] = {BKC, 1, (cuuint32_t)a.tw, 1, 1};
+            if (make_map(&tmA, in_planes, 5, dims, str, box)) return -1;
+        }
+        m_tiles = (long long)((a.M + a.rows_per_tile - 1) / a.rows_per_tile) * a.wsegs;
+    }
+    HN_CHECK(m_tiles * a.n_tiles < (1ll << 31), "conv_tc: too many tiles");
+    a.num_tiles = (int)(m_tiles * a.n_tiles);
+    if (a.num_tiles == 0) return 0;
+    switch (BN) {
+        case 128: return launch<128>(tmA, tmB, a, st);
+        case 64: return launch<64>(tmA, tmB, a, st);
+        default: return launch<32>(tmA, tmB, a, st);
+    }
+}
+
+// ---------------------------------------------------------------------- format conversion kernels
+namespace {
+
+__global__ void split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        h[j] = __float2bfloat16_rn(f[j]);
+        l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
+    }
+    *reinterpret_cast<uint2*>(out + i) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
+    *reinterpret_cast<uint2*>(out + n + i) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+}
+
+__global__ void merge_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = __bfloat162float(in[i]) + __bfloat162float(in[n + i]);
+}
+
+// OIHW fp32 -> [2][Cout][K] bf16 planes, K = (dy*kw+dx)*Cin + c
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
+                                      int kh, int kw) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t K = (size_t)Cin * kh * kw;
+    const size_t total = (size_t)Cout * K;
+    if (i >= total) return;
+    const int n = (int)(i / K);
+    const size_t k = i - (size_t)n * K;
+    const int c = (int)(k % Cin);
+    const int tap = (int)(k / Cin);
+    const int dy = tap / kw, dx = tap % kw;
+    const float v = w[(((size_t)n * Cin + c) * kh + dy) * kw + dx];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = h;
+    out[total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+// packed fp32 [K][Cout] -> [2][Cout][K] bf16 planes (unit-test entry point)
+__global__ void pack_weight_tc_from_kn_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
+                                              size_t K) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)Cout * K;
+    if (i >= total) return;
+    const int n = (int)(i / K);
+    const size_t k = i - (size_t)n * K;
+    const float v = w[k * Cout + n];
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    out[i] = h;
+    out[total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+}  // namespace
+
+int split_planes(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st) {
+    HN_CHECK(n % 4 == 0, "split_planes: element count must be a multiple of 4");
+    if (n == 0) return 0;
+    split_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(in, out, n);
+    HN_LAUNCH_OK();
+    return 0;
+}
+
+int merge_planes(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t st) {
+    if (n == 0) return 0;
+    merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
+    HN_LAUNCH_OK();
+    return 0;
+}
+
+int pack_weight_tc(const float* w_oihw, __nv_bfloat16* out, int Cout, int Cin, int kh, int kw, cudaStream_t st) {
+    const size_t total = (size_t)Cout * Cin * kh * kw;
+    pack_weight_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w_oihw, out, Cout, Cin, kh, kw);
+    HN_LAUNCH_OK();
+    return 0;
+}
+
+// Unit-test / fallback-free convenience: fp32 halo-NHWC in and out, planes built on the fly.
+int conv_tc(const ConvDesc& d, const Act& in, const Act& out, const float* residual, cudaStream_t st) {
+    HN_CHECK(conv_tc_supported(d, in, out), "conv_tc: unsupported shape");
+    const size_t K = (size_t)d.kh * d.kw * d.Cin;
+    const size_t n_in = in.numel(), n_out = out.numel(), n_w = K * d.Cout;
+    __nv_bfloat16 *pin = nullptr, *pout = nullptr, *pres = nullptr, *pw = nullptr;
+    HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pin), n_in * 4, st));
+    HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pout), n_out * 4, st));
+    HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pw), n_w * 4, st));
+    if (residual) HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pres), n_out * 4, st));
+    int rc = split_planes(in.p, pin, n_in, st);
+    if (!rc && residual) rc = split_planes(residual, pres, n_out, st);
+    if (!rc) {
+        pack_weight_tc_from_kn_kernel<<<(unsigned)((n_w + 255) / 256), 256, 0, st>>>(d.w, pw, d.Cout, K);
+        count_launch();
+        if (cudaGetLastError() != cudaSuccess) rc = fail("conv_tc: weight pack launch failed");
+    }
+    if (!rc) rc = conv_tc_planes(d, pw, in, pin, out, pout, nullptr, pres, st);
+    if (!rc) rc = merge_planes(pout, out.p, n_out, st);
+    cudaFreeAsync(pin, st); cudaFreeAsync(pout, st); cudaFreeAsync(pw, st);
+    if (pres) cudaFreeAsync(pres, st);
+    return rc;
+}
+
 }  // namespace hn

@@ -65,6 +65,6 @@ struct ConvDesc {
 int conv_f32(const ConvDesc& d, const Act& in, const Act& out, const float* residual, cudaStream_t st);
 int stem_f32(const float* x_nchw, int B, int in_channels, const float* w_packed, const float* scale,
              const float* shift, const Act& out, cudaStream_t st);
-int maxpool3x3s2(const Act& in, const Act& out, cudaStream_t st);
+int maxpool3x3s2(const Act& in, const Act& out, cudaStream_t st, bool out_split = false);
 
 }  // namespace hn

@@ -10,6 +10,7 @@
 #include <atomic>
 
 #include "hn_common.cuh"
+#include "conv_tc.cuh"
 #include "../../include/horizonnet_b200.h"
 
 #define HN_NUM_CLASSES 8
@@ -23,15 +24,13 @@ void set_error(const std::string& m) { g_err = m; }
 int fail(const std::string& m) { g_err = m; return -1; }
 void count_launch(int n) { g_launches += n; }
 
-int ghc_to_sequence(const Act ghc[4], float* seq, cudaStream_t st);
+int ghc_to_sequence(const Act ghc[4], float* seq, cudaStream_t st, bool split);
 int linear_head(const float* rnn, const float* w, const float* bias, float* bon, float* cor, int T, int B,
                 cudaStream_t st);
 int lstm_layer(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, float* out, int T, int B,
                unsigned int* counters, int* error_flag, cudaStream_t st);
 int pano_stretch_device(const float* img, float* out, int n, int H, int W, int C, const double* kx_dev,
                         const double* ky_dev, double* scratch, int order, cudaStream_t st);
-int conv_tc(const ConvDesc& d, const Act& in, const Act& out, const float* residual, cudaStream_t st);
-bool conv_tc_supported(const ConvDesc& d, const Act& in, const Act& out);
 
 namespace {
 
@@ -113,6 +112,7 @@ struct ConvLayer {
     float* w = nullptr;
     float* scale = nullptr;
     float* shift = nullptr;
+    __nv_bfloat16* wq = nullptr;      // [2][Cout][K] bf16 hi/lo planes for the tcgen05 kernel
 };
 
 }  // namespace
@@ -260,7 +260,9 @@ int pack_conv(hn_model* m, ConvLayer& c, cudaStream_t st) {
         if (m->alloc_t(&c.w, nw)) return -1;
         if (m->alloc_t(&c.scale, c.d.Cout)) return -1;
         if (m->alloc_t(&c.shift, c.d.Cout)) return -1;
+        if (c.d.Cin % 64 == 0 && m->alloc_t(&c.wq, 2 * nw)) return -1;
     }
+    if (c.wq && pack_weight_tc(m->T(c.wkey), c.wq, c.d.Cout, c.d.Cin, c.d.kh, c.d.kw, st)) return -1;
     pack_oihw_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(m->T(c.wkey), c.w, c.d.Cout, c.d.Cin, c.d.kh, c.d.kw);
     HN_LAUNCH_OK();
     fold_bn_kernel<<<(c.d.Cout + 255) / 256, 256, 0, st>>>(
@@ -291,11 +293,16 @@ struct Scope {
 };
 
 int run_conv(hn_model* m, const ConvLayer& c, const Act& in, const Act& out, const float* res, cudaStream_t st,
-             int cls) {
+             int cls, bool out_f32 = false) {
     const double flops = 2.0 * (double)out.B * out.H * out.W * c.d.Cout * c.d.kh * c.d.kw * c.d.Cin;
     Scope sc(m, cls, flops, st);
-    if (m->use_tc && conv_tc_supported(c.d, in, out)) return conv_tc(c.d, in, out, res, st);
-    return conv_f32(c.d, in, out, res, st);
+    if (!m->use_tc) return conv_f32(c.d, in, out, res, st);
+    // tensor-core path: every activation buffer holds bf16 hi/lo planes (same bytes as fp32)
+    if (!c.wq || !conv_tc_supported(c.d, in, out))
+        return fail("hn_model_forward: a convolution of the graph is not covered by the tcgen05 kernel");
+    return conv_tc_planes(c.d, c.wq, in, reinterpret_cast<const __nv_bfloat16*>(in.p), out,
+                          out_f32 ? nullptr : reinterpret_cast<__nv_bfloat16*>(out.p), out_f32 ? out.p : nullptr,
+                          reinterpret_cast<const __nv_bfloat16*>(res), st);
 }
 
 }  // namespace
@@ -398,6 +405,7 @@ int hn_model_finalize(hn_model* m) {
         ConvLayer& c = m->xproj[layer];
         if (!c.w) {
             if (m->alloc_t(&c.w, (size_t)4096 * 1024) || m->alloc_t(&c.scale, 4096) || m->alloc_t(&c.shift, 4096)) return -1;
+            if (m->alloc_t(&c.wq, (size_t)2 * 4096 * 1024)) return -1;
         }
         const std::string l = "_l" + std::to_string(layer);
         // [4096][1024] (fwd rows then reverse rows) -> [K=1024][N=4096]
@@ -409,6 +417,7 @@ int hn_model_finalize(hn_model* m) {
         }
         pack_oihw_kernel<<<(4096 * 1024 + 255) / 256, 256, 0, st>>>(m->XP, c.w, 4096, 1024, 1, 1);
         HN_LAUNCH_OK();
+        if (pack_weight_tc(m->XP, c.wq, 4096, 1024, 1, 1, st)) return -1;
         lstm_bias_kernel<<<16, 256, 0, st>>>(m->T("bi_rnn.bias_ih" + l), m->T("bi_rnn.bias_hh" + l),
                                              m->T("bi_rnn.bias_ih" + l + "_reverse"),
                                              m->T("bi_rnn.bias_hh" + l + "_reverse"), c.scale, c.shift);
@@ -439,7 +448,7 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
     Act cur = mk(m->S1, B, 128, 256, 64);
     {
         Scope sc(m, CLS_POOL, 0.0, st);
-        if (maxpool3x3s2(s0, cur, st)) return -1;
+        if (maxpool3x3s2(s0, cur, st, m->use_tc != 0)) return -1;
     }
 
     // model.py:78-81: layer1..layer4 (torchvision Bottleneck v1.5)
@@ -482,7 +491,7 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
     // model.py:152-155 + :175-178 + :263 -> [T=256][B][1024]
     {
         Scope sc(m, CLS_TAIL, 0.0, st);
-        if (ghc_to_sequence(gout, m->SEQ, st)) return -1;
+        if (ghc_to_sequence(gout, m->SEQ, st, m->use_tc != 0)) return -1;
     }
 
     // model.py:264: 2-layer bidirectional LSTM (eval: dropout = identity)
@@ -491,7 +500,13 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
     for (int layer = 0; layer < 2; ++layer) {
         Act a = mk(const_cast<float*>(lin), 1, 1, 256 * B, 1024, 0);
         Act xp = mk(m->XP, 1, 1, 256 * B, 4096, 0);
-        if (run_conv(m, m->xproj[layer], a, xp, nullptr, st, CLS_XPROJ)) return -1;
+        if (m->use_tc && layer == 1) {
+            // layer-2 projection operand: the fp32 recurrence output as bf16 planes (SEQ is free again)
+            Scope sc(m, CLS_TAIL, 0.0, st);
+            if (split_planes(m->R1, reinterpret_cast<__nv_bfloat16*>(m->SEQ), (size_t)256 * B * 1024, st)) return -1;
+            a.p = m->SEQ;
+        }
+        if (run_conv(m, m->xproj[layer], a, xp, nullptr, st, CLS_XPROJ, true)) return -1;
         {
             Scope sc(m, CLS_LSTM, 2.0 * 256 * B * 2 * 2048 * 512, st);
             if (lstm_layer(m->XP, m->whh[layer][0], m->whh[layer][1], louts[layer], 256, B, m->counters,
@@ -569,7 +584,14 @@ int hn_model_stage(hn_model* m, const char* stage, float* out, long long capacit
             const int C = 256 << l, H = 128 >> l, W = 256 >> l;
             const size_t total = (size_t)B * C * H * W;
             HN_CHECK((long long)total <= capacity, "hn_model_stage: output buffer too small");
-            nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m->F[l], out, B, H, W, C, 1);
+            const float* src = m->F[l];
+            if (m->use_tc) {       // F[l] holds bf16 planes: merge into T1 scratch first (free after the forward)
+                const size_t n = (size_t)B * H * (W + 2) * C;
+                float* tmp = (l == 0) ? m->X[0] : m->T1;
+                if (merge_planes(reinterpret_cast<const __nv_bfloat16*>(m->F[l]), tmp, n, st)) return -1;
+                src = tmp;
+            }
+            nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, out, B, H, W, C, 1);
             HN_LAUNCH_OK();
             dims[0] = B; dims[1] = C; dims[2] = H; dims[3] = W;
             return 0;
@@ -577,6 +599,7 @@ int hn_model_stage(hn_model* m, const char* stage, float* out, long long capacit
     const size_t total = (size_t)256 * B * 1024;
     HN_CHECK((long long)total <= capacity, "hn_model_stage: output buffer too small");
     if (s == "feature") {
+        if (m->use_tc) return fail("hn_model_stage: 'feature' is only kept in fp32 form on the fp32 path");
         seq_to_feature_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m->SEQ, out, 256, B);
         HN_LAUNCH_OK();
         dims[0] = B; dims[1] = 1024; dims[2] = 256; dims[3] = 0;
@@ -595,9 +618,9 @@ void hn_model_destroy(hn_model* m) { delete m; }
 // ---- pano_stretch ------------------------------------------------------------------------------
 int hn_pano_stretch(const float* img, float* out, int n, int h, int w, int c, const double* kx, const double* ky,
                     int order, void* stream) {
-    HN_CHECK(img && out && kx && ky, "hn_pano_stretch: NULL argument");
     HN_CHECK(n >= 0 && h >= 1 && w >= 1, "hn_pano_stretch: bad geometry");
     if (n == 0) return 0;
+    HN_CHECK(img && out && kx && ky, "hn_pano_stretch: NULL argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("hn_pano_stretch: no CUDA device -- libhorizonnet_b200 has no CPU path");
@@ -615,8 +638,8 @@ int hn_pano_stretch(const float* img, float* out, int n, int h, int w, int c, co
 
 int hn_pano_stretch_host(const float* img, float* out, int n, int h, int w, int c, const double* kx,
                          const double* ky, int order) {
-    HN_CHECK(img && out && kx && ky, "hn_pano_stretch_host: NULL argument");
     if (n == 0) return 0;
+    HN_CHECK(img && out && kx && ky, "hn_pano_stretch_host: NULL argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("hn_pano_stretch_host: no CUDA device -- libhorizonnet_b200 has no CPU path");

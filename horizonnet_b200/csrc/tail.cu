@@ -7,6 +7,7 @@
 //   coordinates, i0 = floor(s), l = s - i0 (all exactly representable in fp32; f=1 is the identity).
 // head_kernel: model.py:266-269, Linear(1024 -> 12) + the [T,B,3,4] -> [B,3,T*4] scatter;
 //   channel 0 = cor, 1..2 = bon (model.py:278-279).
+#include <cuda_bf16.h>
 #include "hn_common.cuh"
 
 namespace hn {
@@ -18,6 +19,7 @@ struct GhcSrc {
     int H[4], W[4], C[4], chan_off[4];
 };
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(256) ghc_to_sequence_kernel(const GhcSrc s, float* __restrict__ seq, int B) {
     // seq[t][b][ch], ch = chan_off[s] + c*H + h ; one thread per (t, b, ch), ch fastest
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -36,10 +38,22 @@ __global__ void __launch_bounds__(256) ghc_to_sequence_kernel(const GhcSrc s, fl
     const int i0 = (int)floorf(pos);
     const float l1 = pos - (float)i0;
     const float l0 = 1.f - l1;
-    const float* row = s.p[sc] + ((size_t)b * H + h) * (W + 2) * C;
-    const float v0 = __ldg(row + (size_t)i0 * C + c);
-    const float v1 = __ldg(row + (size_t)min(i0 + 1, W + 1) * C + c);
-    seq[i] = l0 * v0 + l1 * v1;
+    const size_t o0 = (((size_t)b * H + h) * (W + 2) + i0) * C + c;
+    const size_t o1 = (((size_t)b * H + h) * (W + 2) + min(i0 + 1, W + 1)) * C + c;
+    if (!SPLIT) {
+        seq[i] = l0 * __ldg(s.p[sc] + o0) + l1 * __ldg(s.p[sc] + o1);
+    } else {
+        // inputs and output are bf16 hi/lo plane pairs (value = hi + lo)
+        const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(s.p[sc]);
+        const size_t plane = (size_t)B * H * (W + 2) * C;
+        const float v0 = __bfloat162float(pb[o0]) + __bfloat162float(pb[plane + o0]);
+        const float v1 = __bfloat162float(pb[o1]) + __bfloat162float(pb[plane + o1]);
+        const float v = l0 * v0 + l1 * v1;
+        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(seq);
+        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+        ob[i] = hi;
+        ob[total + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+    }
 }
 
 __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ rnn,   // [T][B][1024]
@@ -89,7 +103,7 @@ __global__ void __launch_bounds__(256) head_kernel(const float* __restrict__ rnn
 
 }  // namespace
 
-int ghc_to_sequence(const Act ghc[4], float* seq, cudaStream_t st) {
+int ghc_to_sequence(const Act ghc[4], float* seq, cudaStream_t st, bool split) {
     GhcSrc s;
     int off = 0;
     for (int i = 0; i < 4; ++i) {
@@ -99,14 +113,16 @@ int ghc_to_sequence(const Act ghc[4], float* seq, cudaStream_t st) {
     }
     HN_CHECK(off == 1024, "ghc_to_sequence: the 4 scales must flatten to 1024 channels (model.py:218)");
     const size_t total = (size_t)256 * ghc[0].B * 1024;
-    ghc_to_sequence_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s, seq, ghc[0].B);
+    if (split)
+        ghc_to_sequence_kernel<true><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s, seq, ghc[0].B);
+    else
+        ghc_to_sequence_kernel<false><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(s, seq, ghc[0].B);
     HN_LAUNCH_OK();
     return 0;
 }
 
 int linear_head(const float* rnn, const float* w, const float* bias, float* bon, float* cor, int T, int B,
                 cudaStream_t st) {
-    HN_CUDA_OK(cudaFuncSetAttribute(head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 0));
     head_kernel<<<(T * B + 7) / 8, 256, 0, st>>>(rnn, w, bias, bon, cor, T, B);
     HN_LAUNCH_OK();
     return 0;
