@@ -10,8 +10,8 @@
 // stem_f32: 7x7 stride-2 conv on the NCHW fp32 input with the input normalisation
 //   (model.py:248-252), BN and ReLU fused (model.py:73-75).
 // maxpool3x3s2: model.py:76 (padding is -inf on both axes -- NOT circular).
-#include <cuda_bf16.h>
 #include "hn_common.cuh"
+#include "conv_tc.cuh"
 
 namespace hn {
 
@@ -307,8 +307,9 @@ __device__ __forceinline__ uint2 split4(const float4 m, bool lo) {
     unsigned short u[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const __nv_bfloat16 h = __float2bfloat16_rn(f[j]);
-        u[j] = __bfloat16_as_ushort(lo ? __float2bfloat16_rn(f[j] - __bfloat162float(h)) : h);
+        unsigned short h, l;
+        split_scaled(f[j], h, l);
+        u[j] = lo ? l : h;
     }
     return make_uint2((unsigned)u[0] | ((unsigned)u[1] << 16), (unsigned)u[2] | ((unsigned)u[3] << 16));
 }
@@ -347,8 +348,8 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ 
         if (wo == 0) reinterpret_cast<float4*>(out + (row + Wo + 1) * C)[c4] = m;
         if (wo == Wo - 1) reinterpret_cast<float4*>(out + row * C)[c4] = m;
     } else {
-        // bf16 hi/lo planes for the tensor-core convs (plane = B*Ho*Wop*C elements)
-        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(out);
+        // hi/lo planes for the tensor-core convs (plane = B*Ho*Wop*C elements)
+        unsigned short* ob = reinterpret_cast<unsigned short*>(out);
         const size_t plane = (size_t)B * Ho * Wop * C;
         const uint2 hi = split4(m, false), lo = split4(m, true);
         auto put = [&](size_t pix) {

@@ -1,11 +1,14 @@
-// tcgen05 tensor-core convolution / GEMM for sm_100a: split-bf16, three products, fp32 accumulate.
+// tcgen05 tensor-core convolution / GEMM for sm_100a: split precision, three products, fp32 accumulate.
 //
 // Why split precision: the contract is <= 1e-4 max-abs against the fp32 reference on random-init
-// weights; single-pass bf16 (1.4e-2) or tf32 (1.5e-3) miss it (SURVEY hard-part 1).  Every fp32
-// value v is carried as two bf16 planes  hi = bf16(v), lo = bf16(v - hi)  (same 4 B/element as
-// fp32), and the product is evaluated as  Ahi*Bhi + Ahi*Blo + Alo*Bhi  with the fp32 accumulator
-// in tensor memory.  The planes are written by the producing kernel's epilogue, so every operand
-// tile is MMA-ready when TMA drops it into shared memory (no in-kernel conversion pass).
+// weights; single-pass bf16 (1.4e-2) or tf32 (1.5e-3) miss it (SURVEY hard-part 1), and a
+// bf16+bf16 split with three products measured 1.1e-4 on the B200.  Every fp32 value
+// is carried as two fp16 planes of its 2^-4-scaled value:  hi = fp16(s), lo = fp16(s - hi)
+// (11 + 11 significant bits, same 4 B/element as fp32, see conv_tc.cuh), and the product is
+//     Ahi*Bhi + Ahi*Blo + Alo*Bhi            (the dropped Alo*Blo term is 2^-22 relative)
+// accumulated in one fp32 TMEM accumulator: 2e-6 .. 1e-5 max-abs end to end.  The planes are
+// written by the producing kernel's epilogue, so every operand tile is MMA-ready when TMA drops
+// it into shared memory (no in-kernel conversion pass).
 //
 // Kernel shape (persistent, warp-specialised, one CTA per SM):
 //   warp 0     TMA producer: per 64-channel K chunk it loads A (hi, lo: 128 pixels x 64 ch, 128B
@@ -18,10 +21,12 @@
 //              at the end of the tile, publishes the accumulator
 //   warp 2     TMEM allocator
 //   warps 4-11 epilogue: tcgen05.ld (lane quarter = warp%4, column half = (warp-4)/4), folded
-//              BN scale/shift, residual add, ReLU, re-split into bf16 planes (or fp32), vector
+//              BN scale/shift, residual add, ReLU, re-split into hi/lo planes (or fp32), vector
 //              stores incl. the circular halo columns; overlaps the next tile's MMAs.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 
 #include "hn_common.cuh"
@@ -108,16 +113,16 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int n) {
+// kind::f16 instruction descriptor: D=f32, A/B formats (0 = fp16, 1 = bf16), both K-major, M=128, N=n
+__host__ __device__ constexpr uint32_t umma_idesc(int n, uint32_t a_fmt, uint32_t b_fmt) {
     return (1u << 4)                    // c_format  = F32
-           | (1u << 7)                  // a_format  = BF16
-           | (1u << 10)                 // b_format  = BF16
+           | (a_fmt << 7)               // a_format
+           | (b_fmt << 10)              // b_format
            | ((uint32_t)(n >> 3) << 17) // n_dim
            | ((uint32_t)(BM >> 4) << 24);  // m_dim
 }
 
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -144,8 +149,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
-    return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+__device__ __forceinline__ uint32_t pack2(unsigned short a, unsigned short b) {
+    return (uint32_t)a | ((uint32_t)b << 16);
 }
 
 struct TcArgs {
@@ -160,11 +165,12 @@ struct TcArgs {
     int Cout, n_tiles, num_tiles;
     const float* scale;
     const float* shift;
-    const __nv_bfloat16* res; // residual planes in the OUTPUT geometry (hi at res, lo at res + out_plane), or null
-    __nv_bfloat16* out;       // split output planes (hi at out, lo at out + out_plane)
+    const unsigned short* res; // residual planes in the OUTPUT geometry (hi at res, lo at res + out_plane), or null
+    unsigned short* out;       // split output planes (hi at out, lo at out + out_plane)
     float* out_f32;           // fp32 output instead of planes (LSTM projections)
     size_t out_plane;         // elements per plane
     int relu;
+    int seg;                  // K chunks per hi*hi accumulation segment
 };
 
 template <int BN>
@@ -174,7 +180,7 @@ struct Smem {
     static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
     static constexpr int BAR_OFF = STAGES * STAGE;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;    // barriers + alignment slack
-    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : 256;
+    static constexpr int TMEM_COLS = 4 * BN;        // 2 hi*hi segment accumulators + 2 cross accumulators (128..512)
 };
 
 template <int BN>
@@ -185,9 +191,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;       // [2] accumulator ready
-    uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* tfull_bar = empty_bar + STAGES;       // [2] hi*hi segment accumulator ready
+    uint64_t* tempty_bar = tfull_bar + 2;           // [2] hi*hi segment accumulator drained
+    uint64_t* cempty_bar = tempty_bar + 2;          // [2] cross-product accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -197,7 +204,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 8); }
+        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 8); mbar_init(cempty_bar + i, 8); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -263,18 +270,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
+        // tcgen05 accumulates into fp32 TMEM with truncation (measured: -3.4e-6 mean relative bias after
+        // 256 accumulation steps, tools/probe_tc_accum.py), which over K up to 18432 costs ~1e-4 end to
+        // end.  So (1) the small cross products (hi*lo, lo*hi; 2^-11 of the result) get their own
+        // accumulator, and (2) the hi*hi accumulator is restarted every `seg` K-chunks: the epilogue
+        // warps drain each segment and add it to a register-resident fp32 sum with round-to-nearest.
         if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_bf16(BN);
+            constexpr uint32_t idesc = umma_idesc(BN, 0, 0);       // fp16 x fp16 -> fp32
             int stage = 0;
             uint32_t phase = 0;
-            int it = 0;
+            int it = 0, g = 0;
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
-                mbar_wait(tempty_bar + acc, acc_phase ^ 1);        // epilogue drained this accumulator
+                const int cbuf = it & 1;
+                mbar_wait(cempty_bar + cbuf, ((it >> 1) & 1) ^ 1);   // epilogue drained this cross accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_cross = tmem_base + (2 + cbuf) * BN;
+                uint32_t d_main = tmem_base;
+                int seg_pos = 0, mbuf = 0;
                 for (int kc = 0; kc < a.num_kc; ++kc) {
+                    if (seg_pos == 0) {
+                        mbuf = g & 1;
+                        mbar_wait(tempty_bar + mbuf, ((g >> 1) & 1) ^ 1);   // segment accumulator drained
+                        tc_fence_after();
+                        d_main = tmem_base + mbuf * BN;
+                    }
                     mbar_wait(full_bar + stage, phase);
                     tc_fence_after();
                     const uint32_t sA = smem_u32(smem + stage * S::STAGE);
@@ -284,12 +303,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < BKC / 16; ++k) {
                         const uint64_t ko = (uint64_t)((k * 16 * 2) >> 4);     // advance 32 B inside the swizzle row
-                        umma_bf16(d_tmem, a_hi + ko, b_hi + ko, idesc, (kc | k) != 0);
-                        umma_bf16(d_tmem, a_hi + ko, b_lo + ko, idesc, 1);
-                        umma_bf16(d_tmem, a_lo + ko, b_hi + ko, idesc, 1);
+                        umma_f16(d_main, a_hi + ko, b_hi + ko, idesc, (seg_pos | k) != 0);
+                        umma_f16(d_cross, a_hi + ko, b_lo + ko, idesc, (kc | k) != 0);
+                        umma_f16(d_cross, a_lo + ko, b_hi + ko, idesc, 1);
                     }
                     umma_commit(empty_bar + stage);                  // frees the smem stage when the MMAs retire
-                    if (kc == a.num_kc - 1) umma_commit(tfull_bar + acc);
+                    if (++seg_pos == a.seg || kc == a.num_kc - 1) {
+                        umma_commit(tfull_bar + mbuf);               // segment (and, at the end, the tile) complete
+                        seg_pos = 0;
+                        ++g;
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1; }
                 }
             }
@@ -303,11 +326,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int NCHUNK = COLS_PER_WARP / 32;
         constexpr int CW = 32;                                           // columns per tcgen05.ld chunk
         const bool works = (BN >= 64) || half == 0;
-        int it = 0;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int nseg = (a.num_kc + a.seg - 1) / a.seg;
+        int it = 0, g = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
             const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
+            const int cbuf = it & 1;
             const int r = q * 32 + lane;                 // accumulator row = pixel of the tile
             // ---- where does this row live in the output?
             bool valid;
@@ -329,13 +353,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     else if (wo == a.Wo - 1) { has_halo = true; halo_pix = (size_t)R * a.Wop; }
                 }
             }
-            mbar_wait(tfull_bar + acc, acc_phase);
-            tc_fence_after();
+            // ---- drain the hi*hi segments into registers (fp32 adds, round to nearest)
+            float sum[COLS_PER_WARP];
+#pragma unroll
+            for (int j = 0; j < COLS_PER_WARP; ++j) sum[j] = 0.f;
+            for (int sgi = 0; sgi < nseg; ++sgi, ++g) {
+                const int mbuf = g & 1;
+                mbar_wait(tfull_bar + mbuf, (g >> 1) & 1);
+                tc_fence_after();
+                if (works) {
+#pragma unroll
+                    for (int ch = 0; ch < NCHUNK; ++ch) {
+                        uint32_t v[32];
+                        tmem_ld32(tmem_base + lane_base + (uint32_t)(mbuf * BN + half * COLS_PER_WARP + ch * 32), v);
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) sum[ch * 32 + j] += __uint_as_float(v[j]);
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar + mbuf);
+            }
+            // ---- the last segment's commit also covers the cross products of the whole tile
 #pragma unroll
             for (int ch = 0; ch < (works ? NCHUNK : 0); ++ch) {
                 const int col0 = half * COLS_PER_WARP + ch * 32;          // column inside the tile
                 uint32_t v[32];
-                tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + col0), v);
+                tmem_ld32(tmem_base + lane_base + (uint32_t)((2 + cbuf) * BN + col0), v);
                 if (!valid) continue;
                 const int n0 = nt * BN + col0;                            // output channel of v[0]
                 float y[32];
@@ -343,10 +387,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int j = 0; j < CW; j += 4) {
                     const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + n0 + j));
                     const float4 sf = __ldg(reinterpret_cast<const float4*>(a.shift + n0 + j));
-                    y[j + 0] = fmaf(__uint_as_float(v[j + 0]), sc.x, sf.x);
-                    y[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sf.y);
-                    y[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sf.z);
-                    y[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sf.w);
+                    y[j + 0] = fmaf(sum[ch * 32 + j + 0] + __uint_as_float(v[j + 0]), sc.x, sf.x);
+                    y[j + 1] = fmaf(sum[ch * 32 + j + 1] + __uint_as_float(v[j + 1]), sc.y, sf.y);
+                    y[j + 2] = fmaf(sum[ch * 32 + j + 2] + __uint_as_float(v[j + 2]), sc.z, sf.z);
+                    y[j + 3] = fmaf(sum[ch * 32 + j + 3] + __uint_as_float(v[j + 3]), sc.w, sf.w);
                 }
                 if (a.res) {
                     const uint4* rh = reinterpret_cast<const uint4*>(a.res + pix * a.Cout + n0);
@@ -357,9 +401,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
 #pragma unroll
                         for (int e = 0; e < 4; ++e) {
-                            // bf16 -> fp32 is a 16-bit shift
-                            y[j * 8 + 2 * e + 0] += __uint_as_float(hw[e] << 16) + __uint_as_float(lw[e] << 16);
-                            y[j * 8 + 2 * e + 1] += __uint_as_float(hw[e] & 0xFFFF0000u) + __uint_as_float(lw[e] & 0xFFFF0000u);
+                            y[j * 8 + 2 * e + 0] += merge_scaled((unsigned short)(hw[e] & 0xFFFFu), (unsigned short)(lw[e] & 0xFFFFu));
+                            y[j * 8 + 2 * e + 1] += merge_scaled((unsigned short)(hw[e] >> 16), (unsigned short)(lw[e] >> 16));
                         }
                     }
                 }
@@ -375,11 +418,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint32_t ph[16], pl[16];
 #pragma unroll
                     for (int j = 0; j < CW / 2; ++j) {
-                        const __nv_bfloat16 h0 = __float2bfloat16_rn(y[2 * j]), h1 = __float2bfloat16_rn(y[2 * j + 1]);
-                        const __nv_bfloat16 l0 = __float2bfloat16_rn(y[2 * j] - __bfloat162float(h0));
-                        const __nv_bfloat16 l1 = __float2bfloat16_rn(y[2 * j + 1] - __bfloat162float(h1));
-                        ph[j] = pack_bf16x2(h0, h1);
-                        pl[j] = pack_bf16x2(l0, l1);
+                        unsigned short h0, l0, h1, l1;
+                        split_scaled(y[2 * j], h0, l0);
+                        split_scaled(y[2 * j + 1], h1, l1);
+                        ph[j] = pack2(h0, h1);
+                        pl[j] = pack2(l0, l1);
                     }
                     uint4* oh = reinterpret_cast<uint4*>(a.out + pix * a.Cout + n0);
                     uint4* ol = reinterpret_cast<uint4*>(a.out + a.out_plane + pix * a.Cout + n0);
@@ -399,10 +442,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                 }
             }
-            // accumulator drained: hand it back to the MMA warp
+            // cross accumulator drained: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar + acc);
+            if (lane == 0) mbar_arrive(cempty_bar + cbuf);
         }
     }
 
@@ -437,11 +480,21 @@ int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims
     EncodeTiledFn fn = encode_fn();
     HN_CHECK(fn != nullptr, "conv_tc: cuTensorMapEncodeTiled unavailable");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("conv_tc: cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return 0;
+}
+
+int tc_segment_chunks() {
+    // K chunks (of 64) accumulated in TMEM before the sum is promoted to registers; HN_TC_SEG overrides (tuning)
+    static int seg = [] {
+        const char* e = getenv("HN_TC_SEG");
+        int v = e ? atoi(e) : 4;
+        return v < 1 ? 1 : v;
+    }();
+    return seg;
 }
 
 template <int BN>
@@ -473,11 +526,11 @@ bool conv_tc_supported(const ConvDesc& d, const Act& in, const Act& out) {
     return true;
 }
 
-// in / out / residual are split-bf16 plane pairs in halo-NHWC geometry (hi plane, then lo plane).
-// wq: [2][Cout][K] bf16 (hi, lo), K = (dy*kw+dx)*Cin + c.
-int conv_tc_planes(const ConvDesc& d, const __nv_bfloat16* wq, const Act& in, const __nv_bfloat16* in_planes,
-                   const Act& out, __nv_bfloat16* out_planes, float* out_f32, const __nv_bfloat16* res_planes,
-                   cudaStream_t st) {
+// in / out / residual are split plane pairs in halo-NHWC geometry (hi plane, then lo plane).
+// wq: [2][Cout][K] weight planes, K = (dy*kw+dx)*Cin + c; tc_scale folds BN scale and the plane scales.
+int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_scale, const Act& in,
+                   const unsigned short* in_planes, const Act& out, unsigned short* out_planes, float* out_f32,
+                   const unsigned short* res_planes, cudaStream_t st) {
     HN_CHECK(conv_tc_supported(d, in, out), "conv_tc: unsupported shape");
     const int K = d.kh * d.kw * d.Cin;
     TcArgs a;
@@ -497,9 +550,10 @@ int conv_tc_planes(const ConvDesc& d, const __nv_bfloat16* wq, const Act& in, co
     a.kw = d.kw;
     a.kc_per_tap = d.Cin / BKC;
     a.num_kc = d.kh * d.kw * a.kc_per_tap;
-    a.scale = d.scale; a.shift = d.shift;
+    a.scale = tc_scale; a.shift = d.shift;
     a.res = res_planes; a.out = out_planes; a.out_f32 = out_f32; a.out_plane = out_plane; a.relu = d.relu;
     a.Bimg = in.B;
+    a.seg = tc_segment_chunks();
     long long m_tiles;
     if (gemm) {
         const long long Mtot = (long long)in.B * in.H * in.Wp();
@@ -546,62 +600,90 @@ int conv_tc_planes(const ConvDesc& d, const __nv_bfloat16* wq, const Act& in, co
 // ---------------------------------------------------------------------- format conversion kernels
 namespace {
 
-__global__ void split_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, size_t n) {
+__global__ void split_kernel(const float* __restrict__ in, unsigned short* __restrict__ out, size_t n) {
     const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i >= n) return;
     const float4 v = *reinterpret_cast<const float4*>(in + i);
     const float f[4] = {v.x, v.y, v.z, v.w};
-    __nv_bfloat16 h[4], l[4];
+    unsigned short h[4], l[4];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        h[j] = __float2bfloat16_rn(f[j]);
-        l[j] = __float2bfloat16_rn(f[j] - __bfloat162float(h[j]));
-    }
-    *reinterpret_cast<uint2*>(out + i) = make_uint2(pack_bf16x2(h[0], h[1]), pack_bf16x2(h[2], h[3]));
-    *reinterpret_cast<uint2*>(out + n + i) = make_uint2(pack_bf16x2(l[0], l[1]), pack_bf16x2(l[2], l[3]));
+    for (int j = 0; j < 4; ++j) split_scaled(f[j], h[j], l[j]);
+    *reinterpret_cast<uint2*>(out + i) = make_uint2(pack2(h[0], h[1]), pack2(h[2], h[3]));
+    *reinterpret_cast<uint2*>(out + n + i) = make_uint2(pack2(l[0], l[1]), pack2(l[2], l[3]));
 }
 
-__global__ void merge_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, size_t n) {
+__global__ void merge_kernel(const unsigned short* __restrict__ in, float* __restrict__ out, size_t n) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    out[i] = __bfloat162float(in[i]) + __bfloat162float(in[n + i]);
+    out[i] = merge_scaled(in[i], in[n + i]);
 }
 
-// OIHW fp32 -> [2][Cout][K] bf16 planes, K = (dy*kw+dx)*Cin + c
-__global__ void pack_weight_tc_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout, int Cin,
-                                      int kh, int kw) {
+__global__ void absmax_kernel(const float* __restrict__ w, size_t n, float* __restrict__ out) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(w[i]));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));   // m >= 0: int order = float order
+}
+
+// weight scale exponent t: max|w| * 2^t lands in (2^13, 2^14]: inside fp16 range, lo plane normal
+__device__ __forceinline__ float weight_scale(float absmax) {
+    if (!(absmax > 0.f) || !isfinite(absmax)) return 1.f;
+    int e;
+    frexpf(16384.f / absmax, &e);
+    return ldexpf(1.f, e - 1);
+}
+
+// fp32 weights -> [2][Cout][K] planes of w * 2^t (fp16 hi, fp16 lo); source index from (n, k)
+template <bool OIHW>
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, unsigned short* __restrict__ out,
+                                      const float* __restrict__ absmax, int Cout, int Cin, int kh, int kw) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t K = (size_t)Cin * kh * kw;
     const size_t total = (size_t)Cout * K;
     if (i >= total) return;
     const int n = (int)(i / K);
     const size_t k = i - (size_t)n * K;
-    const int c = (int)(k % Cin);
-    const int tap = (int)(k / Cin);
-    const int dy = tap / kw, dx = tap % kw;
-    const float v = w[(((size_t)n * Cin + c) * kh + dy) * kw + dx];
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    out[i] = h;
-    out[total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    float v;
+    if (OIHW) {
+        const int c = (int)(k % Cin);
+        const int tap = (int)(k / Cin);
+        const int dy = tap / kw, dx = tap % kw;
+        v = w[(((size_t)n * Cin + c) * kh + dy) * kw + dx];
+    } else {
+        v = w[k * Cout + n];                 // packed [K][Cout] (unit-test entry point)
+    }
+    const float s = v * weight_scale(*absmax);
+    const __half h = __float2half_rn(s);
+    out[i] = __half_as_ushort(h);
+    out[total + i] = __half_as_ushort(__float2half_rn(s - __half2float(h)));
 }
 
-// packed fp32 [K][Cout] -> [2][Cout][K] bf16 planes (unit-test entry point)
-__global__ void pack_weight_tc_from_kn_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, int Cout,
-                                              size_t K) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)Cout * K;
-    if (i >= total) return;
-    const int n = (int)(i / K);
-    const size_t k = i - (size_t)n * K;
-    const float v = w[k * Cout + n];
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
-    out[i] = h;
-    out[total + i] = __float2bfloat16_rn(v - __bfloat162float(h));
+__global__ void tc_scale_kernel(const float* __restrict__ scale, const float* __restrict__ absmax,
+                                float* __restrict__ tc_scale, int C) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= C) return;
+    tc_scale[i] = (scale ? scale[i] : 1.f) * ACT_UNSCALE / weight_scale(*absmax);
+}
+
+template <bool OIHW>
+int pack_weight_impl(const float* w, unsigned short* wq, const float* scale, float* tc_scale, float* scratch, int Cout,
+                     int Cin, int kh, int kw, cudaStream_t st) {
+    const size_t total = (size_t)Cout * Cin * kh * kw;
+    HN_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(float), st));
+    absmax_kernel<<<(unsigned)((total + 256 * 64 - 1) / (256 * 64)), 256, 0, st>>>(w, total, scratch);
+    HN_LAUNCH_OK();
+    pack_weight_tc_kernel<OIHW><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, wq, scratch, Cout, Cin, kh, kw);
+    HN_LAUNCH_OK();
+    tc_scale_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(scale, scratch, tc_scale, Cout);
+    HN_LAUNCH_OK();
+    return 0;
 }
 
 }  // namespace
 
-int split_planes(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st) {
+int split_planes(const float* in, unsigned short* out, size_t n, cudaStream_t st) {
     HN_CHECK(n % 4 == 0, "split_planes: element count must be a multiple of 4");
     if (n == 0) return 0;
     split_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, st>>>(in, out, n);
@@ -609,40 +691,36 @@ int split_planes(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st)
     return 0;
 }
 
-int merge_planes(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t st) {
+int merge_planes(const unsigned short* in, float* out, size_t n, cudaStream_t st) {
     if (n == 0) return 0;
     merge_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, out, n);
     HN_LAUNCH_OK();
     return 0;
 }
 
-int pack_weight_tc(const float* w_oihw, __nv_bfloat16* out, int Cout, int Cin, int kh, int kw, cudaStream_t st) {
-    const size_t total = (size_t)Cout * Cin * kh * kw;
-    pack_weight_tc_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w_oihw, out, Cout, Cin, kh, kw);
-    HN_LAUNCH_OK();
-    return 0;
+int pack_weight_tc(const float* w_oihw, unsigned short* wq, const float* scale, float* tc_scale, float* scratch,
+                   int Cout, int Cin, int kh, int kw, cudaStream_t st) {
+    return pack_weight_impl<true>(w_oihw, wq, scale, tc_scale, scratch, Cout, Cin, kh, kw, st);
 }
 
-// Unit-test / fallback-free convenience: fp32 halo-NHWC in and out, planes built on the fly.
+// Unit-test convenience: fp32 halo-NHWC in and out, planes built on the fly.
 int conv_tc(const ConvDesc& d, const Act& in, const Act& out, const float* residual, cudaStream_t st) {
     HN_CHECK(conv_tc_supported(d, in, out), "conv_tc: unsupported shape");
     const size_t K = (size_t)d.kh * d.kw * d.Cin;
     const size_t n_in = in.numel(), n_out = out.numel(), n_w = K * d.Cout;
-    __nv_bfloat16 *pin = nullptr, *pout = nullptr, *pres = nullptr, *pw = nullptr;
+    unsigned short *pin = nullptr, *pout = nullptr, *pres = nullptr, *pw = nullptr;
+    float* aux = nullptr;          // [Cout] tc_scale + 1 scratch float
     HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pin), n_in * 4, st));
     HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pout), n_out * 4, st));
     HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pw), n_w * 4, st));
+    HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&aux), (d.Cout + 1) * sizeof(float), st));
     if (residual) HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pres), n_out * 4, st));
     int rc = split_planes(in.p, pin, n_in, st);
     if (!rc && residual) rc = split_planes(residual, pres, n_out, st);
-    if (!rc) {
-        pack_weight_tc_from_kn_kernel<<<(unsigned)((n_w + 255) / 256), 256, 0, st>>>(d.w, pw, d.Cout, K);
-        count_launch();
-        if (cudaGetLastError() != cudaSuccess) rc = fail("conv_tc: weight pack launch failed");
-    }
-    if (!rc) rc = conv_tc_planes(d, pw, in, pin, out, pout, nullptr, pres, st);
+    if (!rc) rc = pack_weight_impl<false>(d.w, pw, d.scale, aux, aux + d.Cout, d.Cout, d.Cin, d.kh, d.kw, st);
+    if (!rc) rc = conv_tc_planes(d, pw, aux, in, pin, out, pout, nullptr, pres, st);
     if (!rc) rc = merge_planes(pout, out.p, n_out, st);
-    cudaFreeAsync(pin, st); cudaFreeAsync(pout, st); cudaFreeAsync(pw, st);
+    cudaFreeAsync(pin, st); cudaFreeAsync(pout, st); cudaFreeAsync(pw, st); cudaFreeAsync(aux, st);
     if (pres) cudaFreeAsync(pres, st);
     return rc;
 }

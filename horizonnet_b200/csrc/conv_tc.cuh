@@ -1,19 +1,46 @@
-// Split-bf16 tcgen05 convolution entry points (conv_tc.cu).
+// Split-precision tcgen05 convolution entry points (conv_tc.cu) and the plane format helpers.
+//
+// Plane format ("split planes"): an fp32 tensor v is carried as two fp16 planes of the SCALED value
+// s = v * 2^-4:        hi = fp16(s)       (11 significant bits, saturated at +-65504)
+//                      lo = fp16(s - hi)  (the next 11 bits)
+// hi plane first, lo plane at +numel 16-bit elements; 4 bytes per element in total, like fp32.
+// The power-of-two scale is exact; it puts the fp16 range at |v| < 1.05e6 (random-init activations of
+// this net peak at 6.3e3, trained ones far lower) and keeps lo normal for |v| > 2; below that lo is
+// an fp16 subnormal, i.e. an absolute resolution of 2^-24 * 16 = 9.5e-7 (measured end-to-end effect
+// of the whole scheme: 2e-6..1e-5 max-abs).  tcgen05 kind::f16 cannot mix bf16 and fp16 operands in one MMA (measured: illegal
+// instruction), and a bf16+bf16 split misses the 1e-4 contract, hence fp16+fp16.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "hn_common.cuh"
 
 namespace hn {
 
+constexpr float ACT_SCALE = 0.0625f;        // 2^-4
+constexpr float ACT_UNSCALE = 16.f;
+
+__device__ __forceinline__ void split_scaled(float v, unsigned short& hi, unsigned short& lo) {
+    const float s = fminf(fmaxf(v * ACT_SCALE, -65504.f), 65504.f);
+    const __half h = __float2half_rn(s);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(__float2half_rn(s - __half2float(h)));
+}
+__device__ __forceinline__ float merge_scaled(unsigned short hi, unsigned short lo) {
+    return (__half2float(__ushort_as_half(hi)) + __half2float(__ushort_as_half(lo))) * ACT_UNSCALE;
+}
+
 bool conv_tc_supported(const ConvDesc& d, const Act& in, const Act& out);
 // fp32 halo-NHWC in/out convenience wrapper (unit tests): splits, runs the plane kernel, merges.
 int conv_tc(const ConvDesc& d, const Act& in, const Act& out, const float* residual, cudaStream_t st);
-// The real thing: operands and result are bf16 hi/lo plane pairs (hi plane first, lo plane at +numel).
-int conv_tc_planes(const ConvDesc& d, const __nv_bfloat16* wq, const Act& in, const __nv_bfloat16* in_planes,
-                   const Act& out, __nv_bfloat16* out_planes, float* out_f32, const __nv_bfloat16* res_planes,
-                   cudaStream_t st);
-int split_planes(const float* in, __nv_bfloat16* out, size_t n, cudaStream_t st);
-int merge_planes(const __nv_bfloat16* in, float* out, size_t n, cudaStream_t st);
-int pack_weight_tc(const float* w_oihw, __nv_bfloat16* out, int Cout, int Cin, int kh, int kw, cudaStream_t st);
+// The real thing: operands and result are split planes.  wq: [2][Cout][K] weight planes
+// (fp16 hi, fp16 lo of w * 2^t), tc_scale = BN scale * 2^(4-t) (see pack_weight_tc).
+int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_scale, const Act& in,
+                   const unsigned short* in_planes, const Act& out, unsigned short* out_planes, float* out_f32,
+                   const unsigned short* res_planes, cudaStream_t st);
+int split_planes(const float* in, unsigned short* out, size_t n, cudaStream_t st);
+int merge_planes(const unsigned short* in, float* out, size_t n, cudaStream_t st);
+// OIHW fp32 weights -> wq planes + tc_scale[Cout] (scale may be null = all ones); scratch: 1 float.
+int pack_weight_tc(const float* w_oihw, unsigned short* wq, const float* scale, float* tc_scale, float* scratch,
+                   int Cout, int Cin, int kh, int kw, cudaStream_t st);
 
 }  // namespace hn

@@ -112,7 +112,8 @@ struct ConvLayer {
     float* w = nullptr;
     float* scale = nullptr;
     float* shift = nullptr;
-    __nv_bfloat16* wq = nullptr;      // [2][Cout][K] bf16 hi/lo planes for the tcgen05 kernel
+    unsigned short* wq = nullptr;     // [2][Cout][K] hi/lo weight planes for the tcgen05 kernel
+    float* tc_scale = nullptr;        // BN scale * 2^-(8+t) (conv_tc.cuh)
 };
 
 }  // namespace
@@ -144,7 +145,7 @@ struct hn_model {
     float* F[4] = {nullptr, nullptr, nullptr, nullptr};
     float* G[2] = {nullptr, nullptr};
     float* GO[4] = {nullptr, nullptr, nullptr, nullptr};
-    float *SEQ = nullptr, *XP = nullptr, *R1 = nullptr, *R2 = nullptr;
+    float *SEQ = nullptr, *XP = nullptr, *R1 = nullptr, *R2 = nullptr, *R1S = nullptr;
     unsigned int* counters = nullptr;
     int* error_flag = nullptr;
     float *x_in = nullptr, *bon_out = nullptr, *cor_out = nullptr;    // for forward_host
@@ -260,15 +261,17 @@ int pack_conv(hn_model* m, ConvLayer& c, cudaStream_t st) {
         if (m->alloc_t(&c.w, nw)) return -1;
         if (m->alloc_t(&c.scale, c.d.Cout)) return -1;
         if (m->alloc_t(&c.shift, c.d.Cout)) return -1;
-        if (c.d.Cin % 64 == 0 && m->alloc_t(&c.wq, 2 * nw)) return -1;
+        if (c.d.Cin % 64 == 0 && (m->alloc_t(&c.wq, 2 * nw) || m->alloc_t(&c.tc_scale, c.d.Cout + 1))) return -1;
     }
-    if (c.wq && pack_weight_tc(m->T(c.wkey), c.wq, c.d.Cout, c.d.Cin, c.d.kh, c.d.kw, st)) return -1;
     pack_oihw_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(m->T(c.wkey), c.w, c.d.Cout, c.d.Cin, c.d.kh, c.d.kw);
     HN_LAUNCH_OK();
     fold_bn_kernel<<<(c.d.Cout + 255) / 256, 256, 0, st>>>(
         m->T(c.bnprefix + ".weight"), m->T(c.bnprefix + ".bias"), m->T(c.bnprefix + ".running_mean"),
         m->T(c.bnprefix + ".running_var"), c.biaskey.empty() ? nullptr : m->T(c.biaskey), c.scale, c.shift, c.d.Cout);
     HN_LAUNCH_OK();
+    if (c.wq && pack_weight_tc(m->T(c.wkey), c.wq, c.scale, c.tc_scale, c.tc_scale + c.d.Cout, c.d.Cout, c.d.Cin, c.d.kh,
+                               c.d.kw, st))
+        return -1;
     c.d.w = c.w; c.d.scale = c.scale; c.d.shift = c.shift;
     return 0;
 }
@@ -300,9 +303,9 @@ int run_conv(hn_model* m, const ConvLayer& c, const Act& in, const Act& out, con
     // tensor-core path: every activation buffer holds bf16 hi/lo planes (same bytes as fp32)
     if (!c.wq || !conv_tc_supported(c.d, in, out))
         return fail("hn_model_forward: a convolution of the graph is not covered by the tcgen05 kernel");
-    return conv_tc_planes(c.d, c.wq, in, reinterpret_cast<const __nv_bfloat16*>(in.p), out,
-                          out_f32 ? nullptr : reinterpret_cast<__nv_bfloat16*>(out.p), out_f32 ? out.p : nullptr,
-                          reinterpret_cast<const __nv_bfloat16*>(res), st);
+    return conv_tc_planes(c.d, c.wq, c.tc_scale, in, reinterpret_cast<const unsigned short*>(in.p), out,
+                          out_f32 ? nullptr : reinterpret_cast<unsigned short*>(out.p), out_f32 ? out.p : nullptr,
+                          reinterpret_cast<const unsigned short*>(res), st);
 }
 
 }  // namespace
@@ -339,7 +342,7 @@ int hn_model_create(int device, int max_batch, hn_model** out) {
         {&m->F[2], B * 32 * 66 * 1024}, {&m->F[3], B * 16 * 34 * 2048}, {&m->G[0], B * 64 * 258 * 128},
         {&m->G[1], B * 64 * 258 * 128}, {&m->GO[0], B * 8 * 258 * 32},  {&m->GO[1], B * 4 * 130 * 64},
         {&m->GO[2], B * 2 * 66 * 128},  {&m->GO[3], B * 1 * 34 * 256},  {&m->SEQ, 256 * B * 1024},
-        {&m->XP, (256 * B * 4096 > (size_t)4096 * 1024) ? 256 * B * 4096 : (size_t)4096 * 1024},       {&m->R1, 256 * B * 1024},       {&m->R2, 256 * B * 1024},
+        {&m->XP, (256 * B * 4096 > (size_t)4096 * 1024) ? 256 * B * 4096 : (size_t)4096 * 1024},       {&m->R1, 256 * B * 1024},       {&m->R2, 256 * B * 1024},       {&m->R1S, 256 * B * 1024},
         {&m->x_in, B * 3 * 512 * 1024}, {&m->bon_out, B * 2 * 1024},    {&m->cor_out, B * 1024},
         {&m->head_w, 12 * 1024},        {&m->head_b, 12},
     };
@@ -405,7 +408,7 @@ int hn_model_finalize(hn_model* m) {
         ConvLayer& c = m->xproj[layer];
         if (!c.w) {
             if (m->alloc_t(&c.w, (size_t)4096 * 1024) || m->alloc_t(&c.scale, 4096) || m->alloc_t(&c.shift, 4096)) return -1;
-            if (m->alloc_t(&c.wq, (size_t)2 * 4096 * 1024)) return -1;
+            if (m->alloc_t(&c.wq, (size_t)2 * 4096 * 1024) || m->alloc_t(&c.tc_scale, 4096 + 1)) return -1;
         }
         const std::string l = "_l" + std::to_string(layer);
         // [4096][1024] (fwd rows then reverse rows) -> [K=1024][N=4096]
@@ -417,11 +420,12 @@ int hn_model_finalize(hn_model* m) {
         }
         pack_oihw_kernel<<<(4096 * 1024 + 255) / 256, 256, 0, st>>>(m->XP, c.w, 4096, 1024, 1, 1);
         HN_LAUNCH_OK();
-        if (pack_weight_tc(m->XP, c.wq, 4096, 1024, 1, 1, st)) return -1;
+
         lstm_bias_kernel<<<16, 256, 0, st>>>(m->T("bi_rnn.bias_ih" + l), m->T("bi_rnn.bias_hh" + l),
                                              m->T("bi_rnn.bias_ih" + l + "_reverse"),
                                              m->T("bi_rnn.bias_hh" + l + "_reverse"), c.scale, c.shift);
         HN_LAUNCH_OK();
+        if (pack_weight_tc(m->XP, c.wq, c.scale, c.tc_scale, c.tc_scale + 4096, 4096, 1024, 1, 1, st)) return -1;
         c.d.w = c.w; c.d.scale = c.scale; c.d.shift = c.shift;
     }
     HN_CUDA_OK(cudaMemcpyAsync(m->head_w, m->T("linear.weight"), 12 * 1024 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -501,10 +505,10 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
         Act a = mk(const_cast<float*>(lin), 1, 1, 256 * B, 1024, 0);
         Act xp = mk(m->XP, 1, 1, 256 * B, 4096, 0);
         if (m->use_tc && layer == 1) {
-            // layer-2 projection operand: the fp32 recurrence output as bf16 planes (SEQ is free again)
+            // layer-2 projection operand: the fp32 recurrence output as bf16 planes
             Scope sc(m, CLS_TAIL, 0.0, st);
-            if (split_planes(m->R1, reinterpret_cast<__nv_bfloat16*>(m->SEQ), (size_t)256 * B * 1024, st)) return -1;
-            a.p = m->SEQ;
+            if (split_planes(m->R1, reinterpret_cast<unsigned short*>(m->R1S), (size_t)256 * B * 1024, st)) return -1;
+            a.p = m->R1S;
         }
         if (run_conv(m, m->xproj[layer], a, xp, nullptr, st, CLS_XPROJ, true)) return -1;
         {
@@ -588,7 +592,7 @@ int hn_model_stage(hn_model* m, const char* stage, float* out, long long capacit
             if (m->use_tc) {       // F[l] holds bf16 planes: merge into T1 scratch first (free after the forward)
                 const size_t n = (size_t)B * H * (W + 2) * C;
                 float* tmp = (l == 0) ? m->X[0] : m->T1;
-                if (merge_planes(reinterpret_cast<const __nv_bfloat16*>(m->F[l]), tmp, n, st)) return -1;
+                if (merge_planes(reinterpret_cast<const unsigned short*>(m->F[l]), tmp, n, st)) return -1;
                 src = tmp;
             }
             nhwc_to_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, out, B, H, W, C, 1);
@@ -599,8 +603,12 @@ int hn_model_stage(hn_model* m, const char* stage, float* out, long long capacit
     const size_t total = (size_t)256 * B * 1024;
     HN_CHECK((long long)total <= capacity, "hn_model_stage: output buffer too small");
     if (s == "feature") {
-        if (m->use_tc) return fail("hn_model_stage: 'feature' is only kept in fp32 form on the fp32 path");
-        seq_to_feature_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(m->SEQ, out, 256, B);
+        const float* seq = m->SEQ;
+        if (m->use_tc) {      // SEQ holds bf16 planes; XP is dead after the forward and large enough
+            if (merge_planes(reinterpret_cast<const unsigned short*>(m->SEQ), m->XP, total, st)) return -1;
+            seq = m->XP;
+        }
+        seq_to_feature_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(seq, out, 256, B);
         HN_LAUNCH_OK();
         dims[0] = B; dims[1] = 1024; dims[2] = 256; dims[3] = 0;
         return 0;

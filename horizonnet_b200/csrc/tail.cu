@@ -7,8 +7,8 @@
 //   coordinates, i0 = floor(s), l = s - i0 (all exactly representable in fp32; f=1 is the identity).
 // head_kernel: model.py:266-269, Linear(1024 -> 12) + the [T,B,3,4] -> [B,3,T*4] scatter;
 //   channel 0 = cor, 1..2 = bon (model.py:278-279).
-#include <cuda_bf16.h>
 #include "hn_common.cuh"
+#include "conv_tc.cuh"
 
 namespace hn {
 
@@ -43,16 +43,14 @@ __global__ void __launch_bounds__(256) ghc_to_sequence_kernel(const GhcSrc s, fl
     if (!SPLIT) {
         seq[i] = l0 * __ldg(s.p[sc] + o0) + l1 * __ldg(s.p[sc] + o1);
     } else {
-        // inputs and output are bf16 hi/lo plane pairs (value = hi + lo)
-        const __nv_bfloat16* pb = reinterpret_cast<const __nv_bfloat16*>(s.p[sc]);
+        // inputs and output are hi/lo plane pairs (conv_tc.cuh)
+        const unsigned short* pb = reinterpret_cast<const unsigned short*>(s.p[sc]);
         const size_t plane = (size_t)B * H * (W + 2) * C;
-        const float v0 = __bfloat162float(pb[o0]) + __bfloat162float(pb[plane + o0]);
-        const float v1 = __bfloat162float(pb[o1]) + __bfloat162float(pb[plane + o1]);
+        const float v0 = merge_scaled(pb[o0], pb[plane + o0]);
+        const float v1 = merge_scaled(pb[o1], pb[plane + o1]);
         const float v = l0 * v0 + l1 * v1;
-        __nv_bfloat16* ob = reinterpret_cast<__nv_bfloat16*>(seq);
-        const __nv_bfloat16 hi = __float2bfloat16_rn(v);
-        ob[i] = hi;
-        ob[total + i] = __float2bfloat16_rn(v - __bfloat162float(hi));
+        unsigned short* ob = reinterpret_cast<unsigned short*>(seq);
+        split_scaled(v, ob[i], ob[total + i]);
     }
 }
 
