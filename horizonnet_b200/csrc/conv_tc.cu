@@ -41,6 +41,7 @@ constexpr int BKC = 64;            // bf16 channels per K chunk = one 128-byte s
 constexpr int STAGES = 3;
 constexpr int NTHREADS = 384;
 constexpr int EPI_WARP0 = 4;
+constexpr int STAGE_PITCH = 80;    // bytes per staged row: 64 B payload + 16 B pad (conflict-free 16-byte accesses)
 constexpr long long WAIT_LIMIT = 3000000000ll;     // cycles; a stuck barrier traps instead of hanging
 
 // ------------------------------------------------------------------------------------ PTX helpers
@@ -178,7 +179,8 @@ struct Smem {
     static constexpr int A_PLANE = BM * BKC * 2;          // 16 KB
     static constexpr int B_PLANE = BN * BKC * 2;
     static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
-    static constexpr int BAR_OFF = STAGES * STAGE;
+    static constexpr int EPI_OFF = STAGES * STAGE;                    // 8 warp-private epilogue staging buffers
+    static constexpr int BAR_OFF = EPI_OFF + 8 * 32 * STAGE_PITCH;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;    // barriers + alignment slack
     static constexpr int TMEM_COLS = 4 * BN;        // 2 hi*hi segment accumulators + 2 cross accumulators (128..512)
 };
@@ -327,6 +329,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int CW = 32;                                           // columns per tcgen05.ld chunk
         const bool works = (BN >= 64) || half == 0;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        uint8_t* stage = smem + S::EPI_OFF + (warp - EPI_WARP0) * 32 * STAGE_PITCH;
         const int nseg = (a.num_kc + a.seg - 1) / a.seg;
         int it = 0, g = 0;
         for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
@@ -374,13 +377,54 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tempty_bar + mbuf);
             }
-            // ---- the last segment's commit also covers the cross products of the whole tile
+            // ---- the last segment's commit also covers the cross products of the whole tile.
+            // Global traffic of the epilogue is routed through a warp-private staging buffer so that
+            // every load/store instruction touches whole 64-byte row segments (4 lanes x 16 B per pixel,
+            // 8 pixels per instruction) instead of 32 scattered 16-byte pieces.
+            unsigned long long rowpix[4], rowhalo[4];           // pixel / halo pixel of row it*8 + lane/4
+            {
+                const unsigned long long mypix = valid ? (unsigned long long)pix : ~0ull;
+                const unsigned long long myhalo = (valid && has_halo) ? (unsigned long long)halo_pix : ~0ull;
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    rowpix[i4] = __shfl_sync(0xffffffffu, mypix, i4 * 8 + (lane >> 2));
+                    rowhalo[i4] = __shfl_sync(0xffffffffu, myhalo, i4 * 8 + (lane >> 2));
+                }
+            }
+            const int seg16 = (lane & 3) * 16;
+            uint8_t* my_row = stage + lane * STAGE_PITCH;
+            // 64 bytes per row, this lane's row -> global, coalesced
+            auto put64 = [&](const uint4& d0, const uint4& d1, const uint4& d2, const uint4& d3, uint8_t* base,
+                             size_t pitch, size_t colb) {
+                uint4* w = reinterpret_cast<uint4*>(my_row);
+                w[0] = d0; w[1] = d1; w[2] = d2; w[3] = d3;
+                __syncwarp();
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    const uint4 v = *reinterpret_cast<const uint4*>(stage + (i4 * 8 + (lane >> 2)) * STAGE_PITCH + seg16);
+                    if (rowpix[i4] != ~0ull) *reinterpret_cast<uint4*>(base + rowpix[i4] * pitch + colb + seg16) = v;
+                    if (rowhalo[i4] != ~0ull) *reinterpret_cast<uint4*>(base + rowhalo[i4] * pitch + colb + seg16) = v;
+                }
+                __syncwarp();
+            };
+            // global -> 64 bytes of this lane's row, coalesced
+            auto get64 = [&](const uint8_t* base, size_t pitch, size_t colb, uint4 (&d)[4]) {
+#pragma unroll
+                for (int i4 = 0; i4 < 4; ++i4) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (rowpix[i4] != ~0ull) v = __ldg(reinterpret_cast<const uint4*>(base + rowpix[i4] * pitch + colb + seg16));
+                    *reinterpret_cast<uint4*>(stage + (i4 * 8 + (lane >> 2)) * STAGE_PITCH + seg16) = v;
+                }
+                __syncwarp();
+                const uint4* rd = reinterpret_cast<const uint4*>(my_row);
+                d[0] = rd[0]; d[1] = rd[1]; d[2] = rd[2]; d[3] = rd[3];
+                __syncwarp();
+            };
 #pragma unroll
             for (int ch = 0; ch < (works ? NCHUNK : 0); ++ch) {
                 const int col0 = half * COLS_PER_WARP + ch * 32;          // column inside the tile
                 uint32_t v[32];
                 tmem_ld32(tmem_base + lane_base + (uint32_t)((2 + cbuf) * BN + col0), v);
-                if (!valid) continue;
                 const int n0 = nt * BN + col0;                            // output channel of v[0]
                 float y[32];
 #pragma unroll
@@ -393,16 +437,18 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     y[j + 3] = fmaf(sum[ch * 32 + j + 3] + __uint_as_float(v[j + 3]), sc.w, sf.w);
                 }
                 if (a.res) {
-                    const uint4* rh = reinterpret_cast<const uint4*>(a.res + pix * a.Cout + n0);
-                    const uint4* rl = reinterpret_cast<const uint4*>(a.res + a.out_plane + pix * a.Cout + n0);
+                    uint4 rh[4], rl[4];
+                    const size_t pitch = (size_t)a.Cout * 2, colb = (size_t)n0 * 2;
+                    get64(reinterpret_cast<const uint8_t*>(a.res), pitch, colb, rh);
+                    get64(reinterpret_cast<const uint8_t*>(a.res + a.out_plane), pitch, colb, rl);
 #pragma unroll
-                    for (int j = 0; j < CW / 8; ++j) {
-                        const uint4 h = __ldg(rh + j), l = __ldg(rl + j);
-                        const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t hw[4] = {rh[j].x, rh[j].y, rh[j].z, rh[j].w}, lw[4] = {rl[j].x, rl[j].y, rl[j].z, rl[j].w};
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) {
-                            y[j * 8 + 2 * e + 0] += merge_scaled((unsigned short)(hw[e] & 0xFFFFu), (unsigned short)(lw[e] & 0xFFFFu));
-                            y[j * 8 + 2 * e + 1] += merge_scaled((unsigned short)(hw[e] >> 16), (unsigned short)(lw[e] >> 16));
+                        for (int e = 0; e < 4; ++e) {       // y is in plane units here: no rescaling needed
+                            const float2 fh = unpack_half2(hw[e]), fl = unpack_half2(lw[e]);
+                            y[j * 8 + 2 * e + 0] += fh.x + fl.x;
+                            y[j * 8 + 2 * e + 1] += fh.y + fl.y;
                         }
                     }
                 }
@@ -411,35 +457,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int j = 0; j < CW; ++j) y[j] = fmaxf(y[j], 0.f);
                 }
                 if (a.out_f32) {
-                    float4* o = reinterpret_cast<float4*>(a.out_f32 + pix * a.Cout + n0);
+                    const size_t pitch = (size_t)a.Cout * 4;
+                    uint8_t* base = reinterpret_cast<uint8_t*>(a.out_f32);
 #pragma unroll
-                    for (int j = 0; j < CW / 4; ++j) o[j] = make_float4(y[4 * j], y[4 * j + 1], y[4 * j + 2], y[4 * j + 3]);
+                    for (int hq = 0; hq < 2; ++hq) {
+                        const float* yy = y + hq * 16;
+                        put64(make_uint4(__float_as_uint(yy[0]), __float_as_uint(yy[1]), __float_as_uint(yy[2]), __float_as_uint(yy[3])),
+                              make_uint4(__float_as_uint(yy[4]), __float_as_uint(yy[5]), __float_as_uint(yy[6]), __float_as_uint(yy[7])),
+                              make_uint4(__float_as_uint(yy[8]), __float_as_uint(yy[9]), __float_as_uint(yy[10]), __float_as_uint(yy[11])),
+                              make_uint4(__float_as_uint(yy[12]), __float_as_uint(yy[13]), __float_as_uint(yy[14]), __float_as_uint(yy[15])),
+                              base, pitch, (size_t)(n0 + hq * 16) * 4);
+                    }
                 } else {
                     uint32_t ph[16], pl[16];
 #pragma unroll
-                    for (int j = 0; j < CW / 2; ++j) {
-                        unsigned short h0, l0, h1, l1;
-                        split_scaled(y[2 * j], h0, l0);
-                        split_scaled(y[2 * j + 1], h1, l1);
-                        ph[j] = pack2(h0, h1);
-                        pl[j] = pack2(l0, l1);
-                    }
-                    uint4* oh = reinterpret_cast<uint4*>(a.out + pix * a.Cout + n0);
-                    uint4* ol = reinterpret_cast<uint4*>(a.out + a.out_plane + pix * a.Cout + n0);
-#pragma unroll
-                    for (int j = 0; j < CW / 8; ++j) {
-                        oh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-                        ol[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-                    }
-                    if (has_halo) {
-                        uint4* hh = reinterpret_cast<uint4*>(a.out + halo_pix * a.Cout + n0);
-                        uint4* hl = reinterpret_cast<uint4*>(a.out + a.out_plane + halo_pix * a.Cout + n0);
-#pragma unroll
-                        for (int j = 0; j < CW / 8; ++j) {
-                            hh[j] = make_uint4(ph[4 * j], ph[4 * j + 1], ph[4 * j + 2], ph[4 * j + 3]);
-                            hl[j] = make_uint4(pl[4 * j], pl[4 * j + 1], pl[4 * j + 2], pl[4 * j + 3]);
-                        }
-                    }
+                    for (int j = 0; j < CW / 2; ++j) split2_scaled(y[2 * j], y[2 * j + 1], ph[j], pl[j]);
+                    const size_t pitch = (size_t)a.Cout * 2, colb = (size_t)n0 * 2;
+                    put64(make_uint4(ph[0], ph[1], ph[2], ph[3]), make_uint4(ph[4], ph[5], ph[6], ph[7]),
+                          make_uint4(ph[8], ph[9], ph[10], ph[11]), make_uint4(ph[12], ph[13], ph[14], ph[15]),
+                          reinterpret_cast<uint8_t*>(a.out), pitch, colb);
+                    put64(make_uint4(pl[0], pl[1], pl[2], pl[3]), make_uint4(pl[4], pl[5], pl[6], pl[7]),
+                          make_uint4(pl[8], pl[9], pl[10], pl[11]), make_uint4(pl[12], pl[13], pl[14], pl[15]),
+                          reinterpret_cast<uint8_t*>(a.out + a.out_plane), pitch, colb);
                 }
             }
             // cross accumulator drained: hand it back to the MMA warp
@@ -528,7 +567,7 @@ bool conv_tc_supported(const ConvDesc& d, const Act& in, const Act& out) {
 
 // in / out / residual are split plane pairs in halo-NHWC geometry (hi plane, then lo plane).
 // wq: [2][Cout][K] weight planes, K = (dy*kw+dx)*Cin + c; tc_scale folds BN scale and the plane scales.
-int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_scale, const Act& in,
+int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_aux, const Act& in,
                    const unsigned short* in_planes, const Act& out, unsigned short* out_planes, float* out_f32,
                    const unsigned short* res_planes, cudaStream_t st) {
     HN_CHECK(conv_tc_supported(d, in, out), "conv_tc: unsupported shape");
@@ -550,7 +589,9 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
     a.kw = d.kw;
     a.kc_per_tap = d.Cin / BKC;
     a.num_kc = d.kh * d.kw * a.kc_per_tap;
-    a.scale = tc_scale; a.shift = d.shift;
+    HN_CHECK(!(out_f32 && res_planes), "conv_tc: residual with fp32 output is not supported");
+    a.scale = out_f32 ? tc_aux : tc_aux + d.Cout;            // fp32 outputs in true units, planes in plane units
+    a.shift = out_f32 ? d.shift : tc_aux + 2 * d.Cout;
     a.res = res_planes; a.out = out_planes; a.out_f32 = out_f32; a.out_plane = out_plane; a.relu = d.relu;
     a.Bimg = in.B;
     a.seg = tc_segment_chunks();
@@ -660,23 +701,26 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, unsigned shor
     out[total + i] = __half_as_ushort(__float2half_rn(s - __half2float(h)));
 }
 
-__global__ void tc_scale_kernel(const float* __restrict__ scale, const float* __restrict__ absmax,
-                                float* __restrict__ tc_scale, int C) {
+__global__ void tc_scale_kernel(const float* __restrict__ scale, const float* __restrict__ shift,
+                                const float* __restrict__ absmax, float* __restrict__ tc_aux, int C) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= C) return;
-    tc_scale[i] = (scale ? scale[i] : 1.f) * ACT_UNSCALE / weight_scale(*absmax);
+    const float s = (scale ? scale[i] : 1.f) * ACT_UNSCALE / weight_scale(*absmax);   // accumulator -> true units
+    tc_aux[i] = s;
+    tc_aux[C + i] = s * ACT_SCALE;                                                    // accumulator -> plane units
+    tc_aux[2 * C + i] = (shift ? shift[i] : 0.f) * ACT_SCALE;
 }
 
 template <bool OIHW>
-int pack_weight_impl(const float* w, unsigned short* wq, const float* scale, float* tc_scale, float* scratch, int Cout,
-                     int Cin, int kh, int kw, cudaStream_t st) {
+int pack_weight_impl(const float* w, unsigned short* wq, const float* scale, const float* shift, float* tc_aux,
+                     float* scratch, int Cout, int Cin, int kh, int kw, cudaStream_t st) {
     const size_t total = (size_t)Cout * Cin * kh * kw;
     HN_CUDA_OK(cudaMemsetAsync(scratch, 0, sizeof(float), st));
     absmax_kernel<<<(unsigned)((total + 256 * 64 - 1) / (256 * 64)), 256, 0, st>>>(w, total, scratch);
     HN_LAUNCH_OK();
     pack_weight_tc_kernel<OIHW><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w, wq, scratch, Cout, Cin, kh, kw);
     HN_LAUNCH_OK();
-    tc_scale_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(scale, scratch, tc_scale, Cout);
+    tc_scale_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(scale, shift, scratch, tc_aux, Cout);
     HN_LAUNCH_OK();
     return 0;
 }
@@ -698,9 +742,9 @@ int merge_planes(const unsigned short* in, float* out, size_t n, cudaStream_t st
     return 0;
 }
 
-int pack_weight_tc(const float* w_oihw, unsigned short* wq, const float* scale, float* tc_scale, float* scratch,
-                   int Cout, int Cin, int kh, int kw, cudaStream_t st) {
-    return pack_weight_impl<true>(w_oihw, wq, scale, tc_scale, scratch, Cout, Cin, kh, kw, st);
+int pack_weight_tc(const float* w_oihw, unsigned short* wq, const float* scale, const float* shift, float* tc_aux,
+                   float* scratch, int Cout, int Cin, int kh, int kw, cudaStream_t st) {
+    return pack_weight_impl<true>(w_oihw, wq, scale, shift, tc_aux, scratch, Cout, Cin, kh, kw, st);
 }
 
 // Unit-test convenience: fp32 halo-NHWC in and out, planes built on the fly.
@@ -709,15 +753,15 @@ int conv_tc(const ConvDesc& d, const Act& in, const Act& out, const float* resid
     const size_t K = (size_t)d.kh * d.kw * d.Cin;
     const size_t n_in = in.numel(), n_out = out.numel(), n_w = K * d.Cout;
     unsigned short *pin = nullptr, *pout = nullptr, *pres = nullptr, *pw = nullptr;
-    float* aux = nullptr;          // [Cout] tc_scale + 1 scratch float
+    float* aux = nullptr;          // [3*Cout] tc_aux + 1 scratch float
     HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pin), n_in * 4, st));
     HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pout), n_out * 4, st));
     HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pw), n_w * 4, st));
-    HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&aux), (d.Cout + 1) * sizeof(float), st));
+    HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&aux), (3 * d.Cout + 1) * sizeof(float), st));
     if (residual) HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&pres), n_out * 4, st));
     int rc = split_planes(in.p, pin, n_in, st);
     if (!rc && residual) rc = split_planes(residual, pres, n_out, st);
-    if (!rc) rc = pack_weight_impl<false>(d.w, pw, d.scale, aux, aux + d.Cout, d.Cout, d.Cin, d.kh, d.kw, st);
+    if (!rc) rc = pack_weight_impl<false>(d.w, pw, d.scale, d.shift, aux, aux + 3 * d.Cout, d.Cout, d.Cin, d.kh, d.kw, st);
     if (!rc) rc = conv_tc_planes(d, pw, aux, in, pin, out, pout, nullptr, pres, st);
     if (!rc) rc = merge_planes(pout, out.p, n_out, st);
     cudaFreeAsync(pin, st); cudaFreeAsync(pout, st); cudaFreeAsync(pw, st); cudaFreeAsync(aux, st);

@@ -29,18 +29,35 @@ __device__ __forceinline__ float merge_scaled(unsigned short hi, unsigned short 
     return (__half2float(__ushort_as_half(hi)) + __half2float(__ushort_as_half(lo))) * ACT_UNSCALE;
 }
 
+// ---- scaled-domain fast path (conv_tc epilogue): values are already multiplied by ACT_SCALE
+__device__ __forceinline__ uint32_t pack_half2_sat(float e0, float e1) {      // e0 -> low half, e1 -> high half
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(e1), "f"(e0));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_half2(uint32_t v) {
+    return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+__device__ __forceinline__ void split2_scaled(float s0, float s1, uint32_t& hi2, uint32_t& lo2) {
+    hi2 = pack_half2_sat(s0, s1);
+    const float2 b = unpack_half2(hi2);
+    lo2 = pack_half2_sat(s0 - b.x, s1 - b.y);
+}
+
 bool conv_tc_supported(const ConvDesc& d, const Act& in, const Act& out);
 // fp32 halo-NHWC in/out convenience wrapper (unit tests): splits, runs the plane kernel, merges.
 int conv_tc(const ConvDesc& d, const Act& in, const Act& out, const float* residual, cudaStream_t st);
 // The real thing: operands and result are split planes.  wq: [2][Cout][K] weight planes
-// (fp16 hi, fp16 lo of w * 2^t), tc_scale = BN scale * 2^(4-t) (see pack_weight_tc).
-int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_scale, const Act& in,
+// (fp16 hi, fp16 lo of w * 2^t); tc_aux = 3*Cout floats written by pack_weight_tc:
+//   [0,C)  accumulator -> true units   (BN scale * 2^(4-t)),  used with d.shift for fp32 outputs
+//   [C,2C) accumulator -> plane units  (the above * 2^-4),    [2C,3C) shift in plane units
+int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_aux, const Act& in,
                    const unsigned short* in_planes, const Act& out, unsigned short* out_planes, float* out_f32,
                    const unsigned short* res_planes, cudaStream_t st);
 int split_planes(const float* in, unsigned short* out, size_t n, cudaStream_t st);
 int merge_planes(const unsigned short* in, float* out, size_t n, cudaStream_t st);
-// OIHW fp32 weights -> wq planes + tc_scale[Cout] (scale may be null = all ones); scratch: 1 float.
-int pack_weight_tc(const float* w_oihw, unsigned short* wq, const float* scale, float* tc_scale, float* scratch,
-                   int Cout, int Cin, int kh, int kw, cudaStream_t st);
+// OIHW fp32 weights -> wq planes + tc_aux[3*Cout] (scale/shift may be null = ones/zeros); scratch: 1 float.
+int pack_weight_tc(const float* w_oihw, unsigned short* wq, const float* scale, const float* shift, float* tc_aux,
+                   float* scratch, int Cout, int Cin, int kh, int kw, cudaStream_t st);
 
 }  // namespace hn

@@ -113,7 +113,7 @@ struct ConvLayer {
     float* scale = nullptr;
     float* shift = nullptr;
     unsigned short* wq = nullptr;     // [2][Cout][K] hi/lo weight planes for the tcgen05 kernel
-    float* tc_scale = nullptr;        // BN scale * 2^-(8+t) (conv_tc.cuh)
+    float* tc_scale = nullptr;        // 3*Cout (+1 scratch) epilogue constants of the tcgen05 path (conv_tc.cuh: tc_aux)
 };
 
 }  // namespace
@@ -261,7 +261,7 @@ int pack_conv(hn_model* m, ConvLayer& c, cudaStream_t st) {
         if (m->alloc_t(&c.w, nw)) return -1;
         if (m->alloc_t(&c.scale, c.d.Cout)) return -1;
         if (m->alloc_t(&c.shift, c.d.Cout)) return -1;
-        if (c.d.Cin % 64 == 0 && (m->alloc_t(&c.wq, 2 * nw) || m->alloc_t(&c.tc_scale, c.d.Cout + 1))) return -1;
+        if (c.d.Cin % 64 == 0 && (m->alloc_t(&c.wq, 2 * nw) || m->alloc_t(&c.tc_scale, 3 * c.d.Cout + 1))) return -1;
     }
     pack_oihw_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(m->T(c.wkey), c.w, c.d.Cout, c.d.Cin, c.d.kh, c.d.kw);
     HN_LAUNCH_OK();
@@ -269,8 +269,8 @@ int pack_conv(hn_model* m, ConvLayer& c, cudaStream_t st) {
         m->T(c.bnprefix + ".weight"), m->T(c.bnprefix + ".bias"), m->T(c.bnprefix + ".running_mean"),
         m->T(c.bnprefix + ".running_var"), c.biaskey.empty() ? nullptr : m->T(c.biaskey), c.scale, c.shift, c.d.Cout);
     HN_LAUNCH_OK();
-    if (c.wq && pack_weight_tc(m->T(c.wkey), c.wq, c.scale, c.tc_scale, c.tc_scale + c.d.Cout, c.d.Cout, c.d.Cin, c.d.kh,
-                               c.d.kw, st))
+    if (c.wq && pack_weight_tc(m->T(c.wkey), c.wq, c.scale, c.shift, c.tc_scale, c.tc_scale + 3 * c.d.Cout, c.d.Cout,
+                               c.d.Cin, c.d.kh, c.d.kw, st))
         return -1;
     c.d.w = c.w; c.d.scale = c.scale; c.d.shift = c.shift;
     return 0;
@@ -348,7 +348,7 @@ int hn_model_create(int device, int max_batch, hn_model** out) {
     };
     for (auto& b : bufs)
         if (m->alloc_t(b.p, b.n)) return -1;
-    if (m->alloc_t(&m->counters, 4)) return -1;
+    if (m->alloc_t(&m->counters, 16)) return -1;
     if (m->alloc_t(&m->error_flag, 1)) return -1;
     HN_CUDA_OK(cudaMemset(m->error_flag, 0, sizeof(int)));
     *out = m.release();
@@ -408,7 +408,7 @@ int hn_model_finalize(hn_model* m) {
         ConvLayer& c = m->xproj[layer];
         if (!c.w) {
             if (m->alloc_t(&c.w, (size_t)4096 * 1024) || m->alloc_t(&c.scale, 4096) || m->alloc_t(&c.shift, 4096)) return -1;
-            if (m->alloc_t(&c.wq, (size_t)2 * 4096 * 1024) || m->alloc_t(&c.tc_scale, 4096 + 1)) return -1;
+            if (m->alloc_t(&c.wq, (size_t)2 * 4096 * 1024) || m->alloc_t(&c.tc_scale, 3 * 4096 + 1)) return -1;
         }
         const std::string l = "_l" + std::to_string(layer);
         // [4096][1024] (fwd rows then reverse rows) -> [K=1024][N=4096]
@@ -425,7 +425,7 @@ int hn_model_finalize(hn_model* m) {
                                              m->T("bi_rnn.bias_ih" + l + "_reverse"),
                                              m->T("bi_rnn.bias_hh" + l + "_reverse"), c.scale, c.shift);
         HN_LAUNCH_OK();
-        if (pack_weight_tc(m->XP, c.wq, c.scale, c.tc_scale, c.tc_scale + 4096, 4096, 1024, 1, 1, st)) return -1;
+        if (pack_weight_tc(m->XP, c.wq, c.scale, c.shift, c.tc_scale, c.tc_scale + 3 * 4096, 4096, 1024, 1, 1, st)) return -1;
         c.d.w = c.w; c.d.scale = c.scale; c.d.shift = c.shift;
     }
     HN_CUDA_OK(cudaMemcpyAsync(m->head_w, m->T("linear.weight"), 12 * 1024 * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -686,9 +686,9 @@ int hn_lstm_layer(const float* xproj, const float* whf, const float* whb, float*
     HN_CHECK(xproj && whf && whb && out && T >= 1 && B >= 1, "hn_lstm_layer: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned int* ctr = nullptr;
-    HN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ctr), 4 * sizeof(unsigned int)));
-    int* flag = reinterpret_cast<int*>(ctr + 2);
-    cudaMemsetAsync(ctr, 0, 4 * sizeof(unsigned int), st);
+    HN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ctr), 16 * sizeof(unsigned int)));
+    int* flag = reinterpret_cast<int*>(ctr + 12);   // counters live in [0, 12), the error flag behind them
+    cudaMemsetAsync(ctr, 0, 16 * sizeof(unsigned int), st);
     int rc = lstm_layer(xproj, whf, whb, out, T, B, ctr, flag, st);
     int h = 0;
     if (!rc) {

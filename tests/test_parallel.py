@@ -1,0 +1,49 @@
+"""CPU, world_size 2, gloo: the N>1 host logic (sharding + the output all-gather used by bench.py)."""
+import os
+import socket
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from horizonnet_b200.parallel import gather_outputs, shard_bounds
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(('127.0.0.1', 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, total):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(123)
+        bon_full = torch.randn(total, 2, 1024, generator=g)      # the "single-device" result
+        cor_full = torch.randn(total, 1, 1024, generator=g)
+        lo, hi = shard_bounds(total, rank, world)
+        bon_all, cor_all = gather_outputs(bon_full[lo:hi].clone(), cor_full[lo:hi].clone())
+        # gathered == single-device result, bit for bit
+        assert torch.equal(bon_all, bon_full) and torch.equal(cor_all, cor_full)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_of_shards_equals_full_batch_world2():
+    mp.spawn(_worker, args=(2, _free_port(), 8), nprocs=2, join=True)
+
+
+def test_shard_bounds_cover_everything_once():
+    for total in (0, 1, 7, 32, 256):
+        for world in (1, 2, 3, 8):
+            seen = []
+            for r in range(world):
+                lo, hi = shard_bounds(total, r, world)
+                assert 0 <= lo <= hi <= total
+                seen += list(range(lo, hi))
+            assert seen == list(range(total))
+    assert shard_bounds(256, 3, 8) == (96, 128)
