@@ -235,11 +235,20 @@ def run_ours(args):
     conv_n = sum(prof[c][2] for c in conv_cls)
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     stage_ms = {k: round(v[0] / args.steps, 4) for k, v in prof.items()}
+    traffic = None
+    try:
+        import glob
+        files = sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_conv_tc_traffic.json')))
+        if files and not args.fp32:
+            traffic = json.load(open(files[-1]))['dram_bytes_per_launch_avg']
+    except Exception:
+        traffic = None
     roofline = {
         'kernel': 'conv implicit-GEMM family (%s)' % ('conv_igemm_f32, fp32 CUDA cores' if args.fp32 else 'conv_tc_kernel, tcgen05 split-fp16 x3 products'),
         'bound': 'tensor', 'achieved': round(achieved, 3), 'peak': peaks['tf'], 'unit': 'TFLOP/s',
         'frac': round(achieved / peaks['tf'], 5), 'peak_source': peaks['src'] + ' bf16 dense, sustained',
-        'traffic': None, 'launches_per_step': conv_n / args.steps,
+        'traffic': traffic, 'traffic_source': 'dram__bytes_read+write per launch (avg of the 70 conv launches), ncu --set full, see profiles/' if traffic else None,
+        'launches_per_step': conv_n / args.steps,
         'avg_launch_ms': round(conv_ms / max(conv_n, 1), 5),
         'algorithmic_gflop_per_step': round(conv_flops / args.steps / 1e9, 2),
         'share_of_step': round(conv_ms / total_ms, 4),

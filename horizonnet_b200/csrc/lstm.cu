@@ -6,16 +6,23 @@
 // sequential steps of one layer, both directions concurrently:
 //   grid  = 2 directions x 64 CTAs, cooperative launch (all CTAs co-resident, 1 per SM)
 //   CTA   = 8 hidden units x 4 gates = 32 rows of W_hh, held in REGISTERS for the whole sequence
-//           (thread (row, kc) keeps 64 weights: k = 32*i + 4*kc + {0..3}), fp32 FMA (bit-faithful
-//           to the fp32 reference up to summation order)
-//   step  = h_{t-1} [32 batch x 512] is pulled from L2 into shared memory, each warp (= one hidden
-//           unit, lanes = 4 gates x 8 k-slices) reduces with a transposing shuffle butterfly, the
-//           cell update happens in registers (c never leaves the SM) and h_t is written straight
-//           into the layer output [T][B][1024] (which is also where the other CTAs read it from);
-//           a per-direction arrival counter in global memory orders the steps.
+//           (compute warp = one hidden unit, lane = (gate, k-slice); 64 weights per thread), fp32 FMA:
+//           bit-faithful to the fp32 reference up to summation order.
+//   step  = every step needs h_{t-1} of all 512 units, i.e. an all-to-all between the 64 CTAs of a
+//           direction through L2.  That exchange is latency (~2.5 us), so the 32 batch columns of a
+//           launch are cut into NSB independent sub-batches that are software-pipelined: while
+//           sub-batch j's h_t travels, the compute warps work on sub-batch j+1.
+//           Warp roles: warps 0-7 compute (FMA from shared memory, transposing shuffle butterfly,
+//           cell update in registers, h_t stored straight into the layer output [T][B][1024]) and
+//           never wait for anything but their operands; warp 8 loads (acquire-polls the arrival
+//           counter of the next sub-step and pulls h_{t-1} [SBC x 512] into shared memory with
+//           1-D TMA bulk copies that complete on an mbarrier); warp 9 signals (waits until the 8
+//           compute warps have stored h_t of a sub-step, then fence + red.release on the counter --
+//           the gpu-scope fence costs ~1 us and must not sit in the compute warps' path).
 // Batches larger than 32 are processed in chunks of 32 (independent sequences).
 #include <cooperative_groups.h>
 #include "hn_common.cuh"
+#include "ptx.cuh"
 
 namespace hn {
 
@@ -25,13 +32,18 @@ constexpr int HID = 512;
 constexpr int NCTA_DIR = 64;               // CTAs per direction
 constexpr int UNITS = HID / NCTA_DIR;      // 8 hidden units per CTA
 constexpr int BCHUNK = 32;                 // batch columns per launch
+constexpr int NSB = 4;                     // sub-batches pipelined through a CTA
+constexpr int SBC = BCHUNK / NSB;          // columns per sub-batch
+constexpr int FC = SBC / 8;                // columns a lane finishes after the butterfly
+constexpr int NCOMPUTE = 256;              // threads of the 8 compute warps
+constexpr int NTHREADS = NCOMPUTE + 64;    // + loader warp + signalling warp
 constexpr long long SPIN_LIMIT_CYCLES = 4000000000ll;   // ~2 s: never hang the GPU on a logic bug
 
 struct LstmArgs {
     const float* xproj;      // [T][B][4096]  (dir*2048 + gate*512 + unit), bias already added
     const float* w_hh[2];    // [2048][512] per direction (PyTorch layout, row = gate*512 + unit)
     float* out;              // [T][B][1024]  (dir*512 + unit)
-    unsigned int* counters;  // [2] arrival counters, zeroed before launch
+    unsigned int* counters;  // [2][NSB] arrival counters, zeroed before launch
     int* error_flag;
     int T, B, b0, nb;        // batch chunk [b0, b0+nb)
 };
@@ -43,22 +55,79 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
-__global__ void __launch_bounds__(256, 1) lstm_layer_kernel(const LstmArgs a) {
-    extern __shared__ __align__(16) float hs[];          // [BCHUNK][HID] previous hidden state
-    __shared__ int s_abort;
-    if (threadIdx.x == 0) s_abort = 0;
-    __syncthreads();
+__global__ void __launch_bounds__(NTHREADS, 1) lstm_layer_kernel(const LstmArgs a) {
+    extern __shared__ __align__(128) uint8_t lstm_smem[];
+    float (*hs)[SBC * HID] = reinterpret_cast<float (*)[SBC * HID]>(lstm_smem);   // h_{t-1} of each sub-batch
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(lstm_smem + sizeof(float) * NSB * SBC * HID);   // TMA landed
+    uint64_t* empty_bar = full_bar + NSB;                   // compute warps finished reading
+    uint64_t* done_bar = empty_bar + NSB;                   // compute warps stored h_t of the sub-step
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int dir = blockIdx.x / NCTA_DIR;
     const int cta = blockIdx.x % NCTA_DIR;
+    const int nsb = (a.nb + SBC - 1) / SBC;                 // active sub-batches of this chunk
+    const int tstep = dir ? -1 : 1;
+    const int t_first = dir ? a.T - 1 : 0;
+    unsigned int* ctr = a.counters + dir * NSB;
+
+    if (tid == 0) {
+        for (int j = 0; j < NSB; ++j) { mbar_init(full_bar + j, 1); mbar_init(empty_bar + j, 8); mbar_init(done_bar + j, 8); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // rows of partially filled sub-batches are never written by TMA: keep them zero
+    for (int i = tid; i < NSB * SBC * HID; i += NTHREADS) (&hs[0][0])[i] = 0.f;
+    __syncthreads();
+
+    if (warp == 8) {
+        // =============================== communication warp ===============================
+        if (lane == 0) {
+            for (int step = 1; step < a.T; ++step) {
+                const int tprev = t_first + (step - 1) * tstep;
+                for (int j = 0; j < nsb; ++j) {
+                    mbar_wait(empty_bar + j, ((step - 1) & 1) ^ 1);            // buffer j free again
+                    const unsigned int target = (unsigned int)(NCTA_DIR * step);
+                    if (ld_acquire(ctr + j) < target) {
+                        const long long t0 = clock64();
+                        while (ld_acquire(ctr + j) < target) {
+                            if (*reinterpret_cast<volatile int*>(a.error_flag) != 0) break;
+                            if (clock64() - t0 > SPIN_LIMIT_CYCLES) { atomicExch(a.error_flag, 1); break; }
+                        }
+                    }
+                    asm volatile("fence.proxy.async;" ::: "memory");           // generic-proxy acquire -> async-proxy reads
+                    const int ncol = min(SBC, a.nb - j * SBC);
+                    mbar_expect_tx(full_bar + j, (uint32_t)(ncol * HID * sizeof(float)));
+                    for (int b = 0; b < ncol; ++b)
+                        bulk_load_1d(&hs[j][b * HID],
+                                     a.out + ((size_t)tprev * a.B + a.b0 + j * SBC + b) * 1024 + dir * HID,
+                                     HID * sizeof(float), full_bar + j);
+                }
+            }
+        }
+        return;
+    }
+
+    if (warp == 9) {
+        // =============================== signalling warp ===============================
+        if (lane == 0) {
+            for (int step = 0; step < a.T; ++step)
+                for (int j = 0; j < nsb; ++j) {
+                    mbar_wait(done_bar + j, step & 1);          // all 8 compute warps stored h_t of (step, j)
+                    __threadfence();
+                    red_release_add(ctr + j, 1u);
+                }
+        }
+        return;
+    }
+
+    // =============================== compute warps ===============================
     const int gate = lane >> 3, kc = lane & 7;
     const int unit = cta * UNITS + warp;                   // hidden unit of this warp
     const int wrow = gate * HID + unit;                    // row of W_hh
-
-    // W_hh slice -> registers: wreg[i*4+j] = W[wrow][32*i + 4*kc + j]
-    float wreg[64];
+    float wreg[64];                                        // wreg[i*4+j] = W[wrow][32*i + 4*kc + j]
     {
         const float4* wp = reinterpret_cast<const float4*>(a.w_hh[dir] + (size_t)wrow * HID);
 #pragma unroll
@@ -67,130 +136,84 @@ __global__ void __launch_bounds__(256, 1) lstm_layer_kernel(const LstmArgs a) {
             wreg[i * 4 + 0] = v.x; wreg[i * 4 + 1] = v.y; wreg[i * 4 + 2] = v.z; wreg[i * 4 + 3] = v.w;
         }
     }
-    // after the butterfly, lane (gate, kc) owns the sums of batch columns 4*kc .. 4*kc+3
-    const int myb = kc * 4 + gate;                         // the batch column this lane updates
-    const bool active = myb < a.nb;
-    float c_state = 0.f;
-
-    // prefetch of the x-projection for the first step
-    auto xaddr = [&](int t, int g) {
-        return a.xproj + ((size_t)t * a.B + a.b0 + myb) * 4096 + dir * 2048 + g * HID + unit;
-    };
-    int t = dir ? a.T - 1 : 0;
-    const int tstep = dir ? -1 : 1;
-    float xp[4] = {0.f, 0.f, 0.f, 0.f};
-    if (active) {
+    float c_state[NSB][FC];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) xp[g] = __ldg(xaddr(t, g));
-    }
-
-    for (int step = 0; step < a.T; ++step, t += tstep) {
-        float acc[BCHUNK];
+    for (int j = 0; j < NSB; ++j)
 #pragma unroll
-        for (int b = 0; b < BCHUNK; ++b) acc[b] = 0.f;
-        if (step > 0) {
-            // wait until all 64 CTAs of this direction have published h of the previous step
-            if (tid == 0) {
-                const unsigned int target = (unsigned int)(NCTA_DIR * step);
-                const long long t0 = clock64();
-                while (ld_acquire(a.counters + dir) < target) {
-                    if (*reinterpret_cast<volatile int*>(a.error_flag) != 0) { s_abort = 1; break; }
-                    if (clock64() - t0 > SPIN_LIMIT_CYCLES) { atomicExch(a.error_flag, 1); s_abort = 1; break; }
+        for (int i = 0; i < FC; ++i) c_state[j][i] = 0.f;
+
+    for (int step = 0; step < a.T; ++step) {
+        const int t = t_first + step * tstep;
+#pragma unroll
+        for (int j = 0; j < NSB; ++j) {
+            if (j >= nsb) break;
+            // x-projection of the FC columns this lane finishes (all 4 gates; latency hides behind the FMAs)
+            float xp[FC][4];
+#pragma unroll
+            for (int i = 0; i < FC; ++i) {
+                const int col = j * SBC + kc * FC + i;
+                const float* xb = a.xproj + ((size_t)t * a.B + a.b0 + min(col, a.nb - 1)) * 4096 + dir * 2048 + unit;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) xp[i][g] = __ldg(xb + g * HID);
+            }
+            float acc[SBC];
+            if (step > 0) {
+                mbar_wait(full_bar + j, (step - 1) & 1);
+#pragma unroll
+                for (int b = 0; b < SBC; ++b) {
+                    const float4* hp = reinterpret_cast<const float4*>(&hs[j][b * HID]);
+                    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 2) {
+                        const float4 h0 = hp[i * 8 + kc], h1 = hp[(i + 1) * 8 + kc];
+                        s0 = fmaf(wreg[i * 4 + 0], h0.x, s0);
+                        s1 = fmaf(wreg[i * 4 + 4], h1.x, s1);
+                        s0 = fmaf(wreg[i * 4 + 1], h0.y, s0);
+                        s1 = fmaf(wreg[i * 4 + 5], h1.y, s1);
+                        s0 = fmaf(wreg[i * 4 + 2], h0.z, s0);
+                        s1 = fmaf(wreg[i * 4 + 6], h1.z, s1);
+                        s0 = fmaf(wreg[i * 4 + 3], h0.w, s0);
+                        s1 = fmaf(wreg[i * 4 + 7], h1.w, s1);
+                    }
+                    acc[b] = s0 + s1;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(empty_bar + j);                     // this warp is done with hs[j]
+            } else {
+#pragma unroll
+                for (int b = 0; b < SBC; ++b) acc[b] = 0.f;
+            }
+            // transposing butterfly over the 8 k-slices (lane bits 2,1,0): SBC -> SBC/8 values per lane;
+            // lane (gate, kc) ends with the sums of columns kc*FC .. kc*FC+FC-1
+#pragma unroll
+            for (int sh = 4, n = SBC / 2; sh >= 1; sh >>= 1, n >>= 1) {
+                const bool up = kc & sh;
+#pragma unroll
+                for (int i = 0; i < SBC / 2; ++i) {
+                    if (i < n) {
+                        const float send = up ? acc[i] : acc[i + n];
+                        const float keep = up ? acc[i + n] : acc[i];
+                        acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, sh);
+                    }
                 }
             }
-            __syncthreads();
-            if (s_abort) return;             // a peer CTA never arrived: fail loudly on the host side
-            const int tprev = t - tstep;
-            // h_{t-1}: rows of 512 floats inside out[tprev][b][dir*512 ...] -> shared (L2 loads, no L1)
-            for (int i = tid; i < BCHUNK * (HID / 4); i += 256) {
-                const int b = i >> 7, q = i & 127;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (b < a.nb)
-                    v = __ldcg(reinterpret_cast<const float4*>(
-                            a.out + ((size_t)tprev * a.B + a.b0 + b) * 1024 + dir * HID) + q);
-                reinterpret_cast<float4*>(hs)[i] = v;
+            // all 4 gate lanes of a column fetch the 4 gate sums and update the cell redundantly
+#pragma unroll
+            for (int i = 0; i < FC; ++i) {
+                const float gi = __shfl_sync(0xffffffffu, acc[i], kc) + xp[i][0];
+                const float gf = __shfl_sync(0xffffffffu, acc[i], 8 + kc) + xp[i][1];
+                const float gg = __shfl_sync(0xffffffffu, acc[i], 16 + kc) + xp[i][2];
+                const float go = __shfl_sync(0xffffffffu, acc[i], 24 + kc) + xp[i][3];
+                const float c_new = sigmoidf_(gf) * c_state[j][i] + sigmoidf_(gi) * tanhf(gg);
+                c_state[j][i] = c_new;
+                const float h_new = sigmoidf_(go) * tanhf(c_new);
+                const int col = j * SBC + kc * FC + i;
+                if (gate == 0 && col < a.nb)
+                    a.out[((size_t)t * a.B + a.b0 + col) * 1024 + dir * HID + unit] = h_new;
             }
-            __syncthreads();
-            // partial dot products over this lane's k-slice, all 32 batch columns
-#pragma unroll
-            for (int b = 0; b < BCHUNK; ++b) {
-                const float4* hp = reinterpret_cast<const float4*>(hs + b * HID);
-                float s = 0.f;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float4 h = hp[i * 8 + kc];
-                    s = fmaf(wreg[i * 4 + 0], h.x, s);
-                    s = fmaf(wreg[i * 4 + 1], h.y, s);
-                    s = fmaf(wreg[i * 4 + 2], h.z, s);
-                    s = fmaf(wreg[i * 4 + 3], h.w, s);
-                }
-                acc[b] = s;
-            }
-        }
-        // transposing butterfly over the 8 k-slices (lane bits 0..2): 32 -> 16 -> 8 -> 4 values
-        float r16[16], r8[8], r4[4];
-        {
-            const bool up = kc & 4;
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float send = up ? acc[i] : acc[i + 16];
-                const float keep = up ? acc[i + 16] : acc[i];
-                r16[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-        }
-        {
-            const bool up = kc & 2;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float send = up ? r16[i] : r16[i + 8];
-                const float keep = up ? r16[i + 8] : r16[i];
-                r8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-            }
-        }
-        {
-            const bool up = kc & 1;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const float send = up ? r8[i] : r8[i + 4];
-                const float keep = up ? r8[i + 4] : r8[i];
-                r4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-            }
-        }
-        // r4[q] = W_hh[gate row] . h[b = kc*4 + q].  Gather the 4 gates of column q == gate:
-        // lanes (g', kc) for g' = 0..3 exchange so that every lane gets all 4 gate values of ITS column.
-        float gv[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            // value wanted: gate g, column 'gate' (my own index) -> held by lane (g, kc) in r4[gate]
-            const int src_lane = g * 8 + kc;
-            float v = 0.f;
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                // every lane offers r4[q] in round q; only the lane whose 'gate' == q reads it
-                const float got = __shfl_sync(0xffffffffu, r4[q], src_lane);
-                if (gate == q) v = got;
-            }
-            gv[g] = v;
-        }
-        float h_new = 0.f;
-        if (active) {
-            const float ig = sigmoidf_(gv[0] + xp[0]);
-            const float fg = sigmoidf_(gv[1] + xp[1]);
-            const float gg = tanhf(gv[2] + xp[2]);
-            const float og = sigmoidf_(gv[3] + xp[3]);
-            c_state = fg * c_state + ig * gg;
-            h_new = og * tanhf(c_state);
-            a.out[((size_t)t * a.B + a.b0 + myb) * 1024 + dir * HID + unit] = h_new;
-        }
-        // prefetch next step's x-projection while the other CTAs catch up
-        if (active && step + 1 < a.T) {
-#pragma unroll
-            for (int g = 0; g < 4; ++g) xp[g] = __ldg(xaddr(t + tstep, g));
-        }
-        __syncthreads();                      // all h_t stores of this CTA issued
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(a.counters + dir, 1u);
+            // this warp's h_t stores are issued -> tell the signalling warp
+            __syncwarp();
+            if (lane == 0) mbar_arrive(done_bar + j);
         }
     }
 }
@@ -199,18 +222,18 @@ __global__ void __launch_bounds__(256, 1) lstm_layer_kernel(const LstmArgs a) {
 
 // One LSTM layer, both directions.  xproj [T][B][4096], out [T][B][1024].
 int lstm_layer(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, float* out, int T, int B,
-               unsigned int* counters /* >= 2 uints */, int* error_flag, cudaStream_t st) {
-    const size_t smem = (size_t)BCHUNK * HID * sizeof(float);
+               unsigned int* counters /* >= 8 uints */, int* error_flag, cudaStream_t st) {
+    const size_t smem = sizeof(float) * NSB * SBC * HID + 3 * NSB * sizeof(uint64_t);
     HN_CUDA_OK(cudaFuncSetAttribute(lstm_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int b0 = 0; b0 < B; b0 += BCHUNK) {
         LstmArgs a;
         a.xproj = xproj; a.w_hh[0] = w_hh_fwd; a.w_hh[1] = w_hh_bwd; a.out = out;
         a.counters = counters; a.error_flag = error_flag;
         a.T = T; a.B = B; a.b0 = b0; a.nb = (B - b0 < BCHUNK) ? (B - b0) : BCHUNK;
-        HN_CUDA_OK(cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned int), st));
+        HN_CUDA_OK(cudaMemsetAsync(counters, 0, 2 * NSB * sizeof(unsigned int), st));
         void* args[] = {(void*)&a};
-        HN_CUDA_OK(cudaLaunchCooperativeKernel((const void*)lstm_layer_kernel, dim3(2 * NCTA_DIR), dim3(256),
-                                               args, smem, st));
+        HN_CUDA_OK(cudaLaunchCooperativeKernel((const void*)lstm_layer_kernel, dim3(2 * NCTA_DIR),
+                                               dim3(NTHREADS), args, smem, st));
         HN_LAUNCH_OK();
     }
     return 0;
