@@ -124,18 +124,22 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_layer_kernel(const LstmArgs 
     }
 
     // =============================== compute warps ===============================
-    const int gate = lane >> 3, kc = lane & 7;
+    // warp = one hidden unit; lane = one of 32 k-slices (k = 128*i + 4*lane + e) holding the weights of all
+    // 4 gates for that slice.  (128-bit shared loads are issued per quarter-warp, so a layout where the
+    // 4 gate groups of a warp re-read the same h values costs 4x the shared-memory wavefronts: measured
+    // 16.8 K wavefronts per step, 43 % short-scoreboard stalls.  Here every lane reads distinct data.)
     const int unit = cta * UNITS + warp;                   // hidden unit of this warp
-    const int wrow = gate * HID + unit;                    // row of W_hh
-    float wreg[64];                                        // wreg[i*4+j] = W[wrow][32*i + 4*kc + j]
-    {
-        const float4* wp = reinterpret_cast<const float4*>(a.w_hh[dir] + (size_t)wrow * HID);
+    float wreg[4][16];                                     // wreg[g][i*4+e] = W_hh[g*512+unit][128*i + 4*lane + e]
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float4 v = __ldg(wp + i * 8 + kc);
-            wreg[i * 4 + 0] = v.x; wreg[i * 4 + 1] = v.y; wreg[i * 4 + 2] = v.z; wreg[i * 4 + 3] = v.w;
+    for (int g = 0; g < 4; ++g) {
+        const float4* wp = reinterpret_cast<const float4*>(a.w_hh[dir] + (size_t)(g * HID + unit) * HID);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 v = __ldg(wp + i * 32 + lane);
+            wreg[g][i * 4 + 0] = v.x; wreg[g][i * 4 + 1] = v.y; wreg[g][i * 4 + 2] = v.z; wreg[g][i * 4 + 3] = v.w;
         }
     }
+    const int gate = lane >> 3, kc = lane & 7;             // after the butterfly: lane = (gate, column kc)
     float c_state[NSB][FC];
 #pragma unroll
     for (int j = 0; j < NSB; ++j)
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_layer_kernel(const LstmArgs 
 #pragma unroll
         for (int j = 0; j < NSB; ++j) {
             if (j >= nsb) break;
-            // x-projection of the FC columns this lane finishes (all 4 gates; latency hides behind the FMAs)
+            // x-projection of the column this lane finishes (all 4 gates; latency hides behind the FMAs)
             float xp[FC][4];
 #pragma unroll
             for (int i = 0; i < FC; ++i) {
@@ -156,40 +160,39 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_layer_kernel(const LstmArgs 
 #pragma unroll
                 for (int g = 0; g < 4; ++g) xp[i][g] = __ldg(xb + g * HID);
             }
-            float acc[SBC];
+            // acc[g*SBC + b]: partial dot product of gate g with column b over this lane's k-slice
+            float acc[4 * SBC];
+#pragma unroll
+            for (int v = 0; v < 4 * SBC; ++v) acc[v] = 0.f;
             if (step > 0) {
                 mbar_wait(full_bar + j, (step - 1) & 1);
 #pragma unroll
                 for (int b = 0; b < SBC; ++b) {
                     const float4* hp = reinterpret_cast<const float4*>(&hs[j][b * HID]);
-                    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-                    for (int i = 0; i < 16; i += 2) {
-                        const float4 h0 = hp[i * 8 + kc], h1 = hp[(i + 1) * 8 + kc];
-                        s0 = fmaf(wreg[i * 4 + 0], h0.x, s0);
-                        s1 = fmaf(wreg[i * 4 + 4], h1.x, s1);
-                        s0 = fmaf(wreg[i * 4 + 1], h0.y, s0);
-                        s1 = fmaf(wreg[i * 4 + 5], h1.y, s1);
-                        s0 = fmaf(wreg[i * 4 + 2], h0.z, s0);
-                        s1 = fmaf(wreg[i * 4 + 6], h1.z, s1);
-                        s0 = fmaf(wreg[i * 4 + 3], h0.w, s0);
-                        s1 = fmaf(wreg[i * 4 + 7], h1.w, s1);
+                    for (int i = 0; i < 4; ++i) {
+                        const float4 h = hp[i * 32 + lane];
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            float s = acc[g * SBC + b];
+                            s = fmaf(wreg[g][i * 4 + 0], h.x, s);
+                            s = fmaf(wreg[g][i * 4 + 1], h.y, s);
+                            s = fmaf(wreg[g][i * 4 + 2], h.z, s);
+                            s = fmaf(wreg[g][i * 4 + 3], h.w, s);
+                            acc[g * SBC + b] = s;
+                        }
                     }
-                    acc[b] = s0 + s1;
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty_bar + j);                     // this warp is done with hs[j]
-            } else {
-#pragma unroll
-                for (int b = 0; b < SBC; ++b) acc[b] = 0.f;
             }
-            // transposing butterfly over the 8 k-slices (lane bits 2,1,0): SBC -> SBC/8 values per lane;
-            // lane (gate, kc) ends with the sums of columns kc*FC .. kc*FC+FC-1
+            // transposing butterfly over the 32 k-slices (lane bits 4..0): 4*SBC -> FC values per lane;
+            // lane L ends with value indices L*FC .. L*FC+FC-1, i.e. gate L/8, columns (L%8)*FC + i
 #pragma unroll
-            for (int sh = 4, n = SBC / 2; sh >= 1; sh >>= 1, n >>= 1) {
-                const bool up = kc & sh;
+            for (int sh = 16, n = 2 * SBC; sh >= 1; sh >>= 1, n >>= 1) {
+                const bool up = lane & sh;
 #pragma unroll
-                for (int i = 0; i < SBC / 2; ++i) {
+                for (int i = 0; i < 2 * SBC; ++i) {
                     if (i < n) {
                         const float send = up ? acc[i] : acc[i + n];
                         const float keep = up ? acc[i + n] : acc[i];
