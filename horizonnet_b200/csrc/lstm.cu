@@ -55,6 +55,10 @@ __device__ __forceinline__ unsigned int ld_acquire(const unsigned int* p) {
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
+// two independent fp32 FMAs in one instruction (sm_100+): d.lo += a.lo*b.lo, d.hi += a.hi*b.hi
+__device__ __forceinline__ void fma2(unsigned long long& d, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
 __device__ __forceinline__ void red_release_add(unsigned int* p, unsigned int v) {
     asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -129,14 +133,16 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_layer_kernel(const LstmArgs 
     // 4 gate groups of a warp re-read the same h values costs 4x the shared-memory wavefronts: measured
     // 16.8 K wavefronts per step, 43 % short-scoreboard stalls.  Here every lane reads distinct data.)
     const int unit = cta * UNITS + warp;                   // hidden unit of this warp
-    float wreg[4][16];                                     // wreg[g][i*4+e] = W_hh[g*512+unit][128*i + 4*lane + e]
+    // weights as packed fp32 pairs for fma.rn.f32x2 (Blackwell: two fp32 FMAs per issue slot):
+    // wreg[g][2*i+p] = (W_hh[g*512+unit][k], W[..][k+1]),  k = 128*i + 4*lane + 2*p
+    unsigned long long wreg[4][8];
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        const float4* wp = reinterpret_cast<const float4*>(a.w_hh[dir] + (size_t)(g * HID + unit) * HID);
+        const ulonglong2* wp = reinterpret_cast<const ulonglong2*>(a.w_hh[dir] + (size_t)(g * HID + unit) * HID);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const float4 v = __ldg(wp + i * 32 + lane);
-            wreg[g][i * 4 + 0] = v.x; wreg[g][i * 4 + 1] = v.y; wreg[g][i * 4 + 2] = v.z; wreg[g][i * 4 + 3] = v.w;
+            const ulonglong2 v = __ldg(wp + i * 32 + lane);
+            wreg[g][2 * i + 0] = v.x; wreg[g][2 * i + 1] = v.y;
         }
     }
     const int gate = lane >> 3, kc = lane & 7;             // after the butterfly: lane = (gate, column kc)
@@ -162,29 +168,32 @@ __global__ void __launch_bounds__(NTHREADS, 1) lstm_layer_kernel(const LstmArgs 
             }
             // acc[g*SBC + b]: partial dot product of gate g with column b over this lane's k-slice
             float acc[4 * SBC];
-#pragma unroll
-            for (int v = 0; v < 4 * SBC; ++v) acc[v] = 0.f;
             if (step > 0) {
+                unsigned long long acc2[4 * SBC];          // (even-k partial sum, odd-k partial sum)
+#pragma unroll
+                for (int v = 0; v < 4 * SBC; ++v) acc2[v] = 0ull;
                 mbar_wait(full_bar + j, (step - 1) & 1);
 #pragma unroll
                 for (int b = 0; b < SBC; ++b) {
-                    const float4* hp = reinterpret_cast<const float4*>(&hs[j][b * HID]);
+                    const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(&hs[j][b * HID]);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
-                        const float4 h = hp[i * 32 + lane];
+                        const ulonglong2 h = hp[i * 32 + lane];
 #pragma unroll
                         for (int g = 0; g < 4; ++g) {
-                            float s = acc[g * SBC + b];
-                            s = fmaf(wreg[g][i * 4 + 0], h.x, s);
-                            s = fmaf(wreg[g][i * 4 + 1], h.y, s);
-                            s = fmaf(wreg[g][i * 4 + 2], h.z, s);
-                            s = fmaf(wreg[g][i * 4 + 3], h.w, s);
-                            acc[g * SBC + b] = s;
+                            fma2(acc2[g * SBC + b], wreg[g][2 * i + 0], h.x);
+                            fma2(acc2[g * SBC + b], wreg[g][2 * i + 1], h.y);
                         }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(empty_bar + j);                     // this warp is done with hs[j]
+#pragma unroll
+                for (int v = 0; v < 4 * SBC; ++v)
+                    acc[v] = __uint_as_float((unsigned)(acc2[v] & 0xffffffffull)) + __uint_as_float((unsigned)(acc2[v] >> 32));
+            } else {
+#pragma unroll
+                for (int v = 0; v < 4 * SBC; ++v) acc[v] = 0.f;
             }
             // transposing butterfly over the 32 k-slices (lane bits 4..0): 4*SBC -> FC values per lane;
             // lane L ends with value indices L*FC .. L*FC+FC-1, i.e. gate L/8, columns (L%8)*FC + i

@@ -149,6 +149,12 @@ struct hn_model {
     unsigned int* counters = nullptr;
     int* error_flag = nullptr;
     float *x_in = nullptr, *bon_out = nullptr, *cor_out = nullptr;    // for forward_host
+    // pipelined host API: 2 input slots, a copy stream and a compute stream (H2D of batch i+1 overlaps forward i)
+    float* x_slot[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr, compute_stream = nullptr;
+    cudaEvent_t slot_ready[2] = {nullptr, nullptr};
+    int slot_batch[2] = {0, 0};
+    int submit_count = 0, collect_count = 0;
     int last_batch = 0;
 
     // optional per-op-class timing (bench.py roofline): CUDA event pairs around every launch
@@ -164,6 +170,9 @@ struct hn_model {
         cudaSetDevice(device);
         for (auto& sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
         for (auto e : free_events) cudaEventDestroy(e);
+        for (int i = 0; i < 2; ++i) if (slot_ready[i]) cudaEventDestroy(slot_ready[i]);
+        if (copy_stream) cudaStreamDestroy(copy_stream);
+        if (compute_stream) cudaStreamDestroy(compute_stream);
         for (void* p : allocs) cudaFree(p);
     }
     cudaEvent_t get_event() {
@@ -344,6 +353,7 @@ int hn_model_create(int device, int max_batch, hn_model** out) {
         {&m->GO[2], B * 2 * 66 * 128},  {&m->GO[3], B * 1 * 34 * 256},  {&m->SEQ, 256 * B * 1024},
         {&m->XP, (256 * B * 4096 > (size_t)4096 * 1024) ? 256 * B * 4096 : (size_t)4096 * 1024},       {&m->R1, 256 * B * 1024},       {&m->R2, 256 * B * 1024},       {&m->R1S, 256 * B * 1024},
         {&m->x_in, B * 3 * 512 * 1024}, {&m->bon_out, B * 2 * 1024},    {&m->cor_out, B * 1024},
+        {&m->x_slot[1], B * 3 * 512 * 1024},
         {&m->head_w, 12 * 1024},        {&m->head_b, 12},
     };
     for (auto& b : bufs)
@@ -351,6 +361,10 @@ int hn_model_create(int device, int max_batch, hn_model** out) {
     if (m->alloc_t(&m->counters, 16)) return -1;
     if (m->alloc_t(&m->error_flag, 1)) return -1;
     HN_CUDA_OK(cudaMemset(m->error_flag, 0, sizeof(int)));
+    m->x_slot[0] = m->x_in;
+    HN_CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    HN_CUDA_OK(cudaStreamCreateWithFlags(&m->compute_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) HN_CUDA_OK(cudaEventCreateWithFlags(&m->slot_ready[i], cudaEventDisableTiming));
     *out = m.release();
     return 0;
 }
@@ -574,6 +588,38 @@ int hn_model_forward_host(hn_model* m, const float* x, int B, int in_channels, f
     HN_CUDA_OK(cudaMemcpyAsync(cor, m->cor_out, (size_t)B * 1024 * sizeof(float), cudaMemcpyDeviceToHost, st));
     HN_CUDA_OK(cudaStreamSynchronize(st));
     return hn_model_check(m);
+}
+
+int hn_model_submit_host(hn_model* m, const float* x, int B, int in_channels) {
+    HN_CHECK(m && x, "hn_model_submit_host: NULL argument");
+    HN_CHECK(B >= 1 && B <= m->max_batch, "hn_model_submit_host: batch exceeds max_batch");
+    HN_CHECK(in_channels >= 3, "hn_model_submit_host: need >= 3 channels");
+    HN_CHECK(m->submit_count - m->collect_count < 2, "hn_model_submit_host: both input slots are in flight (collect first)");
+    HN_CUDA_OK(cudaSetDevice(m->device));
+    const int slot = m->submit_count & 1;
+    for (int b = 0; b < B; ++b)
+        HN_CUDA_OK(cudaMemcpyAsync(m->x_slot[slot] + (size_t)b * 3 * 512 * 1024, x + (size_t)b * in_channels * 512 * 1024,
+                                   (size_t)3 * 512 * 1024 * sizeof(float), cudaMemcpyHostToDevice, m->copy_stream));
+    HN_CUDA_OK(cudaEventRecord(m->slot_ready[slot], m->copy_stream));
+    m->slot_batch[slot] = B;
+    ++m->submit_count;
+    return 0;
+}
+
+int hn_model_collect_host(hn_model* m, float* bon, float* cor) {
+    HN_CHECK(m && bon && cor, "hn_model_collect_host: NULL argument");
+    HN_CHECK(m->collect_count < m->submit_count, "hn_model_collect_host: nothing submitted");
+    HN_CUDA_OK(cudaSetDevice(m->device));
+    const int slot = m->collect_count & 1;
+    const int B = m->slot_batch[slot];
+    cudaStream_t st = m->compute_stream;
+    HN_CUDA_OK(cudaStreamWaitEvent(st, m->slot_ready[slot], 0));
+    if (hn_model_forward(m, m->x_slot[slot], B, 3, m->bon_out, m->cor_out, st)) return -1;
+    HN_CUDA_OK(cudaMemcpyAsync(bon, m->bon_out, (size_t)B * 2 * 1024 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HN_CUDA_OK(cudaMemcpyAsync(cor, m->cor_out, (size_t)B * 1024 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HN_CUDA_OK(cudaStreamSynchronize(st));
+    ++m->collect_count;
+    return 0;
 }
 
 int hn_model_stage(hn_model* m, const char* stage, float* out, long long capacity, int dims[4], void* stream) {

@@ -229,6 +229,26 @@ class HorizonNet(nn.Module):
                    'hn_model_forward_host')
         return bon, cor
 
+    def submit_host(self, x_host, device=0):
+        """Pipelined host API (hn_model_submit_host): enqueue the upload of a batch; pair with collect_host()."""
+        xt = torch.as_tensor(x_host)
+        if xt.is_cuda or xt.dtype != torch.float32 or not xt.is_contiguous():
+            raise RuntimeError('submit_host expects a contiguous fp32 host array')
+        if xt.shape[2] != PANO_H or xt.shape[3] != PANO_W:
+            raise NotImplementedError()
+        h = self._handle(torch.device('cuda', device), xt.shape[0])
+        _lib.check(_lib.lib().hn_model_submit_host(h['ptr'], xt.data_ptr(), xt.shape[0], xt.shape[1]), 'hn_model_submit_host')
+        h.setdefault('pending', []).append((xt, xt.shape[0]))        # keep the host buffer alive until collected
+
+    def collect_host(self, device=0):
+        """Forward + D2H of the oldest submitted batch -> (bon, cor) CPU tensors."""
+        h = self._handles[device]
+        _, B = h['pending'].pop(0)
+        bon = torch.empty(B, 2, PANO_W, dtype=torch.float32)
+        cor = torch.empty(B, 1, PANO_W, dtype=torch.float32)
+        _lib.check(_lib.lib().hn_model_collect_host(h['ptr'], bon.data_ptr(), cor.data_ptr()), 'hn_model_collect_host')
+        return bon, cor
+
     def debug_stage(self, name, device=None):
         """Intermediate result of the last forward in the reference's layout (test hook)."""
         lib = _lib.lib()

@@ -63,6 +63,15 @@ int hn_model_forward(hn_model* m, const float* x_nchw_dev, int batch, int in_cha
 int hn_model_forward_host(hn_model* m, const float* x_nchw_host, int batch, int in_channels,
                           float* bon_host, float* cor_host);
 
+/* Pipelined form of the host call for streams of batches: hn_model_submit_host enqueues the H2D
+ * copy of a batch (pinned memory recommended) on an internal copy stream into one of two input
+ * slots and returns; hn_model_collect_host runs the forward of the OLDEST submitted batch on an
+ * internal compute stream, copies bon/cor back and synchronises.  Calling submit(i+1) before
+ * collect(i) overlaps the upload of the next batch with the forward of the current one
+ * (at most 2 batches in flight).  Results are identical to hn_model_forward_host. */
+int hn_model_submit_host(hn_model* m, const float* x_nchw_host, int batch, int in_channels);
+int hn_model_collect_host(hn_model* m, float* bon_host, float* cor_host);
+
 /* Test hook: copies an intermediate result of the LAST forward, converted to the reference's
  * layout, into `out_dev` (fp32).  Stages: "layer1".."layer4" (NCHW [B,C,H,W], model.py:78-81),
  * "feature" ([B,1024,256], model.py:175-178), "rnn_out" ([256,B,1024], model.py:264).

@@ -174,6 +174,16 @@ def test_forward_host_equals_device_forward():
         bon, cor = net(x.to(DEV))
     hb, hc = net.forward_host(x.pin_memory())
     assert torch.equal(hb, bon.cpu()) and torch.equal(hc, cor.cpu())
+    # pipelined host API: two batches in flight, results in submission order
+    x2 = synthetic_panoramas(1, seed=10)
+    with torch.no_grad():
+        bon2, cor2 = net(x2.to(DEV))
+    net.submit_host(x.pin_memory())
+    net.submit_host(x2.pin_memory())
+    pb, pc = net.collect_host()
+    qb, qc = net.collect_host()
+    assert torch.equal(pb, bon.cpu()) and torch.equal(pc, cor.cpu())
+    assert torch.equal(qb, bon2.cpu()) and torch.equal(qc, cor2.cpu())
 
 
 def test_zero_head_weight_gives_bias_exactly():
