@@ -138,6 +138,7 @@ struct TcArgs {
     size_t out_plane;         // elements per plane
     int relu;
     int seg;                  // K chunks per hi*hi accumulation segment
+    int dbg;                  // HN_TC_DBG experiment bits: 1 skip residual reads, 2 skip output stores, 4 skip epilogue math
 };
 
 template <int BN>
@@ -402,7 +403,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     y[j + 2] = fmaf(sum[ch * 32 + j + 2] + __uint_as_float(v[j + 2]), sc.z, sf.z);
                     y[j + 3] = fmaf(sum[ch * 32 + j + 3] + __uint_as_float(v[j + 3]), sc.w, sf.w);
                 }
-                if (a.res) {
+                if (a.res && !(a.dbg & 1)) {
                     uint4 rh[4], rl[4];
                     const size_t pitch = (size_t)a.Cout * 2, colb = (size_t)n0 * 2;
                     get64(reinterpret_cast<const uint8_t*>(a.res), pitch, colb, rh);
@@ -422,6 +423,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int j = 0; j < CW; ++j) y[j] = fmaxf(y[j], 0.f);
                 }
+                if (a.dbg & 2) continue;
                 if (a.out_f32) {
                     const size_t pitch = (size_t)a.Cout * 4;
                     uint8_t* base = reinterpret_cast<uint8_t*>(a.out_f32);
@@ -452,6 +454,252 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             __syncwarp();
             if (lane == 0) mbar_arrive(cempty_bar + cbuf);
         }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ================================================================================================
+// gemm_tc_kernel: 1x1 stride-1 convolutions in GEMM mode with K <= 512 (all conv3 / most conv1 of the
+// bottlenecks).  These layers are bound by the epilogue, not by the MMAs: in conv_tc_kernel the residual
+// loads and the output stores of a tile sit in the epilogue warps' dependency chain (measured: 4.7 of
+// 13.3 ms of the encoder convs disappear when those memory instructions are removed, HN_TC_DBG).  Here
+// all epilogue traffic is asynchronous: the producer warp TMA-loads the residual tile (hi, lo planes,
+// 128 rows x 64 channels, 128-byte swizzle) into one of two epilogue buffers a whole tile ahead, the
+// epilogue warps update it IN PLACE from TMEM (BN scale/shift, + residual, ReLU, re-split) and one thread
+// hands the buffer to the TMA engine for the store.  Tiles are 128 x 64 so that a 3-stage operand ring
+// (48 KB/stage) and the two 32 KB epilogue buffers fit into shared memory together.
+constexpr int GBN = 64;
+
+struct GSmem {
+    static constexpr int A_PLANE = BM * BKC * 2;          // 16 KB
+    static constexpr int B_PLANE = GBN * BKC * 2;         // 8 KB
+    static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;            // 48 KB
+    static constexpr int E_PLANE = BM * GBN * 2;          // 16 KB: 128 rows x 64 channels fp16
+    static constexpr int EBUF = 2 * E_PLANE;              // hi + lo
+    static constexpr int EPI_OFF = STAGES * STAGE;        // 144 KB
+    static constexpr int BAR_OFF = EPI_OFF + 2 * EBUF;    // 208 KB
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+    static constexpr int TMEM_COLS = 4 * GBN;
+};
+
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, const void* src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const TcArgs a) {
+    using S = GSmem;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;       // [2] hi*hi segment accumulator ready
+    uint64_t* tempty_bar = tfull_bar + 2;           // [2] hi*hi segment accumulator drained
+    uint64_t* cempty_bar = tempty_bar + 2;          // [2] cross-product accumulator drained
+    uint64_t* rfull_bar = cempty_bar + 2;           // [2] epilogue buffer holds the residual tile (or is simply free)
+    uint64_t* efree_bar = rfull_bar + 2;            // [2] the TMA store has finished reading the epilogue buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(efree_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool has_res = a.res != nullptr;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 8); mbar_init(cempty_bar + i, 8);
+            mbar_init(rfull_bar + i, 1); mbar_init(efree_bar + i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+                const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+                // operands first: the MMAs of this tile overlap the epilogue of the previous one
+                for (int kc = 0; kc < a.num_kc; ++kc) {
+                    mbar_wait(empty_bar + stage, phase ^ 1);
+                    uint8_t* sA = smem + stage * S::STAGE;
+                    uint8_t* sB = sA + 2 * S::A_PLANE;
+                    mbar_expect_tx(full_bar + stage, 2u * S::A_PLANE + 2u * S::B_PLANE);
+                    tma_load_3d(sA, &tmA, full_bar + stage, kc * BKC, mt * BM, 0);
+                    tma_load_3d(sA + S::A_PLANE, &tmA, full_bar + stage, kc * BKC, mt * BM, 1);
+                    tma_load_3d(sB, &tmB, full_bar + stage, kc * BKC, nt * GBN, 0);
+                    tma_load_3d(sB + S::B_PLANE, &tmB, full_bar + stage, kc * BKC, nt * GBN, 1);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+                // epilogue buffer of this tile: wait until its previous store is done, then load the residual
+                const int eb = it & 1;
+                mbar_wait(efree_bar + eb, ((it >> 1) & 1) ^ 1);
+                uint8_t* ebuf = smem + S::EPI_OFF + eb * S::EBUF;
+                if (has_res) {
+                    mbar_expect_tx(rfull_bar + eb, 2u * S::E_PLANE);
+                    tma_load_3d(ebuf, &tmR, rfull_bar + eb, nt * GBN, mt * BM, 0);
+                    tma_load_3d(ebuf + S::E_PLANE, &tmR, rfull_bar + eb, nt * GBN, mt * BM, 1);
+                } else {
+                    mbar_arrive(rfull_bar + eb);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer (same scheme as conv_tc_kernel) ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(GBN, 0, 0);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0, g = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+                const int cbuf = it & 1;
+                mbar_wait(cempty_bar + cbuf, ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_cross = tmem_base + (2 + cbuf) * GBN;
+                uint32_t d_main = tmem_base;
+                int seg_pos = 0, mbuf = 0;
+                for (int kc = 0; kc < a.num_kc; ++kc) {
+                    if (seg_pos == 0) {
+                        mbuf = g & 1;
+                        mbar_wait(tempty_bar + mbuf, ((g >> 1) & 1) ^ 1);
+                        tc_fence_after();
+                        d_main = tmem_base + mbuf * GBN;
+                    }
+                    mbar_wait(full_bar + stage, phase);
+                    tc_fence_after();
+                    const uint32_t sA = smem_u32(smem + stage * S::STAGE);
+                    const uint32_t sB = sA + 2 * S::A_PLANE;
+                    const uint64_t a_hi = umma_desc_sw128(sA), a_lo = umma_desc_sw128(sA + S::A_PLANE);
+                    const uint64_t b_hi = umma_desc_sw128(sB), b_lo = umma_desc_sw128(sB + S::B_PLANE);
+#pragma unroll
+                    for (int k = 0; k < BKC / 16; ++k) {
+                        const uint64_t ko = (uint64_t)((k * 16 * 2) >> 4);
+                        umma_f16(d_main, a_hi + ko, b_hi + ko, idesc, (seg_pos | k) != 0);
+                        umma_f16(d_cross, a_hi + ko, b_lo + ko, idesc, (kc | k) != 0);
+                        umma_f16(d_cross, a_lo + ko, b_hi + ko, idesc, 1);
+                    }
+                    umma_commit(empty_bar + stage);
+                    if (++seg_pos == a.seg || kc == a.num_kc - 1) {
+                        umma_commit(tfull_bar + mbuf);
+                        seg_pos = 0;
+                        ++g;
+                    }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        // =============================== epilogue ===============================
+        const int q = warp & 3;                          // TMEM lane quarter
+        const int half = (warp - EPI_WARP0) >> 2;        // column half: 32 of the 64 columns
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int nseg = (a.num_kc + a.seg - 1) / a.seg;
+        const int r = q * 32 + lane;                     // row of the tile owned by this thread
+        int it = 0, g = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+            const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+            const int cbuf = it & 1, eb = it & 1;
+            float sum[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) sum[j] = 0.f;
+            for (int sgi = 0; sgi < nseg; ++sgi, ++g) {
+                const int mbuf = g & 1;
+                mbar_wait(tfull_bar + mbuf, (g >> 1) & 1);
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_base + (uint32_t)(mbuf * GBN + half * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(v[j]);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar + mbuf);
+            }
+            {   // cross products, then give both accumulators back before the math
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_base + (uint32_t)((2 + cbuf) * GBN + half * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sum[j] += __uint_as_float(v[j]);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(cempty_bar + cbuf);
+            }
+            const int n0 = nt * GBN + half * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + n0 + j));
+                const float4 sf = __ldg(reinterpret_cast<const float4*>(a.shift + n0 + j));
+                sum[j + 0] = fmaf(sum[j + 0], sc.x, sf.x);
+                sum[j + 1] = fmaf(sum[j + 1], sc.y, sf.y);
+                sum[j + 2] = fmaf(sum[j + 2], sc.z, sf.z);
+                sum[j + 3] = fmaf(sum[j + 3], sc.w, sf.w);
+            }
+            // epilogue buffer: row r, 16-byte chunk c lives at r*128 + ((c ^ (r & 7)) << 4)  (128-byte swizzle)
+            mbar_wait(rfull_bar + eb, (it >> 1) & 1);
+            const uint32_t e_hi = smem_u32(smem + S::EPI_OFF + eb * S::EBUF) + r * 128;
+            const uint32_t e_lo = e_hi + S::E_PLANE;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const uint32_t off = (uint32_t)(((half * 4 + c) ^ (r & 7)) << 4);
+                float* y = sum + c * 8;
+                if (has_res) {
+                    const uint4 h = ld_shared_v4(e_hi + off), l = ld_shared_v4(e_lo + off);
+                    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 fh = unpack_half2(hw[e]), fl = unpack_half2(lw[e]);
+                        y[2 * e + 0] += fh.x + fl.x;
+                        y[2 * e + 1] += fh.y + fl.y;
+                    }
+                }
+                if (a.relu) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.f);
+                }
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split2_scaled(y[2 * e], y[2 * e + 1], ph[e], pl[e]);
+                st_shared_v4(e_hi + off, make_uint4(ph[0], ph[1], ph[2], ph[3]));
+                st_shared_v4(e_lo + off, make_uint4(pl[0], pl[1], pl[2], pl[3]));
+            }
+            // make the generic-proxy writes visible to the TMA engine, wait for all 8 epilogue warps, store
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("bar.sync 2, 256;" ::: "memory");
+            if (warp == EPI_WARP0 && lane == 0) {
+                const uint8_t* ebuf = smem + S::EPI_OFF + eb * S::EBUF;
+                tma_store_3d(&tmO, ebuf, nt * GBN, mt * BM, 0);
+                tma_store_3d(&tmO, ebuf + S::E_PLANE, nt * GBN, mt * BM, 1);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (it > 0) {       // the previous tile's store has read its buffer by now: hand that buffer back
+                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    mbar_arrive(efree_bar + ((it - 1) & 1));
+                }
+            }
+        }
+        if (warp == EPI_WARP0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores landed
     }
 
     tc_fence_before();
@@ -561,7 +809,47 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
     a.res = res_planes; a.out = out_planes; a.out_f32 = out_f32; a.out_plane = out_plane; a.relu = d.relu;
     a.Bimg = in.B;
     a.seg = tc_segment_chunks();
+    { static int dbg = [] { const char* e = getenv("HN_TC_DBG"); return e ? atoi(e) : 0; }(); a.dbg = dbg; }
     long long m_tiles;
+    // asynchronous-epilogue GEMM kernel: plane output, K <= 512, Cout a multiple of 64
+    static const bool gemm_kernel_on = [] { const char* e = getenv("HN_TC_GEMM"); return !(e && atoi(e) == 0); }();
+    const bool use_gemm_kernel = gemm && gemm_kernel_on && !out_f32 && d.Cin <= 512 && d.Cout % GBN == 0;
+    if (use_gemm_kernel) {
+        const long long Mtot = (long long)in.B * in.H * in.Wp();
+        a.mode = 0;
+        a.M = (int)Mtot;
+        a.n_tiles = d.Cout / GBN;
+        CUtensorMap tmR, tmO;
+        {
+            cuuint64_t dims[3] = {(cuuint64_t)d.Cin, (cuuint64_t)Mtot, 2};
+            cuuint64_t str[2] = {(cuuint64_t)d.Cin * 2, (cuuint64_t)in_plane * 2};
+            cuuint32_t box[3] = {BKC, BM, 1};
+            if (make_map(&tmA, in_planes, 3, dims, str, box)) return -1;
+        }
+        {
+            cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)d.Cout, 2};
+            cuuint64_t str[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * d.Cout * 2};
+            cuuint32_t box[3] = {BKC, GBN, 1};
+            if (make_map(&tmB, wq, 3, dims, str, box)) return -1;
+        }
+        {
+            cuuint64_t dims[3] = {(cuuint64_t)d.Cout, (cuuint64_t)Mtot, 2};
+            cuuint64_t str[2] = {(cuuint64_t)d.Cout * 2, (cuuint64_t)out_plane * 2};
+            cuuint32_t box[3] = {GBN, BM, 1};
+            if (make_map(&tmO, out_planes, 3, dims, str, box)) return -1;
+            if (make_map(&tmR, res_planes ? res_planes : out_planes, 3, dims, str, box)) return -1;
+        }
+        const long long mt = (Mtot + BM - 1) / BM;
+        HN_CHECK(mt * a.n_tiles < (1ll << 31), "conv_tc: too many tiles");
+        a.num_tiles = (int)(mt * a.n_tiles);
+        HN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GSmem::TOTAL));
+        int dev = 0, sms = 0;
+        HN_CUDA_OK(cudaGetDevice(&dev));
+        HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        gemm_tc_kernel<<<a.num_tiles < sms ? a.num_tiles : sms, NTHREADS, GSmem::TOTAL, st>>>(tmA, tmB, tmR, tmO, a);
+        HN_LAUNCH_OK();
+        return 0;
+    }
     if (gemm) {
         const long long Mtot = (long long)in.B * in.H * in.Wp();
         a.mode = 0;
