@@ -465,7 +465,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // ================================================================================================
-// gemm_tc_kernel: 1x1 stride-1 convolutions in GEMM mode with K <= 512 (all conv3 / most conv1 of the
+// gemm_tc_kernel: 1x1 stride-1 convolutions in GEMM mode with K <= 256 (conv3 / conv1 of layer1-3: the
 // bottlenecks).  These layers are bound by the epilogue, not by the MMAs: in conv_tc_kernel the residual
 // loads and the output stores of a tile sit in the epilogue warps' dependency chain (measured: 4.7 of
 // 13.3 ms of the encoder convs disappear when those memory instructions are removed, HN_TC_DBG).  Here
@@ -508,7 +508,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* cempty_bar = tempty_bar + 2;          // [2] cross-product accumulator drained
     uint64_t* rfull_bar = cempty_bar + 2;           // [2] epilogue buffer holds the residual tile (or is simply free)
     uint64_t* efree_bar = rfull_bar + 2;            // [2] the TMA store has finished reading the epilogue buffer
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(efree_bar + 2);
+    uint64_t* oready_bar = efree_bar + 2;           // [2] all 8 epilogue warps have written their part of the output tile
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(oready_bar + 2);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool has_res = a.res != nullptr;
 
@@ -521,7 +522,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 8); mbar_init(cempty_bar + i, 8);
-            mbar_init(rfull_bar + i, 1); mbar_init(efree_bar + i, 1);
+            mbar_init(rfull_bar + i, 1); mbar_init(efree_bar + i, 1); mbar_init(oready_bar + i, 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -685,21 +686,30 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 st_shared_v4(e_hi + off, make_uint4(ph[0], ph[1], ph[2], ph[3]));
                 st_shared_v4(e_lo + off, make_uint4(pl[0], pl[1], pl[2], pl[3]));
             }
-            // make the generic-proxy writes visible to the TMA engine, wait for all 8 epilogue warps, store
+            // make the generic-proxy writes visible to the TMA engine and tell the store warp
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-            asm volatile("bar.sync 2, 256;" ::: "memory");
-            if (warp == EPI_WARP0 && lane == 0) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(oready_bar + eb);
+        }
+    } else if (warp == 3) {
+        // =============================== store warp ===============================
+        // one thread hands finished output tiles to the TMA engine and returns the buffer to the producer
+        // as soon as the engine has read it, so the residual of tile it+2 is prefetched a whole tile ahead
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+                const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+                const int eb = it & 1;
+                mbar_wait(oready_bar + eb, (it >> 1) & 1);
                 const uint8_t* ebuf = smem + S::EPI_OFF + eb * S::EBUF;
                 tma_store_3d(&tmO, ebuf, nt * GBN, mt * BM, 0);
                 tma_store_3d(&tmO, ebuf + S::E_PLANE, nt * GBN, mt * BM, 1);
                 asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                if (it > 0) {       // the previous tile's store has read its buffer by now: hand that buffer back
-                    asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-                    mbar_arrive(efree_bar + ((it - 1) & 1));
-                }
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(efree_bar + eb);
             }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");          // all stores have landed
         }
-        if (warp == EPI_WARP0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // stores landed
     }
 
     tc_fence_before();
@@ -813,7 +823,7 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
     long long m_tiles;
     // asynchronous-epilogue GEMM kernel: plane output, K <= 512, Cout a multiple of 64
     static const bool gemm_kernel_on = [] { const char* e = getenv("HN_TC_GEMM"); return !(e && atoi(e) == 0); }();
-    const bool use_gemm_kernel = gemm && gemm_kernel_on && !out_f32 && d.Cin <= 512 && d.Cout % GBN == 0;
+    const bool use_gemm_kernel = gemm && gemm_kernel_on && !out_f32 && d.Cin <= 256 && d.Cout % GBN == 0;
     if (use_gemm_kernel) {
         const long long Mtot = (long long)in.B * in.H * in.Wp();
         a.mode = 0;
