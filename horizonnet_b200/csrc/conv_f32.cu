@@ -229,7 +229,11 @@ namespace {
 constexpr int ST_TW = 64, ST_TH = 4;
 constexpr int ST_PW = ST_TW * 2 + 5;   // 133 input cols
 constexpr int ST_PH = ST_TH * 2 + 5;   // 13 input rows
+constexpr int ST_PP = 136;             // patch row pitch: multiple of 4 floats so rows can be read as float4
 
+// thread = 4 consecutive output pixels x 16 output channels.  Per (dy, c) the 13 input values the 4 pixels
+// need for all 7 dx taps are read once (4 x LDS.128) and the 7 x 4 weight vectors once each, i.e. 32 shared
+// loads per 448 FMAs: the kernel runs at the fp32 FMA rate instead of the shared-memory rate.
 __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, int Cx,
                                                    const float* __restrict__ w,      // [147][64], k=(dy*7+dx)*3+c
                                                    const float* __restrict__ scale,
@@ -237,8 +241,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
                                                    float* __restrict__ out, int Hin, int Win) {
     extern __shared__ __align__(16) float smem[];
     float* ws = smem;                              // 147*64
-    float* patch = smem + 147 * 64;                // [3][ST_PH][ST_PW+1]
-    constexpr int PP = ST_PW + 1;
+    float* patch = smem + 147 * 64;                // [3][ST_PH][ST_PP]
     const int Ho = Hin / 2, Wo = Win / 2;
     const int b = blockIdx.z;
     const int ho0 = blockIdx.y * ST_TH, wo0 = blockIdx.x * ST_TW;
@@ -248,57 +251,81 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
     const float mean[3] = {0.485f, 0.456f, 0.406f};       // reference model.py:186
     const float stdv[3] = {0.229f, 0.224f, 0.225f};       // reference model.py:187
     const int hi0 = ho0 * 2 - 3, wi0 = wo0 * 2 - 3;
-    for (int i = tid; i < 3 * ST_PH * ST_PW; i += 256) {
-        int c = i / (ST_PH * ST_PW);
-        int r = i - c * (ST_PH * ST_PW);
-        int py = r / ST_PW, px = r - py * ST_PW;
+    for (int i = tid; i < 3 * ST_PH * ST_PP; i += 256) {
+        int c = i / (ST_PH * ST_PP);
+        int r = i - c * (ST_PH * ST_PP);
+        int py = r / ST_PP, px = r - py * ST_PP;
         int hi = hi0 + py;
         int wi = wi0 + px;
         wi = wi < 0 ? wi + Win : (wi >= Win ? wi - Win : wi);       // circular W (model.py:27-29)
         float v = 0.f;                                               // zero H pad of the *normalised* input
-        if (hi >= 0 && hi < Hin)
+        if (px < ST_PW && hi >= 0 && hi < Hin)
             v = (__ldg(x + (((size_t)b * Cx + c) * Hin + hi) * Win + wi) - mean[c]) / stdv[c];
-        patch[(c * ST_PH + py) * PP + px] = v;
+        patch[i] = v;
     }
     __syncthreads();
-    const int ly = tid / ST_TW, lx = tid % ST_TW;
-    float acc[64];
+    const int cg = tid & 3;                        // channel group: channels cg*16 .. +15
+    const int pg = tid >> 2;                       // pixel group: 4 consecutive pixels of one row
+    const int ly = pg >> 4, lx0 = (pg & 15) * 4;
+    float acc[4][16];
 #pragma unroll
-    for (int n = 0; n < 64; ++n) acc[n] = 0.f;
-    for (int dy = 0; dy < 7; ++dy)
-        for (int dx = 0; dx < 7; ++dx) {
+    for (int p = 0; p < 4; ++p)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                const float v = patch[(c * ST_PH + ly * 2 + dy) * PP + lx * 2 + dx];
-                const float4* wr = reinterpret_cast<const float4*>(ws + ((dy * 7 + dx) * 3 + c) * 64);
+        for (int n = 0; n < 16; ++n) acc[p][n] = 0.f;
+    for (int dy = 0; dy < 7; ++dy) {
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
+        for (int c = 0; c < 3; ++c) {
+            float in[16];                          // input columns 2*lx0 .. 2*lx0+15 (13 are used)
+            const float4* ip = reinterpret_cast<const float4*>(patch + (c * ST_PH + ly * 2 + dy) * ST_PP + lx0 * 2);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 v = ip[q];
+                in[q * 4 + 0] = v.x; in[q * 4 + 1] = v.y; in[q * 4 + 2] = v.z; in[q * 4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int dx = 0; dx < 7; ++dx) {
+                const float4* wr = reinterpret_cast<const float4*>(ws + ((dy * 7 + dx) * 3 + c) * 64 + cg * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
                     const float4 wv = wr[q];
-                    acc[q * 4 + 0] = fmaf(v, wv.x, acc[q * 4 + 0]);
-                    acc[q * 4 + 1] = fmaf(v, wv.y, acc[q * 4 + 1]);
-                    acc[q * 4 + 2] = fmaf(v, wv.z, acc[q * 4 + 2]);
-                    acc[q * 4 + 3] = fmaf(v, wv.w, acc[q * 4 + 3]);
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float v = in[2 * p + dx];
+                        acc[p][q * 4 + 0] = fmaf(v, wv.x, acc[p][q * 4 + 0]);
+                        acc[p][q * 4 + 1] = fmaf(v, wv.y, acc[p][q * 4 + 1]);
+                        acc[p][q * 4 + 2] = fmaf(v, wv.z, acc[p][q * 4 + 2]);
+                        acc[p][q * 4 + 3] = fmaf(v, wv.w, acc[p][q * 4 + 3]);
+                    }
                 }
             }
         }
-    const int ho = ho0 + ly, wo = wo0 + lx;
-    if (ho >= Ho || wo >= Wo) return;
+    }
+    const int ho = ho0 + ly;
+    if (ho >= Ho) return;
     const int Wop = Wo + 2;
-    float* o = out + (((size_t)b * Ho + ho) * Wop + wo + 1) * 64;
-    float* ol = (wo == 0) ? out + (((size_t)b * Ho + ho) * Wop + Wo + 1) * 64 : nullptr;
-    float* orr = (wo == Wo - 1) ? out + (((size_t)b * Ho + ho) * Wop) * 64 : nullptr;
+    float4 sc[4], sf[4];
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
-        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + q);
-        const float4 sf = __ldg(reinterpret_cast<const float4*>(shift) + q);
-        float4 v;
-        v.x = fmaxf(fmaf(acc[q * 4 + 0], sc.x, sf.x), 0.f);
-        v.y = fmaxf(fmaf(acc[q * 4 + 1], sc.y, sf.y), 0.f);
-        v.z = fmaxf(fmaf(acc[q * 4 + 2], sc.z, sf.z), 0.f);
-        v.w = fmaxf(fmaf(acc[q * 4 + 3], sc.w, sf.w), 0.f);
-        reinterpret_cast<float4*>(o)[q] = v;
-        if (ol) reinterpret_cast<float4*>(ol)[q] = v;
-        if (orr) reinterpret_cast<float4*>(orr)[q] = v;
+    for (int q = 0; q < 4; ++q) {
+        sc[q] = __ldg(reinterpret_cast<const float4*>(scale + cg * 16) + q);
+        sf[q] = __ldg(reinterpret_cast<const float4*>(shift + cg * 16) + q);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int wo = wo0 + lx0 + p;
+        if (wo >= Wo) continue;
+        const size_t row = ((size_t)b * Ho + ho) * Wop;
+        float* o = out + (row + wo + 1) * 64 + cg * 16;
+        float* oh = (wo == 0) ? out + (row + Wo + 1) * 64 + cg * 16 : ((wo == Wo - 1) ? out + row * 64 + cg * 16 : nullptr);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float4 v;
+            v.x = fmaxf(fmaf(acc[p][q * 4 + 0], sc[q].x, sf[q].x), 0.f);
+            v.y = fmaxf(fmaf(acc[p][q * 4 + 1], sc[q].y, sf[q].y), 0.f);
+            v.z = fmaxf(fmaf(acc[p][q * 4 + 2], sc[q].z, sf[q].z), 0.f);
+            v.w = fmaxf(fmaf(acc[p][q * 4 + 3], sc[q].w, sf[q].w), 0.f);
+            reinterpret_cast<float4*>(o)[q] = v;
+            if (oh) reinterpret_cast<float4*>(oh)[q] = v;
+        }
     }
 }
 
@@ -368,7 +395,7 @@ int stem_f32(const float* x_nchw, int B, int in_channels, const float* w_packed,
              const float* shift, const Act& out, cudaStream_t st) {
     HN_CHECK(in_channels >= 3, "stem: input needs >= 3 channels (reference model.py:252 uses x[:, :3])");
     HN_CHECK(out.B == B && out.H == 256 && out.W == 512 && out.C == 64 && out.halo == 1, "stem: bad output tensor");
-    const size_t smem = (147 * 64 + 3 * ST_PH * (ST_PW + 1)) * sizeof(float);
+    const size_t smem = (147 * 64 + 3 * ST_PH * ST_PP) * sizeof(float);
     HN_CUDA_OK(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 g(512 / ST_TW, 256 / ST_TH, B);
     stem_kernel<<<g, 256, smem, st>>>(x_nchw, in_channels, w_packed, scale, shift, out.p, 512, 1024);

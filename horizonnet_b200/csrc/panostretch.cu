@@ -6,8 +6,9 @@
 //   out  = scipy.ndimage.map_coordinates(img[...,c], [refy, refx], order, mode='wrap')   (:99-102)
 //
 // refx and g = sin(u0)/sin u * ky depend on the column only, so a prologue kernel builds two fp64
-// tables of W entries per (kx, ky) pair and the main kernel spends one fp64 atan per TWO pixels
-// (rows y and H-1-y have tan v of opposite sign, so v0 is odd: refy(H-1-y) = H-1-refy(y)).
+// tables of W entries per (kx, ky) pair and the main kernel spends one fp64 atan per FOUR pixels
+// (rows y and H-1-y have tan v of opposite sign, so v0 is odd: refy(H-1-y) = H-1-refy(y); columns x
+// and W-1-x have u of opposite sign, so g is even).
 // Coordinates and the bilinear accumulation are fp64 like scipy (result cast to fp32); scipy's
 // legacy 'wrap' folds coordinates with period n-1.  HBM-bound: 2*H*W*C*4 bytes per panorama.
 #include "hn_common.cuh"
@@ -77,7 +78,9 @@ __device__ __forceinline__ void sample_store(const float* __restrict__ img, floa
     }
 }
 
-// grid: (ceil(W/128), ceil(H/2), n); thread = column x, row pair (y, H-1-y)
+// grid: (ceil(ceil(W/2)/128), ceil(H/2), n); thread = column pair (x, W-1-x) x row pair (y, H-1-y).
+// u(W-1-x) = -u(x) and v(H-1-y) = -v(y), so g is even in the column and v0 is odd in the row: one fp64
+// atan serves four pixels (the kernel is bound by the fp64 pipe, not by HBM: ~90 DP ops per pixel otherwise).
 template <int C>
 __global__ void __launch_bounds__(128) stretch_kernel(const float* __restrict__ img, float* __restrict__ out,
                                                       const double* __restrict__ refx,
@@ -86,22 +89,29 @@ __global__ void __launch_bounds__(128) stretch_kernel(const float* __restrict__ 
     const int x = blockIdx.x * 128 + threadIdx.x;
     const int y = blockIdx.y;
     const int n = blockIdx.z;
-    if (x >= W) return;
+    const int xm = W - 1 - x;
+    if (x > xm) return;
     const size_t plane = (size_t)H * W * C;
     const float* src = img + (size_t)n * plane;
     float* dst = out + (size_t)n * plane;
-    const double rx = refx[(size_t)n * W + x];
     const double v0 = atan(tanv[y] * gcol[(size_t)n * W + x]);                   // panostretch.py:93
     const double ry = (v0 / PI_D + 0.5) * (double)H - 0.5;                        // :96
-    float px[C];
-    sample_store<C>(src, px, ry, rx, H, W, order);
-#pragma unroll
-    for (int c = 0; c < C; ++c) dst[((size_t)y * W + x) * C + c] = px[c];
+    const double rym = (double)(H - 1) - ry;
     const int ym = H - 1 - y;
-    if (ym != y) {
-        sample_store<C>(src, px, (double)(H - 1) - ry, rx, H, W, order);
+    float px[C];
 #pragma unroll
-        for (int c = 0; c < C; ++c) dst[((size_t)ym * W + x) * C + c] = px[c];
+    for (int side = 0; side < 2; ++side) {
+        const int xx = side ? xm : x;
+        if (side && xm == x) break;
+        const double rx = refx[(size_t)n * W + xx];
+        sample_store<C>(src, px, ry, rx, H, W, order);
+#pragma unroll
+        for (int c = 0; c < C; ++c) dst[((size_t)y * W + xx) * C + c] = px[c];
+        if (ym != y) {
+            sample_store<C>(src, px, rym, rx, H, W, order);
+#pragma unroll
+            for (int c = 0; c < C; ++c) dst[((size_t)ym * W + xx) * C + c] = px[c];
+        }
     }
 }
 
@@ -121,7 +131,7 @@ int pano_stretch_device(const float* img, float* out, int n, int H, int W, int C
     const int tot = (n * W > H) ? n * W : H;
     stretch_tables_kernel<<<(tot + 255) / 256, 256, 0, st>>>(kx_dev, ky_dev, refx, gcol, tanv, n, H, W);
     HN_LAUNCH_OK();
-    dim3 g((W + 127) / 128, (H + 1) / 2, n);
+    dim3 g(((W + 1) / 2 + 127) / 128, (H + 1) / 2, n);
     HN_CHECK(n <= 65535, "pano_stretch: at most 65535 images per call");
     switch (C) {
         case 1: stretch_kernel<1><<<g, 128, 0, st>>>(img, out, refx, gcol, tanv, H, W, order); break;
