@@ -681,7 +681,7 @@ int hn_pano_stretch(const float* img, float* out, int n, int h, int w, int c, co
     for (int i = 0; i < n; ++i) HN_CHECK(kx[i] > 0 && ky[i] > 0, "hn_pano_stretch: kx, ky must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     double* scratch = nullptr;
-    const size_t nd = (size_t)2 * n + (size_t)2 * n * w + h;
+    const size_t nd = (size_t)2 * n + (size_t)4 * n * w + h;
     HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&scratch), nd * sizeof(double), st));
     HN_CUDA_OK(cudaMemcpyAsync(scratch, kx, n * sizeof(double), cudaMemcpyHostToDevice, st));
     HN_CUDA_OK(cudaMemcpyAsync(scratch + n, ky, n * sizeof(double), cudaMemcpyHostToDevice, st));
