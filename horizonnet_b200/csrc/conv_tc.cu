@@ -69,6 +69,56 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, ui
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// ---- 2-CTA (cta_group::2) helpers: the pair's leader (cluster rank 0) owns the operand barriers
+__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads whose completion is signalled on an mbarrier given as a shared::cluster address (possibly the peer CTA's)
+__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_5d(void* dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3,
+                                             int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+        : "memory");
+}
+// commit of the pair's MMAs: arrives on the barrier at the same offset in BOTH CTAs
+__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                     smem_u32(bar)),
+                 "h"((unsigned short)3)
+                 : "memory");
+}
+
 // K-major, 128-byte swizzle shared-memory operand descriptor (rows of 128 B, 8-row atoms 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -80,13 +130,13 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
-// kind::f16 instruction descriptor: D=f32, A/B formats (0 = fp16, 1 = bf16), both K-major, M=128, N=n
-__host__ __device__ constexpr uint32_t umma_idesc(int n, uint32_t a_fmt, uint32_t b_fmt) {
+// kind::f16 instruction descriptor: D=f32, A/B formats (0 = fp16, 1 = bf16), both K-major, M=m (128, or 256 for a CTA pair), N=n
+__host__ __device__ constexpr uint32_t umma_idesc(int n, uint32_t a_fmt, uint32_t b_fmt, int m = BM) {
     return (1u << 4)                    // c_format  = F32
            | (a_fmt << 7)               // a_format
            | (b_fmt << 10)              // b_format
            | ((uint32_t)(n >> 3) << 17) // n_dim
-           | ((uint32_t)(BM >> 4) << 24);  // m_dim
+           | ((uint32_t)(m >> 4) << 24);   // m_dim
 }
 
 __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
@@ -141,26 +191,34 @@ struct TcArgs {
     int dbg;                  // HN_TC_DBG experiment bits: 1 skip residual reads, 2 skip output stores, 4 skip epilogue math
 };
 
-template <int BN>
+// PAIR: two CTAs of a cluster work on a 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128 A rows
+// and HALF of the B rows, so a stage is 48 KB instead of 64 KB (4 stages instead of 3) and the B operand is
+// fetched once per pair -- the large-K convs are bound by operand feed, not by the tensor pipe.
+template <int BN, bool PAIR = false>
 struct Smem {
+    static constexpr int NST = PAIR ? 4 : STAGES;
     static constexpr int A_PLANE = BM * BKC * 2;          // 16 KB
-    static constexpr int B_PLANE = BN * BKC * 2;
+    static constexpr int B_PLANE = (PAIR ? BN / 2 : BN) * BKC * 2;
     static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
-    static constexpr int EPI_OFF = STAGES * STAGE;                    // 8 warp-private epilogue staging buffers
+    static constexpr int EPI_OFF = NST * STAGE;                       // 8 warp-private epilogue staging buffers
     static constexpr int BAR_OFF = EPI_OFF + 8 * 32 * STAGE_PITCH;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;    // barriers + alignment slack
     static constexpr int TMEM_COLS = 4 * BN;        // 2 hi*hi segment accumulators + 2 cross accumulators (128..512)
 };
 
-template <int BN>
+template <int BN, bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-    using S = Smem<BN>;
+    using S = Smem<BN, PAIR>;
+    constexpr int NST = S::NST;
+    const uint32_t rank = PAIR ? cluster_rank() : 0u;                 // 0 = leader of the pair
+    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+    const int tstride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;       // [2] hi*hi segment accumulator ready
+    uint64_t* empty_bar = full_bar + NST;
+    uint64_t* tfull_bar = empty_bar + NST;       // [2] hi*hi segment accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;           // [2] hi*hi segment accumulator drained
     uint64_t* cempty_bar = tempty_bar + 2;          // [2] cross-product accumulator drained
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cempty_bar + 2);
@@ -172,18 +230,30 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
     }
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < STAGES; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 8); mbar_init(cempty_bar + i, 8); }
+        for (int i = 0; i < NST; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        // accumulator hand-back: 8 epilogue warps per CTA arrive (for a pair: on the leader's barriers, 16 arrivals)
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull_bar + i, 1);
+            mbar_init(tempty_bar + i, PAIR ? 16 : 8);
+            mbar_init(cempty_bar + i, PAIR ? 16 : 8);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)S::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)S::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)S::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();      // barriers initialised in both CTAs before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -192,48 +262,81 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
-                const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+            for (int tile = tile0; tile < a.num_tiles; tile += tstride) {
+                const int mtp = tile / a.n_tiles, nt = tile - mtp * a.n_tiles;
+                const int mt = PAIR ? mtp * 2 + (int)rank : mtp;
                 int valid_rows = 1, row0 = 0, wo0 = 0;
                 if (a.mode == 1) {
                     const int rg = mt / a.wsegs;
                     wo0 = (mt - rg * a.wsegs) * a.tw;
                     row0 = rg * a.rows_per_tile;
-                    valid_rows = min(a.rows_per_tile, a.M - row0);
+                    // a pair always loads full tiles (rows past the end are out-of-bounds boxes: zero fill, full byte count)
+                    valid_rows = PAIR ? a.rows_per_tile : min(a.rows_per_tile, a.M - row0);
                 }
                 const uint32_t a_bytes = (a.mode == 0) ? 2u * S::A_PLANE : (uint32_t)(2 * valid_rows * a.tw * BKC * 2);
                 for (int kc = 0; kc < a.num_kc; ++kc) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
                     uint8_t* sA = smem + stage * S::STAGE;
                     uint8_t* sB = sA + 2 * S::A_PLANE;
-                    mbar_expect_tx(full_bar + stage, a_bytes + 2u * S::B_PLANE);
                     const int tap = kc / a.kc_per_tap;
                     const int c0 = (kc - tap * a.kc_per_tap) * BKC;
-                    if (a.mode == 0) {
-                        tma_load_3d(sA, &tmA, full_bar + stage, c0, mt * BM, 0);
-                        tma_load_3d(sA + S::A_PLANE, &tmA, full_bar + stage, c0, mt * BM, 1);
-                    } else {
-                        const int dy = tap / a.kw, dx = tap - dy * a.kw;
-                        for (int rr = 0; rr < valid_rows; ++rr) {
-                            const int R = row0 + rr;
-                            const int b = R / a.Ho, ho = R - b * a.Ho;
-                            const int hin = ho * a.sh + dy - a.ph;
-                            uint8_t* dst = sA + rr * a.tw * (BKC * 2);
-                            if (a.parity) {
-                                const int p = dx + a.woff;
-                                tma_load_5d(dst, &tmA, full_bar + stage, c0, p & 1, wo0 + (p >> 1), hin, b);
-                                tma_load_5d(dst + S::A_PLANE, &tmA, full_bar + stage, c0, p & 1, wo0 + (p >> 1), hin,
-                                            a.Bimg + b);
-                            } else {
-                                tma_load_4d(dst, &tmA, full_bar + stage, c0, wo0 + dx + a.woff, hin, b);
-                                tma_load_4d(dst + S::A_PLANE, &tmA, full_bar + stage, c0, wo0 + dx + a.woff, hin,
-                                            a.Bimg + b);
+                    if (!PAIR) {
+                        mbar_expect_tx(full_bar + stage, a_bytes + 2u * S::B_PLANE);
+                        if (a.mode == 0) {
+                            tma_load_3d(sA, &tmA, full_bar + stage, c0, mt * BM, 0);
+                            tma_load_3d(sA + S::A_PLANE, &tmA, full_bar + stage, c0, mt * BM, 1);
+                        } else {
+                            const int dy = tap / a.kw, dx = tap - dy * a.kw;
+                            for (int rr = 0; rr < valid_rows; ++rr) {
+                                const int R = row0 + rr;
+                                const int b = R / a.Ho, ho = R - b * a.Ho;
+                                const int hin = ho * a.sh + dy - a.ph;
+                                uint8_t* dst = sA + rr * a.tw * (BKC * 2);
+                                if (a.parity) {
+                                    const int p = dx + a.woff;
+                                    tma_load_5d(dst, &tmA, full_bar + stage, c0, p & 1, wo0 + (p >> 1), hin, b);
+                                    tma_load_5d(dst + S::A_PLANE, &tmA, full_bar + stage, c0, p & 1, wo0 + (p >> 1), hin,
+                                                a.Bimg + b);
+                                } else {
+                                    tma_load_4d(dst, &tmA, full_bar + stage, c0, wo0 + dx + a.woff, hin, b);
+                                    tma_load_4d(dst + S::A_PLANE, &tmA, full_bar + stage, c0, wo0 + dx + a.woff, hin,
+                                                a.Bimg + b);
+                                }
                             }
                         }
+                        tma_load_3d(sB, &tmB, full_bar + stage, kc * BKC, nt * BN, 0);
+                        tma_load_3d(sB + S::B_PLANE, &tmB, full_bar + stage, kc * BKC, nt * BN, 1);
+                    } else {
+                        // all bytes of both CTAs are counted on the LEADER's barrier (it issues the MMAs for the pair)
+                        const uint32_t fb = map_to_cta(smem_u32(full_bar + stage), 0);
+                        if (rank == 0) mbar_expect_tx(full_bar + stage, 2u * (2u * S::A_PLANE + 2u * S::B_PLANE));
+                        if (a.mode == 0) {
+                            tma2_load_3d(sA, &tmA, fb, c0, mt * BM, 0);
+                            tma2_load_3d(sA + S::A_PLANE, &tmA, fb, c0, mt * BM, 1);
+                        } else {
+                            const int dy = tap / a.kw, dx = tap - dy * a.kw;
+                            for (int rr = 0; rr < valid_rows; ++rr) {
+                                const int R = row0 + rr;
+                                const int b = R / a.Ho, ho = R - b * a.Ho;
+                                const int hin = ho * a.sh + dy - a.ph;
+                                uint8_t* dst = sA + rr * a.tw * (BKC * 2);
+                                // rows past the end: b >= Bimg; keep the lo-plane coordinate out of bounds as well
+                                const int bl = (b < a.Bimg) ? a.Bimg + b : 2 * a.Bimg + b;
+                                if (a.parity) {
+                                    const int p = dx + a.woff;
+                                    tma2_load_5d(dst, &tmA, fb, c0, p & 1, wo0 + (p >> 1), hin, b < a.Bimg ? b : 2 * a.Bimg + b);
+                                    tma2_load_5d(dst + S::A_PLANE, &tmA, fb, c0, p & 1, wo0 + (p >> 1), hin, bl);
+                                } else {
+                                    tma2_load_4d(dst, &tmA, fb, c0, wo0 + dx + a.woff, hin, b < a.Bimg ? b : 2 * a.Bimg + b);
+                                    tma2_load_4d(dst + S::A_PLANE, &tmA, fb, c0, wo0 + dx + a.woff, hin, bl);
+                                }
+                            }
+                        }
+                        const int nrow = nt * BN + (int)rank * (BN / 2);       // this CTA stages its half of the B rows
+                        tma2_load_3d(sB, &tmB, fb, kc * BKC, nrow, 0);
+                        tma2_load_3d(sB + S::B_PLANE, &tmB, fb, kc * BKC, nrow, 1);
                     }
-                    tma_load_3d(sB, &tmB, full_bar + stage, kc * BKC, nt * BN, 0);
-                    tma_load_3d(sB + S::B_PLANE, &tmB, full_bar + stage, kc * BKC, nt * BN, 1);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -244,12 +347,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // end.  So (1) the small cross products (hi*lo, lo*hi; 2^-11 of the result) get their own
         // accumulator, and (2) the hi*hi accumulator is restarted every `seg` K-chunks: the epilogue
         // warps drain each segment and add it to a register-resident fp32 sum with round-to-nearest.
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc(BN, 0, 0);       // fp16 x fp16 -> fp32
+        if (lane == 0 && rank == 0) {                              // for a pair only the leader issues MMAs
+            constexpr uint32_t idesc = umma_idesc(BN, 0, 0, PAIR ? 2 * BM : BM);       // fp16 x fp16 -> fp32
             int stage = 0;
             uint32_t phase = 0;
             int it = 0, g = 0;
-            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+            for (int tile = tile0; tile < a.num_tiles; tile += tstride, ++it) {
                 const int cbuf = it & 1;
                 mbar_wait(cempty_bar + cbuf, ((it >> 1) & 1) ^ 1);   // epilogue drained this cross accumulator
                 tc_fence_after();
@@ -272,17 +375,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < BKC / 16; ++k) {
                         const uint64_t ko = (uint64_t)((k * 16 * 2) >> 4);     // advance 32 B inside the swizzle row
-                        umma_f16(d_main, a_hi + ko, b_hi + ko, idesc, (seg_pos | k) != 0);
-                        umma_f16(d_cross, a_hi + ko, b_lo + ko, idesc, (kc | k) != 0);
-                        umma_f16(d_cross, a_lo + ko, b_hi + ko, idesc, 1);
+                        if (PAIR) {
+                            umma2_f16(d_main, a_hi + ko, b_hi + ko, idesc, (seg_pos | k) != 0);
+                            umma2_f16(d_cross, a_hi + ko, b_lo + ko, idesc, (kc | k) != 0);
+                            umma2_f16(d_cross, a_lo + ko, b_hi + ko, idesc, 1);
+                        } else {
+                            umma_f16(d_main, a_hi + ko, b_hi + ko, idesc, (seg_pos | k) != 0);
+                            umma_f16(d_cross, a_hi + ko, b_lo + ko, idesc, (kc | k) != 0);
+                            umma_f16(d_cross, a_lo + ko, b_hi + ko, idesc, 1);
+                        }
                     }
-                    umma_commit(empty_bar + stage);                  // frees the smem stage when the MMAs retire
+                    // frees the smem stage (in both CTAs of a pair) when the MMAs retire
+                    if (PAIR) umma2_commit(empty_bar + stage); else umma_commit(empty_bar + stage);
                     if (++seg_pos == a.seg || kc == a.num_kc - 1) {
-                        umma_commit(tfull_bar + mbuf);               // segment (and, at the end, the tile) complete
+                        // segment (and, at the end, the tile) complete
+                        if (PAIR) umma2_commit(tfull_bar + mbuf); else umma_commit(tfull_bar + mbuf);
                         seg_pos = 0;
                         ++g;
                     }
-                    if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -298,9 +409,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         uint8_t* stage = smem + S::EPI_OFF + (warp - EPI_WARP0) * 32 * STAGE_PITCH;
         const int nseg = (a.num_kc + a.seg - 1) / a.seg;
+        // accumulators are handed back on the leader's barriers (remote arrive for the peer CTA)
+        const uint32_t tempty_l[2] = {map_to_cta(smem_u32(tempty_bar), 0), map_to_cta(smem_u32(tempty_bar + 1), 0)};
+        const uint32_t cempty_l[2] = {map_to_cta(smem_u32(cempty_bar), 0), map_to_cta(smem_u32(cempty_bar + 1), 0)};
         int it = 0, g = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
-            const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+        for (int tile = tile0; tile < a.num_tiles; tile += tstride, ++it) {
+            const int mtp = tile / a.n_tiles, nt = tile - mtp * a.n_tiles;
+            const int mt = PAIR ? mtp * 2 + (int)rank : mtp;
             const int cbuf = it & 1;
             const int r = q * 32 + lane;                 // accumulator row = pixel of the tile
             // ---- where does this row live in the output?
@@ -342,7 +457,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar + mbuf);
+                if (lane == 0) { if (PAIR) mbar_arrive_cluster(tempty_l[mbuf]); else mbar_arrive(tempty_bar + mbuf); }
             }
             // ---- the last segment's commit also covers the cross products of the whole tile.
             // Global traffic of the epilogue is routed through a warp-private staging buffer so that
@@ -452,15 +567,19 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // cross accumulator drained: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(cempty_bar + cbuf);
+            if (lane == 0) { if (PAIR) mbar_arrive_cluster(cempty_l[cbuf]); else mbar_arrive(cempty_bar + cbuf); }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();      // nobody leaves while the peer may still signal / read
     if (warp == 2) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
-                     : "memory");
+        if (PAIR)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
+                         : "memory");
     }
 }
 
@@ -762,13 +881,35 @@ int tc_segment_chunks() {
 
 template <int BN>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
-    using S = Smem<BN>;
-    HN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    using S = Smem<BN, false>;
+    HN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     int dev = 0, sms = 0;
     HN_CUDA_OK(cudaGetDevice(&dev));
     HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    conv_tc_kernel<BN><<<grid, NTHREADS, S::TOTAL, st>>>(tmA, tmB, a);
+    conv_tc_kernel<BN, false><<<grid, NTHREADS, S::TOTAL, st>>>(tmA, tmB, a);
+    HN_LAUNCH_OK();
+    return 0;
+}
+
+// CTA-pair launch: a.num_tiles counts PAIR tiles (256 rows x 128 channels); clusters of 2 CTAs
+int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
+    using S = Smem<128, true>;
+    HN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    int dev = 0, sms = 0;
+    HN_CUDA_OK(cudaGetDevice(&dev));
+    HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int pairs = a.num_tiles < sms / 2 ? a.num_tiles : sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    HN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true>, tmA, tmB, a));
     HN_LAUNCH_OK();
     return 0;
 }
@@ -895,6 +1036,20 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
     HN_CHECK(m_tiles * a.n_tiles < (1ll << 31), "conv_tc: too many tiles");
     a.num_tiles = (int)(m_tiles * a.n_tiles);
     if (a.num_tiles == 0) return 0;
+    // CTA pairs (cta_group::2, M = 256 per pair).  Correct (unit tests run it with HN_TC_PAIR=1) but measured 5-25 %
+    // SLOWER than single-CTA tiles on every layer of this net: the large-K convs are bound by shared-memory
+    // bandwidth (three products re-read the same 128x64 tiles: 96 KB of MMA operand reads + 64 KB of TMA fill
+    // per 768-cycle chunk = 213 B/clk against 128 B/clk => ~60 % tensor pipe, which is what ncu shows), and in a
+    // pair each SM still serves its B half to both tensor cores, so only the L2 fill is halved.  Off by default.
+    static const bool pair_on = [] { const char* e = getenv("HN_TC_PAIR"); return e && atoi(e) == 1; }();
+    if (pair_on && BN == 128 && a.num_kc >= 8 && m_tiles >= 2) {
+        cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)d.Cout, 2};
+        cuuint64_t str[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * d.Cout * 2};
+        cuuint32_t box[3] = {BKC, 64, 1};                          // each CTA of the pair stages 64 of the 128 B rows
+        if (make_map(&tmB, wq, 3, dims, str, box)) return -1;
+        a.num_tiles = (int)(((m_tiles + 1) / 2) * a.n_tiles);
+        return launch_pair(tmA, tmB, a, st);
+    }
     switch (BN) {
         case 128: return launch<128>(tmA, tmB, a, st);
         case 64: return launch<64>(tmA, tmB, a, st);

@@ -45,6 +45,9 @@ CONV_CASES = [
     (2, 64, 16, 32, 32, 3, (2, 1), False, True),       # GHC conv, stride (2,1)
     (3, 512, 2, 32, 256, 3, (2, 1), False, True),      # H 2 -> 1
     (1, 1024, 4, 32, 4096, 1, (1, 1), False, False),   # LSTM projection shape family
+    (2, 512, 8, 32, 256, 3, (1, 1), False, True),      # large-K 3x3: CTA-pair (cta_group::2) kernel, conv mode
+    (1, 512, 9, 62, 256, 1, (1, 1), True, True),       # K=512 1x1 with residual: CTA-pair kernel, GEMM mode, odd tile count
+    (3, 256, 16, 64, 128, 3, (2, 1), False, True),     # stride (2,1), two rows per tile, pair kernel
 ]
 
 
