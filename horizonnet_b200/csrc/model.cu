@@ -28,7 +28,8 @@ int ghc_to_sequence(const Act ghc[4], float* seq, cudaStream_t st, bool split);
 int linear_head(const float* rnn, const float* w, const float* bias, float* bon, float* cor, int T, int B,
                 cudaStream_t st);
 int lstm_layer(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, float* out, int T, int B,
-               unsigned int* counters, int* error_flag, cudaStream_t st);
+               void* scratch, int* error_flag, cudaStream_t st);
+size_t lstm_scratch_bytes();
 int pano_stretch_device(const float* img, float* out, int n, int H, int W, int C, const double* kx_dev,
                         const double* ky_dev, double* scratch, int order, cudaStream_t st);
 
@@ -358,7 +359,7 @@ int hn_model_create(int device, int max_batch, hn_model** out) {
     };
     for (auto& b : bufs)
         if (m->alloc_t(b.p, b.n)) return -1;
-    if (m->alloc_t(&m->counters, 16)) return -1;
+    if (m->alloc(reinterpret_cast<void**>(&m->counters), lstm_scratch_bytes())) return -1;
     if (m->alloc_t(&m->error_flag, 1)) return -1;
     HN_CUDA_OK(cudaMemset(m->error_flag, 0, sizeof(int)));
     m->x_slot[0] = m->x_in;
@@ -732,9 +733,9 @@ int hn_lstm_layer(const float* xproj, const float* whf, const float* whb, float*
     HN_CHECK(xproj && whf && whb && out && T >= 1 && B >= 1, "hn_lstm_layer: bad argument");
     cudaStream_t st = (cudaStream_t)stream;
     unsigned int* ctr = nullptr;
-    HN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ctr), 16 * sizeof(unsigned int)));
-    int* flag = reinterpret_cast<int*>(ctr + 12);   // counters live in [0, 12), the error flag behind them
-    cudaMemsetAsync(ctr, 0, 16 * sizeof(unsigned int), st);
+    HN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&ctr), lstm_scratch_bytes()));
+    int* flag = reinterpret_cast<int*>(ctr + 64);   // counters live in [0, 8), the error flag behind them (first KB of scratch)
+    cudaMemsetAsync(ctr, 0, 1024, st);
     int rc = lstm_layer(xproj, whf, whb, out, T, B, ctr, flag, st);
     int h = 0;
     if (!rc) {
