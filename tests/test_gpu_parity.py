@@ -78,6 +78,15 @@ def test_conv_kernel_vs_torch(case, impl):
     assert torch.equal(raw[:, :, 0], raw[:, :, -2]) and torch.equal(raw[:, :, -1], raw[:, :, 1])
 
 
+def test_cta_pair_kernel_variant_in_subprocess():
+    """The cta_group::2 variant is off by default (measured slower); keep it correct: run it with HN_TC_PAIR=1."""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'tools', 'check_pair.py')], capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0 and 'PAIR OK' in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
+
+
 # ------------------------------------------------------------------------------- LSTM kernel
 @pytest.mark.parametrize('T,B', [(5, 1), (24, 7), (16, 32), (12, 40)])
 def test_lstm_layer_vs_oracle(T, B):
