@@ -30,6 +30,9 @@ int linear_head(const float* rnn, const float* w, const float* bias, float* bon,
 int lstm_layer(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, float* out, int T, int B,
                void* scratch, int* error_flag, cudaStream_t st);
 size_t lstm_scratch_bytes();
+int tta_views(const float* x, float* views, int V, const int* modes_dev, const int* shifts_dev, cudaStream_t st);
+int tta_merge(const float* bon, const float* cor, int V, const int* modes_dev, const int* shifts_dev, float* y_bon,
+              float* y_cor, cudaStream_t st);
 int pano_stretch_device(const float* img, float* out, int n, int H, int W, int C, const double* kx_dev,
                         const double* ky_dev, double* scratch, int order, cudaStream_t st);
 
@@ -156,6 +159,7 @@ struct hn_model {
     cudaEvent_t slot_ready[2] = {nullptr, nullptr};
     int slot_batch[2] = {0, 0};
     int submit_count = 0, collect_count = 0;
+    int* tta_ints = nullptr;                        // [2][64] view modes / shifts for hn_model_infer_tta
     int last_batch = 0;
 
     // optional per-op-class timing (bench.py roofline): CUDA event pairs around every launch
@@ -361,6 +365,7 @@ int hn_model_create(int device, int max_batch, hn_model** out) {
         if (m->alloc_t(b.p, b.n)) return -1;
     if (m->alloc(reinterpret_cast<void**>(&m->counters), lstm_scratch_bytes())) return -1;
     if (m->alloc_t(&m->error_flag, 1)) return -1;
+    if (m->alloc_t(&m->tta_ints, 128)) return -1;
     HN_CUDA_OK(cudaMemset(m->error_flag, 0, sizeof(int)));
     m->x_slot[0] = m->x_in;
     HN_CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
@@ -621,6 +626,27 @@ int hn_model_collect_host(hn_model* m, float* bon, float* cor) {
     HN_CUDA_OK(cudaStreamSynchronize(st));
     ++m->collect_count;
     return 0;
+}
+
+int hn_model_infer_tta(hn_model* m, const float* x, int in_channels, int flip, const int* shifts, int n_rotate,
+                       float* y_bon_pix, float* y_cor, void* stream) {
+    HN_CHECK(m && x && y_bon_pix && y_cor, "hn_model_infer_tta: NULL argument");
+    HN_CHECK(in_channels == 3, "hn_model_infer_tta: expects a 3-channel panorama (inference.py:196-200)");
+    HN_CHECK(n_rotate >= 0 && n_rotate <= 32 && (n_rotate == 0 || shifts), "hn_model_infer_tta: bad rotate list");
+    const int V = 1 + (flip ? 1 : 0) + n_rotate;
+    HN_CHECK(V <= m->max_batch && V <= 64, "hn_model_infer_tta: views exceed max_batch");
+    HN_CUDA_OK(cudaSetDevice(m->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int host[128];
+    int v = 0;
+    host[v] = 0; host[64 + v] = 0; ++v;                         // aug_type '' (inference.py:34)
+    if (flip) { host[v] = 1; host[64 + v] = 0; ++v; }           // 'flip' (:36-38)
+    for (int i = 0; i < n_rotate; ++i, ++v) { host[v] = 2; host[64 + v] = shifts[i]; }   // 'rotate shift' (:39-42)
+    HN_CUDA_OK(cudaMemcpyAsync(m->tta_ints, host, sizeof(host), cudaMemcpyHostToDevice, st));
+    HN_CUDA_OK(cudaStreamSynchronize(st));                      // host[] is a stack array
+    if (tta_views(x, m->x_slot[1], V, m->tta_ints, m->tta_ints + 64, st)) return -1;
+    if (hn_model_forward(m, m->x_slot[1], V, 3, m->bon_out, m->cor_out, st)) return -1;
+    return tta_merge(m->bon_out, m->cor_out, V, m->tta_ints, m->tta_ints + 64, y_bon_pix, y_cor, st);
 }
 
 int hn_model_stage(hn_model* m, const char* stage, float* out, long long capacity, int dims[4], void* stream) {

@@ -72,6 +72,15 @@ int hn_model_forward_host(hn_model* m, const float* x_nchw_host, int batch, int 
 int hn_model_submit_host(hn_model* m, const float* x_nchw_host, int batch, int in_channels);
 int hn_model_collect_host(hn_model* m, float* bon_host, float* cor_host);
 
+/* Test-time-augmented inference on the device ("next" row f2; reference inference.py:32-62 augment /
+ * augment_undo and inference.py:77-93).  x: ONE panorama [3][512][1024] fp32 on the device; views =
+ * identity (+ horizontal flip if `flip`) + one np.roll per entry of shifts_host (pixels, as computed by
+ * inference.py:40 `int(round(shift_p * W))`).  Outputs on the device: y_bon_pix [2][1024] = boundary rows in
+ * pixels, mean over un-augmented views, clipped like inference.py:90-92; y_cor [1024] = mean of the
+ * un-augmented sigmoid(cor).  Needs max_batch >= number of views. */
+int hn_model_infer_tta(hn_model* m, const float* x_dev, int in_channels, int flip, const int* shifts_host,
+                       int n_rotate, float* y_bon_pix_dev, float* y_cor_dev, void* stream);
+
 /* Test hook: copies an intermediate result of the LAST forward, converted to the reference's
  * layout, into `out_dev` (fp32).  Stages: "layer1".."layer4" (NCHW [B,C,H,W], model.py:78-81),
  * "feature" ([B,1024,256], model.py:175-178), "rnn_out" ([256,B,1024], model.py:264).

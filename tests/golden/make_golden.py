@@ -95,7 +95,47 @@ def golden_panostretch():
     print('panostretch fixtures written')
 
 
+def golden_tta():
+    """TTA internals of reference inference.py:77-93, computed with the reference's own augment /
+    augment_undo, plus the public inference(..., force_raw=True) result (its cor_id exposes y_bon_[0])."""
+    import types
+    for name in ('shapely', 'shapely.geometry'):                    # shim 2: not installed, never called with force_raw
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules['shapely.geometry'].Polygon = object
+    sys.modules['shapely.geometry'].LineString = object
+    try:
+        import scipy.ndimage.filters                                 # noqa: F401  (removed in recent scipy)
+    except Exception:
+        import scipy.ndimage
+        m = types.ModuleType('scipy.ndimage.filters')
+        m.maximum_filter = scipy.ndimage.maximum_filter
+        sys.modules['scipy.ndimage.filters'] = m
+    import inference as ref_inf                                      # reference inference.py
+    torch.manual_seed(0)
+    net = ref_model.HorizonNet('resnet50', True).eval()
+    net.load_state_dict(synthetic_state_dict(2, 'random'), strict=True)
+    x = synthetic_panoramas(1, seed=102)
+    flip, rotate = True, [0.25, 0.333]
+    with torch.no_grad():
+        xa, aug_type = ref_inf.augment(x, flip, rotate)
+        y_bon_, y_cor_ = net(xa)
+        y_bon_ = ref_inf.augment_undo(y_bon_.cpu(), aug_type).mean(0)
+        y_cor_ = ref_inf.augment_undo(torch.sigmoid(y_cor_).cpu(), aug_type).mean(0)
+        H = 512
+        y_bon_ = (y_bon_[0] / np.pi + 0.5) * H - 0.5
+        y_bon_[0] = np.clip(y_bon_[0], 1, H / 2 - 1)
+        y_bon_[1] = np.clip(y_bon_[1], H / 2 + 1, H - 2)
+        y_cor_ = y_cor_[0, 0]
+        cor_id, z0, z1, _ = ref_inf.inference(net, x, 'cpu', flip=flip, rotate=rotate, force_raw=True)
+    assert np.abs(cor_id[0::2, 1] * H - y_bon_[0]).max() < 1e-3      # the public function agrees with the restated lines
+    np.savez_compressed(os.path.join(HERE, 'tta_randombn.npz'), y_bon=y_bon_.astype(np.float32),
+                        y_cor=y_cor_.astype(np.float32), cor_id=cor_id, z1=np.float64(z1), seed=2, x_seed=102,
+                        flip=flip, rotate=np.array(rotate))
+    print('tta golden', y_bon_.min(), y_bon_.max(), float(y_cor_.max()))
+
+
 if __name__ == '__main__':
+    golden_tta()
     golden_panostretch()
     golden_forward('identity', seed=0, bn='identity', batch=2)
     golden_forward('randombn', seed=1, bn='random', batch=1)

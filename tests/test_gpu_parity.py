@@ -222,6 +222,32 @@ def test_forward_rejects_wrong_size_and_reloads_weights():
     assert not torch.equal(b0, b1)
 
 
+# ------------------------------------------------------------------------------- device-side TTA (next row f2)
+def test_tta_forward_matches_reference_golden_and_oracle(golden_dir):
+    from horizonnet_b200.inference import tta_forward
+    from oracle import tta_ref
+    g = np.load(os.path.join(golden_dir, 'tta_randombn.npz'))
+    sd = synthetic_state_dict(int(g['seed']), 'random')
+    net = _net(sd, True)
+    x = synthetic_panoramas(1, seed=int(g['x_seed']))
+    y_bon, y_cor = tta_forward(net, x, flip=bool(g['flip']), rotate=list(g['rotate']))
+    assert y_bon.shape == (2, 1024) and y_cor.shape == (1024,)
+    # boundary rows in pixels: 1e-4 rad * 512/pi = 1.6e-2 px is the forward tolerance; cor: sigmoid of 1e-4
+    assert np.abs(y_bon - g['y_bon']).max() < 1.6e-2
+    assert np.abs(y_cor - g['y_cor']).max() < 1e-4
+    # no-augmentation path == plain forward + decode, and oracle agreement on another setting
+    y_bon0, y_cor0 = tta_forward(net, x)
+    with torch.no_grad():
+        bon, cor = net(x.to(DEV))
+    ref_rows = (bon[0].cpu().numpy() / np.float32(np.pi) + 0.5) * 512 - 0.5
+    ref_rows[0] = np.clip(ref_rows[0], 1, 255); ref_rows[1] = np.clip(ref_rows[1], 257, 510)
+    assert np.abs(y_bon0 - ref_rows).max() < 1e-3
+    assert np.abs(y_cor0 - torch.sigmoid(cor[0, 0]).cpu().numpy()).max() < 1e-6
+    ob, oc = tta_ref.tta_forward(sd, x, flip=False, rotate=[0.5])
+    tb, tc = tta_forward(net, x, flip=False, rotate=[0.5])
+    assert np.abs(tb - ob).max() < 1.6e-2 and np.abs(tc - oc).max() < 1e-4
+
+
 # ------------------------------------------------------------------------------- pano_stretch
 def test_pano_stretch_small_grid_vs_golden(golden_dir):
     g = np.load(os.path.join(golden_dir, 'panostretch_small.npz'))

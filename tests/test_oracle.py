@@ -92,3 +92,15 @@ def test_legacy_wrap_rule():
     a = np.array([[10., 20., 30., 40., 50.]])
     v = panostretch_ref.map_coordinates_wrap(a, np.array([[0.0]]), np.array([[-0.3]]))
     assert abs(float(v[0, 0]) - 47.0) < 1e-12
+
+
+def test_tta_oracle_matches_reference(golden_dir):
+    """oracle/tta_ref.py vs the reference's own augment / augment_undo / inference() (tests/golden/tta_randombn.npz)."""
+    from oracle import tta_ref
+    g = np.load(os.path.join(golden_dir, 'tta_randombn.npz'))
+    sd = synthetic_state_dict(int(g['seed']), 'random')
+    x = synthetic_panoramas(1, seed=int(g['x_seed']))
+    y_bon, y_cor = tta_ref.tta_forward(sd, x, flip=bool(g['flip']), rotate=list(g['rotate']))
+    assert np.abs(y_bon - g['y_bon']).max() < 5e-3          # pixel rows: 1e-5 rad * 512 / pi
+    assert np.abs(y_cor - g['y_cor']).max() < 2e-5
+    assert np.abs(g['cor_id'][0::2, 1] * 512 - y_bon[0]).max() < 5e-3
