@@ -285,6 +285,22 @@ def run_ours(args):
                                'bytes_per_pano': 12582912, 'sample': '64 distinct 512x1024x3 fp32 panos (805 MB in+out > L2), 49-pair kx/ky grid'}
     except Exception as e:
         aux['pano_stretch'] = {'error': str(e)}
+    # ---- auxiliary: single-panorama inference with device-side TTA (flip + 2 rotations = 4 views), "next" row f2
+    try:
+        from horizonnet_b200.inference import tta_forward
+        xi = synthetic_panoramas(1, seed=77)
+        for _ in range(2):
+            tta_forward(net, xi, flip=True, rotate=[0.25, 0.5])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        reps = 10
+        for _ in range(reps):
+            tta_forward(net, xi, flip=True, rotate=[0.25, 0.5])     # host tensor in, numpy out: includes H2D + D2H
+        dt = (time.perf_counter() - t0) / reps
+        aux['tta_single_image'] = {'images_per_s': round(1.0 / dt, 2), 'ms_per_image': round(dt * 1e3, 3), 'views': 4,
+                                   'api': 'horizonnet_b200.inference.tta_forward (hn_model_infer_tta), host in / host out'}
+    except Exception as e:
+        aux['tta_single_image'] = {'error': str(e)}
     lstm_ms = prof['lstm_recurrence'][0] / args.steps
     aux['lstm_recurrence'] = {'ms_per_step': round(lstm_ms, 4),
                               'achieved_gbs': round(151.4e6 / (lstm_ms * 1e-3) / 1e9, 2) if lstm_ms > 0 else None,

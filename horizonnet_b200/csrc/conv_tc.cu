@@ -940,7 +940,12 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
     TcArgs a;
     memset(&a, 0, sizeof(a));
     const bool gemm = (d.kh == 1 && d.kw == 1 && d.sh == 1 && d.sw == 1 && in.halo == out.halo);
-    const int BN = d.Cout >= 128 ? 128 : d.Cout;
+    int BN = d.Cout >= 128 ? 128 : d.Cout;
+    {   // layers with too few 128x128 tiles to fill the SMs (the tail of the height-reduction convs): halve the tile width
+        const long long rows = gemm ? (long long)in.B * in.H * in.Wp() : (long long)out.B * out.H * out.W;
+        const long long tiles128 = ((rows + BM - 1) / BM) * (d.Cout / 128 > 0 ? d.Cout / 128 : 1);
+        if (BN == 128 && tiles128 < 110) BN = 64;
+    }
     const size_t in_plane = in.numel(), out_plane = out.numel();
     CUtensorMap tmA, tmB;
     {   // weights: {K, Cout, 2}
