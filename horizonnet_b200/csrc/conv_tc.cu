@@ -188,6 +188,7 @@ struct TcArgs {
     size_t out_plane;         // elements per plane
     int relu;
     int seg;                  // K chunks per hi*hi accumulation segment
+    int rowbox;               // 1: the rows_per_tile output rows of a tile come from consecutive input rows of one image -> one TMA box
     int dbg;                  // HN_TC_DBG experiment bits: 1 skip residual reads, 2 skip output stores, 4 skip epilogue math
 };
 
@@ -287,7 +288,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             tma_load_3d(sA + S::A_PLANE, &tmA, full_bar + stage, c0, mt * BM, 1);
                         } else {
                             const int dy = tap / a.kw, dx = tap - dy * a.kw;
-                            for (int rr = 0; rr < valid_rows; ++rr) {
+                            // rowbox: the tile's output rows map to consecutive input rows of one image: one box per plane
+                            // (small per-row boxes cost tensor-pipe time: 31 % on the W=32 layers vs 55-60 % on W>=128)
+                            const int nbox = a.rowbox ? 1 : valid_rows;
+                            for (int rr = 0; rr < nbox; ++rr) {
                                 const int R = row0 + rr;
                                 const int b = R / a.Ho, ho = R - b * a.Ho;
                                 const int hin = ho * a.sh + dy - a.ph;
@@ -1024,16 +1028,20 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
         a.wsegs = out.W / a.tw;
         a.sh = d.sh; a.ph = d.ph; a.woff = in.halo - d.pw;
         a.parity = (d.sw == 2);
+        // one box for all rows of a tile when they are consecutive input rows of one image (stride 1 along H)
+        static const bool rowbox_on = [] { const char* e = getenv("HN_TC_ROWBOX"); return !(e && atoi(e) == 0); }();
+        a.rowbox = (rowbox_on && a.rows_per_tile > 1 && d.sh == 1 && out.H % a.rows_per_tile == 0) ? 1 : 0;
+        const cuuint32_t boxrows = a.rowbox ? (cuuint32_t)a.rows_per_tile : 1u;
         const cuuint64_t C2 = (cuuint64_t)d.Cin * 2, Wp = in.Wp();
         if (!a.parity) {
             cuuint64_t dims[4] = {(cuuint64_t)d.Cin, Wp, (cuuint64_t)in.H, (cuuint64_t)2 * in.B};
             cuuint64_t str[3] = {C2, C2 * Wp, C2 * Wp * in.H};
-            cuuint32_t box[4] = {BKC, (cuuint32_t)a.tw, 1, 1};
+            cuuint32_t box[4] = {BKC, (cuuint32_t)a.tw, boxrows, 1};
             if (make_map(&tmA, in_planes, 4, dims, str, box)) return -1;
         } else {
             cuuint64_t dims[5] = {(cuuint64_t)d.Cin, 2, Wp / 2, (cuuint64_t)in.H, (cuuint64_t)2 * in.B};
             cuuint64_t str[4] = {C2, 2 * C2, C2 * Wp, C2 * Wp * in.H};
-            cuuint32_t box[5] = {BKC, 1, (cuuint32_t)a.tw, 1, 1};
+            cuuint32_t box[5] = {BKC, 1, (cuuint32_t)a.tw, boxrows, 1};
             if (make_map(&tmA, in_planes, 5, dims, str, box)) return -1;
         }
         m_tiles = (long long)((a.M + a.rows_per_tile - 1) / a.rows_per_tile) * a.wsegs;
@@ -1053,6 +1061,7 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
         cuuint32_t box[3] = {BKC, 64, 1};                          // each CTA of the pair stages 64 of the 128 B rows
         if (make_map(&tmB, wq, 3, dims, str, box)) return -1;
         a.num_tiles = (int)(((m_tiles + 1) / 2) * a.n_tiles);
+        HN_CHECK(!a.rowbox, "conv_tc: the CTA-pair experiment needs HN_TC_ROWBOX=0");
         return launch_pair(tmA, tmB, a, st);
     }
     switch (BN) {

@@ -1,6 +1,7 @@
 """GPU: exercise the CTA-pair (cta_group::2) variant of conv_tc_kernel (HN_TC_PAIR=1) against torch fp64."""
 import os, sys
 os.environ['HN_TC_PAIR'] = '1'
+os.environ['HN_TC_ROWBOX'] = '0'
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, 'tests'))
 import torch
