@@ -862,10 +862,11 @@ EncodeTiledFn encode_fn() {
 }
 
 int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-             const cuuint32_t* box) {
+             const cuuint32_t* box, int stride_dim = -1, int stride = 1) {
     EncodeTiledFn fn = encode_fn();
     HN_CHECK(fn != nullptr, "conv_tc: cuTensorMapEncodeTiled unavailable");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (stride_dim >= 0) estr[stride_dim] = (cuuint32_t)stride;      // traversal stride: every stride-th element of the box span
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1030,19 +1031,23 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
         a.parity = (d.sw == 2);
         // one box for all rows of a tile when they are consecutive input rows of one image (stride 1 along H)
         static const bool rowbox_on = [] { const char* e = getenv("HN_TC_ROWBOX"); return !(e && atoi(e) == 0); }();
-        a.rowbox = (rowbox_on && a.rows_per_tile > 1 && d.sh == 1 && out.H % a.rows_per_tile == 0) ? 1 : 0;
-        const cuuint32_t boxrows = a.rowbox ? (cuuint32_t)a.rows_per_tile : 1u;
+        static const bool rowbox2_on = [] { const char* e = getenv("HN_TC_ROWBOX2"); return !(e && atoi(e) == 0); }();
+        a.rowbox = (rowbox_on && a.rows_per_tile > 1 && (d.sh == 1 || (d.sh == 2 && rowbox2_on)) &&
+                    out.H % a.rows_per_tile == 0) ? 1 : 0;
+        // stride 2 along H (height-reduction convs): the box spans 2*R input rows and takes every second one
+        const cuuint32_t boxrows = a.rowbox ? (cuuint32_t)(a.rows_per_tile * d.sh) : 1u;
+        const int hs = (a.rowbox && d.sh == 2) ? 2 : 1;
         const cuuint64_t C2 = (cuuint64_t)d.Cin * 2, Wp = in.Wp();
         if (!a.parity) {
             cuuint64_t dims[4] = {(cuuint64_t)d.Cin, Wp, (cuuint64_t)in.H, (cuuint64_t)2 * in.B};
             cuuint64_t str[3] = {C2, C2 * Wp, C2 * Wp * in.H};
             cuuint32_t box[4] = {BKC, (cuuint32_t)a.tw, boxrows, 1};
-            if (make_map(&tmA, in_planes, 4, dims, str, box)) return -1;
+            if (make_map(&tmA, in_planes, 4, dims, str, box, hs == 2 ? 2 : -1, hs)) return -1;
         } else {
             cuuint64_t dims[5] = {(cuuint64_t)d.Cin, 2, Wp / 2, (cuuint64_t)in.H, (cuuint64_t)2 * in.B};
             cuuint64_t str[4] = {C2, 2 * C2, C2 * Wp, C2 * Wp * in.H};
             cuuint32_t box[5] = {BKC, 1, (cuuint32_t)a.tw, boxrows, 1};
-            if (make_map(&tmA, in_planes, 5, dims, str, box)) return -1;
+            if (make_map(&tmA, in_planes, 5, dims, str, box, hs == 2 ? 3 : -1, hs)) return -1;
         }
         m_tiles = (long long)((a.M + a.rows_per_tile - 1) / a.rows_per_tile) * a.wsegs;
     }
