@@ -197,7 +197,7 @@ struct TcArgs {
 // fetched once per pair -- the large-K convs are bound by operand feed, not by the tensor pipe.
 template <int BN, bool PAIR = false>
 struct Smem {
-    static constexpr int NST = PAIR ? 4 : STAGES;
+    static constexpr int NST = (PAIR || BN <= 64) ? 4 : STAGES;   // 48 KB stages (BN <= 64) leave room for a 4th
     static constexpr int A_PLANE = BM * BKC * 2;          // 16 KB
     static constexpr int B_PLANE = (PAIR ? BN / 2 : BN) * BKC * 2;
     static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
