@@ -843,6 +843,267 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+
+// ================================================================================================
+// stem_tc_kernel: the 7x7 stride-2 stem (3 -> 64 channels, model.py:73-75) as an implicit GEMM on tcgen05.
+//
+// Cin = 3 does not give a K-major operand by itself, so a pre-pass (stem_pack_kernel) writes the normalised
+// input as split planes of PIXEL PAIRS:  P[plane][b][h][j][8] fp16,  element e of pair j = channel e&3 (channel 3
+// is zero) of input column 2j + (e>>2) - 3 (circular in W), h = input row + 3 (rows outside the image are zero:
+// the zero H padding of the normalised input).  With K ordered (dy, pair p, e) -- i.e. an 8-wide dx window whose
+// 8th tap has zero weight -- the A row of output pixel xo for (dy, p) is pair xo + p of row 2*yo + dy: for a tile
+// of 128 consecutive output pixels all four p are the SAME shared-memory bytes shifted by p*16 B.  That is exactly
+// the no-swizzle K-major UMMA layout (core matrix = 8 rows x 16 B contiguous, SBO = 128 B) with a leading-dimension
+// offset of one row (LBO = 16 B): a tile needs ONE TMA box per plane (7 rows x 136 pairs, 15 KB) and the MMAs read
+// overlapping operands straight out of it.  K = 7 x 32 = 224 (147 useful), 14 K-steps x 3 products per tile.
+// The weights ([2][64][224] fp16 planes, 128-byte swizzle) stay resident in shared memory for the whole kernel.
+// Epilogue: TMEM -> BN scale/shift -> ReLU -> fp32 [128 px][64 ch] tile in shared memory (2 x 16 KB, swizzled)
+// -> two TMA stores into the halo-NHWC fp32 stem output (the max-pool does not read the halo columns).
+constexpr int SP_ROWS = 517;                 // input rows -3 .. 513
+constexpr int SP_PAIRS = 520;                // pixel pairs per row (516 used, padded to a multiple of 8)
+constexpr int SP_K = 224;                    // 7 dy x 4 pairs x 8
+constexpr float STEM_IN_SCALE = 16.f;        // planes hold 16 * normalised input: keeps the lo plane a normal fp16
+
+struct StSmem {
+    static constexpr int B_CHUNK = 64 * BKC * 2;              // 8 KB: 64 couts x 64 k
+    static constexpr int B_BYTES = 2 * 4 * B_CHUNK;           // hi/lo x 4 chunks = 64 KB
+    static constexpr int A_ROW = 136 * 16;                    // one dy: 136 pairs x 16 B
+    static constexpr int A_PLANE = 7 * A_ROW;                 // 15232 B
+    static constexpr int A_STAGE = 30 * 1024;                 // hi + lo (30464 B) rounded up
+    static constexpr int NSTAGE = 3;
+    static constexpr int A_OFF = B_BYTES;
+    static constexpr int E_HALF = 128 * 128;                  // 128 px x 32 ch fp32
+    static constexpr int EBUF = 2 * E_HALF;
+    static constexpr int EPI_OFF = A_OFF + NSTAGE * A_STAGE;  // 154 KB
+    static constexpr int BAR_OFF = EPI_OFF + 2 * EBUF;        // 218 KB
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+    static constexpr int TMEM_COLS = 128;                     // two 64-column accumulators
+};
+
+struct StemArgs {
+    int B, num_tiles;
+    const float* scale;       // accumulator -> true units for an input scaled by 2^-4 (tc_aux[0..64))
+    const float* shift;       // folded BN shift
+};
+
+// K-major operand without swizzle: 8-row x 16-byte core matrices, `lbo` bytes between the two core matrices of a
+// K=16 step, `sbo` bytes between 8-row groups
+__device__ __forceinline__ uint64_t umma_desc_interleave(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+    d |= (uint64_t)(lbo >> 4) << 16;
+    d |= (uint64_t)(sbo >> 4) << 32;
+    d |= (uint64_t)1 << 46;                               // descriptor version 1 (sm_100); layout type 0 = no swizzle
+    return d;
+}
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tm)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(256) stem_pack_kernel(const float* __restrict__ x, int Cx,
+                                                        unsigned short* __restrict__ out, int B) {
+    const size_t total = (size_t)B * SP_ROWS * SP_PAIRS;
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int j = (int)(i % SP_PAIRS);
+    const size_t t = i / SP_PAIRS;
+    const int h = (int)(t % SP_ROWS);
+    const int b = (int)(t / SP_ROWS);
+    const int row = h - 3;
+    uint32_t hi[4] = {0u, 0u, 0u, 0u}, lo[4] = {0u, 0u, 0u, 0u};
+    if (row >= 0 && row < 512 && j < 516) {
+        const float mean[3] = {0.485f, 0.456f, 0.406f};       // reference model.py:186
+        const float stdv[3] = {0.229f, 0.224f, 0.225f};       // reference model.py:187
+        unsigned short hs[8], ls[8];
+#pragma unroll
+        for (int e2 = 0; e2 < 2; ++e2) {
+            int px = 2 * j + e2 - 3;
+            px = px < 0 ? px + 1024 : (px >= 1024 ? px - 1024 : px);        // circular W (model.py:27-29)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float v = 0.f;
+                if (c < 3) v = (__ldg(x + (((size_t)b * Cx + c) * 512 + row) * 1024 + px) - mean[c]) / stdv[c] * STEM_IN_SCALE;
+                const __half hh = __float2half_rn(v);
+                hs[e2 * 4 + c] = __half_as_ushort(hh);
+                ls[e2 * 4 + c] = __half_as_ushort(__float2half_rn(v - __half2float(hh)));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { hi[q] = pack2(hs[2 * q], hs[2 * q + 1]); lo[q] = pack2(ls[2 * q], ls[2 * q + 1]); }
+    }
+    *reinterpret_cast<uint4*>(out + i * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(out + (total + i) * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// OIHW [64][3][7][7] -> OIHW [64][4][7][8] with zero 4th channel / 8th column (so that pack_weight_tc's K order
+// (dy, dx, c) becomes the kernel's (dy, pair, e) order)
+__global__ void stem_weight_pad_kernel(const float* __restrict__ w, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 64 * 4 * 7 * 8) return;
+    const int dx = i % 8, dy = (i / 8) % 7, c = (i / 56) % 4, n = i / 224;
+    out[i] = (c < 3 && dx < 7) ? w[((n * 3 + c) * 7 + dy) * 7 + dx] : 0.f;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+stem_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmO, const StemArgs a) {
+    using S = StSmem;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint64_t* empty_bar = full_bar + S::NSTAGE;
+    uint64_t* bfull_bar = empty_bar + S::NSTAGE;   // weights resident
+    uint64_t* tfull_bar = bfull_bar + 1;           // [2] accumulator ready
+    uint64_t* tempty_bar = tfull_bar + 2;          // [2] accumulator drained
+    uint64_t* oready_bar = tempty_bar + 2;         // [2] output tile staged by all 8 epilogue warps
+    uint64_t* efree_bar = oready_bar + 2;          // [2] the TMA store has read the staging buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(efree_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S::NSTAGE; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        mbar_init(bfull_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 8);
+            mbar_init(oready_bar + i, 8); mbar_init(efree_bar + i, 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    // tile -> (image b, output row yo, 128-pixel segment sg): 4 segments per row, 256 rows per image
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_expect_tx(bfull_bar, (uint32_t)S::B_BYTES);
+            for (int pl = 0; pl < 2; ++pl)
+                for (int c = 0; c < 4; ++c)
+                    tma_load_3d(smem + (pl * 4 + c) * S::B_CHUNK, &tmB, bfull_bar, c * BKC, 0, pl);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+                const int b = tile >> 10, yo = (tile >> 2) & 255, sg = tile & 3;
+                mbar_wait(empty_bar + stage, phase ^ 1);
+                uint8_t* sA = smem + S::A_OFF + stage * S::A_STAGE;
+                mbar_expect_tx(full_bar + stage, 2u * S::A_PLANE);
+                tma_load_4d(sA, &tmA, full_bar + stage, 0, sg * 16, 2 * yo, b);
+                tma_load_4d(sA + S::A_PLANE, &tmA, full_bar + stage, 0, sg * 16, 2 * yo, a.B + b);
+                if (++stage == S::NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(64, 0, 0);
+            mbar_wait(bfull_bar, 0);
+            tc_fence_after();
+            const uint32_t sB = smem_u32(smem);
+            int stage = 0, it = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                mbar_wait(tempty_bar + acc, ((it >> 1) & 1) ^ 1);
+                mbar_wait(full_bar + stage, phase);
+                tc_fence_after();
+                const uint32_t d = tmem_base + (uint32_t)(acc * 64);
+                const uint32_t sA = smem_u32(smem + S::A_OFF + stage * S::A_STAGE);
+#pragma unroll
+                for (int prod = 0; prod < 3; ++prod) {            // hi*hi, hi*lo, lo*hi
+                    const uint32_t pa = sA + (prod == 2 ? S::A_PLANE : 0);
+                    const uint32_t pb = sB + (prod == 1 ? 4 * S::B_CHUNK : 0);
+#pragma unroll
+                    for (int dy = 0; dy < 7; ++dy)
+#pragma unroll
+                        for (int h2 = 0; h2 < 2; ++h2) {
+                            const uint64_t ad = umma_desc_interleave(pa + dy * S::A_ROW + h2 * 32, 16, 128);
+                            const uint64_t bd = umma_desc_sw128(pb + (dy >> 1) * S::B_CHUNK) +
+                                                (uint64_t)((((dy & 1) * 32 + h2 * 16) * 2) >> 4);
+                            umma_f16(d, ad, bd, idesc, (prod | dy | h2) != 0);
+                        }
+                }
+                umma_commit(empty_bar + stage);
+                umma_commit(tfull_bar + acc);
+                if (++stage == S::NSTAGE) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= EPI_WARP0) {
+        const int q = warp & 3;
+        const int half = (warp - EPI_WARP0) >> 2;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int r = q * 32 + lane;
+        float sc[32], sf[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            sc[j] = __ldg(a.scale + half * 32 + j) * (ACT_SCALE / STEM_IN_SCALE);   // tc_aux assumes 2^-4-scaled inputs
+            sf[j] = __ldg(a.shift + half * 32 + j);
+        }
+        int it = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1, eb = it & 1;
+            mbar_wait(tfull_bar + acc, (it >> 1) & 1);
+            tc_fence_after();
+            uint32_t v[32];
+            tmem_ld32(tmem_base + lane_base + (uint32_t)(acc * 64 + half * 32), v);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar + acc);
+            float y[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y[j] = fmaxf(fmaf(__uint_as_float(v[j]), sc[j], sf[j]), 0.f);
+            mbar_wait(efree_bar + eb, ((it >> 1) & 1) ^ 1);
+            const uint32_t e = smem_u32(smem + S::EPI_OFF + eb * S::EBUF + half * S::E_HALF) + r * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                st_shared_v4(e + (uint32_t)((c ^ (r & 7)) << 4),
+                             make_uint4(__float_as_uint(y[4 * c]), __float_as_uint(y[4 * c + 1]),
+                                        __float_as_uint(y[4 * c + 2]), __float_as_uint(y[4 * c + 3])));
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(oready_bar + eb);
+        }
+    } else if (warp == 3) {
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+                const int b = tile >> 10, yo = (tile >> 2) & 255, sg = tile & 3;
+                const int eb = it & 1;
+                mbar_wait(oready_bar + eb, (it >> 1) & 1);
+                const uint8_t* ebuf = smem + S::EPI_OFF + eb * S::EBUF;
+                const int pix = (b * 256 + yo) * 514 + sg * 128 + 1;
+                tma_store_2d(&tmO, ebuf, 0, pix);
+                tma_store_2d(&tmO, ebuf + S::E_HALF, 32, pix);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(efree_bar + eb);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
+    }
+}
+
 // -------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -862,13 +1123,15 @@ EncodeTiledFn encode_fn() {
 }
 
 int make_map(CUtensorMap* tm, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-             const cuuint32_t* box, int stride_dim = -1, int stride = 1) {
+             const cuuint32_t* box, int stride_dim = -1, int stride = 1,
+             CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+             CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = encode_fn();
     HN_CHECK(fn != nullptr, "conv_tc: cuTensorMapEncodeTiled unavailable");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     if (stride_dim >= 0) estr[stride_dim] = (cuuint32_t)stride;      // traversal stride: every stride-th element of the box span
-    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
-                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = fn(tm, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes,
+                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail("conv_tc: cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
     return 0;
@@ -1074,6 +1337,59 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
         case 64: return launch<64>(tmA, tmB, a, st);
         default: return launch<32>(tmA, tmB, a, st);
     }
+}
+
+
+// ---------------------------------------------------------------------- stem on tensor cores (host side)
+size_t stem_tc_scratch_bytes(int B) { return (size_t)2 * B * SP_ROWS * SP_PAIRS * 16; }
+
+int stem_tc_pack_weights(const float* w_oihw, float* pad_scratch, unsigned short* wq, const float* scale,
+                         const float* shift, float* tc_aux, cudaStream_t st) {
+    stem_weight_pad_kernel<<<(64 * SP_K + 255) / 256, 256, 0, st>>>(w_oihw, pad_scratch);
+    HN_LAUNCH_OK();
+    return pack_weight_tc(pad_scratch, wq, scale, shift, tc_aux, tc_aux + 3 * 64, 64, 4, 7, 8, st);
+}
+
+int stem_tc(const float* x_nchw, int B, int in_channels, const unsigned short* wq, const float* tc_aux,
+            const float* shift, unsigned short* scratch, const Act& out, cudaStream_t st) {
+    HN_CHECK(in_channels >= 3, "stem: input needs >= 3 channels (reference model.py:252 uses x[:, :3])");
+    HN_CHECK(out.B == B && out.H == 256 && out.W == 512 && out.C == 64 && out.halo == 1, "stem: bad output tensor");
+    HN_CHECK(B >= 1 && B <= 2048, "stem: bad batch");
+    const size_t total = (size_t)B * SP_ROWS * SP_PAIRS;
+    stem_pack_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(x_nchw, in_channels, scratch, B);
+    HN_LAUNCH_OK();
+    CUtensorMap tmA, tmB, tmO;
+    {   // packed input: {64 = 8 pairs x 8 elements, 65 pair groups, 517 rows, 2 planes x B}
+        cuuint64_t dims[4] = {64, SP_PAIRS / 8, SP_ROWS, (cuuint64_t)2 * B};
+        cuuint64_t str[3] = {128, (cuuint64_t)SP_PAIRS * 16, (cuuint64_t)SP_ROWS * SP_PAIRS * 16};
+        cuuint32_t box[4] = {64, 17, 7, 1};
+        if (make_map(&tmA, scratch, 4, dims, str, box, -1, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_NONE))
+            return -1;
+    }
+    {   // weights: {K = 224, 64, 2}; the last 64-wide chunk is half out of bounds (zero filled, never multiplied)
+        cuuint64_t dims[3] = {SP_K, 64, 2};
+        cuuint64_t str[2] = {SP_K * 2, SP_K * 64 * 2};
+        cuuint32_t box[3] = {BKC, 64, 1};
+        if (make_map(&tmB, wq, 3, dims, str, box)) return -1;
+    }
+    {   // fp32 halo-NHWC output as {64 channels, B*256*514 pixels}
+        cuuint64_t dims[2] = {64, (cuuint64_t)B * 256 * 514};
+        cuuint64_t str[1] = {256};
+        cuuint32_t box[2] = {32, 128};
+        if (make_map(&tmO, out.p, 2, dims, str, box, -1, 1, CU_TENSOR_MAP_DATA_TYPE_FLOAT32)) return -1;
+    }
+    StemArgs a;
+    a.B = B;
+    a.num_tiles = B * 1024;
+    a.scale = tc_aux;
+    a.shift = shift;
+    HN_CUDA_OK(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StSmem::TOTAL));
+    int dev = 0, sms = 0;
+    HN_CUDA_OK(cudaGetDevice(&dev));
+    HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    stem_tc_kernel<<<a.num_tiles < sms ? a.num_tiles : sms, NTHREADS, StSmem::TOTAL, st>>>(tmA, tmB, tmO, a);
+    HN_LAUNCH_OK();
+    return 0;
 }
 
 // ---------------------------------------------------------------------- format conversion kernels

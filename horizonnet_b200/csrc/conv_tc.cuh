@@ -54,6 +54,14 @@ int conv_tc(const ConvDesc& d, const Act& in, const Act& out, const float* resid
 int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_aux, const Act& in,
                    const unsigned short* in_planes, const Act& out, unsigned short* out_planes, float* out_f32,
                    const unsigned short* res_planes, cudaStream_t st);
+// 7x7 stride-2 stem on tcgen05 (conv_tc.cu: stem_tc_kernel): NCHW fp32 input -> fp32 halo-NHWC [B][256][514][64]
+// (interior columns only).  wq [2][64][224] / tc_aux [3*64+1] come from stem_tc_pack_weights (pad_scratch: 64*224 floats);
+// scratch: stem_tc_scratch_bytes(B) bytes of packed input planes.
+size_t stem_tc_scratch_bytes(int B);
+int stem_tc_pack_weights(const float* w_oihw, float* pad_scratch, unsigned short* wq, const float* scale,
+                         const float* shift, float* tc_aux, cudaStream_t st);
+int stem_tc(const float* x_nchw, int B, int in_channels, const unsigned short* wq, const float* tc_aux,
+            const float* shift, unsigned short* scratch, const Act& out, cudaStream_t st);
 int split_planes(const float* in, unsigned short* out, size_t n, cudaStream_t st);
 int merge_planes(const unsigned short* in, float* out, size_t n, cudaStream_t st);
 // OIHW fp32 weights -> wq planes + tc_aux[3*Cout] (scale/shift may be null = ones/zeros); scratch: 1 float.

@@ -136,6 +136,9 @@ struct hn_model {
 
     // graph
     ConvLayer stem;                                  // weights packed [147][64]
+    unsigned short* stem_wq = nullptr;               // tcgen05 stem: [2][64][224] fp16 planes (conv_tc.cu: stem_tc)
+    float* stem_aux = nullptr;                       // 3*64 + 1 epilogue constants
+    int stem_tc_on = 1;                              // option "stem_tc" / HN_TC_STEM=0: fp32 CUDA-core stem inside the TC path
     struct Block { ConvLayer c1, c2, c3, ds; bool has_ds = false; };
     std::vector<Block> blocks[4];
     ConvLayer ghc[4][4];
@@ -345,6 +348,7 @@ int hn_model_create(int device, int max_batch, hn_model** out) {
     std::unique_ptr<hn_model> m(new hn_model());
     m->device = device;
     m->max_batch = max_batch;
+    if (const char* e = getenv("HN_TC_STEM")) m->stem_tc_on = atoi(e);
     build_graph(m.get());
     for (auto& s : m->slots)
         if (!s.ignored && m->alloc_t(&s.dev, (size_t)s.numel)) return -1;
@@ -406,6 +410,7 @@ int hn_model_set_option(hn_model* m, const char* name, int value) {
     HN_CHECK(m && name, "hn_model_set_option: NULL argument");
     if (std::strcmp(name, "tensor_cores") == 0) { m->use_tc = value; return 0; }
     if (std::strcmp(name, "profile") == 0) { m->profile = value; return 0; }
+    if (std::strcmp(name, "stem_tc") == 0) { m->stem_tc_on = value; return 0; }
     return fail(std::string("hn_model_set_option: unknown option '") + name + "'");
 }
 
@@ -416,6 +421,8 @@ int hn_model_finalize(hn_model* m) {
     HN_CUDA_OK(cudaSetDevice(m->device));
     cudaStream_t st = 0;
     if (pack_conv(m, m->stem, st)) return -1;
+    if (!m->stem_wq && (m->alloc_t(&m->stem_wq, (size_t)2 * 64 * 224) || m->alloc_t(&m->stem_aux, 3 * 64 + 1))) return -1;
+    if (stem_tc_pack_weights(m->T(m->stem.wkey), m->XP, m->stem_wq, m->stem.scale, m->stem.shift, m->stem_aux, st)) return -1;
     for (int l = 0; l < 4; ++l)
         for (auto& b : m->blocks[l]) {
             if (pack_conv(m, b.c1, st) || pack_conv(m, b.c2, st) || pack_conv(m, b.c3, st)) return -1;
@@ -467,7 +474,11 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
     Act s0 = mk(m->S0, B, 256, 512, 64);
     {
         Scope sc(m, CLS_STEM, 2.0 * B * 256 * 512 * 64 * 147, st);
-        if (stem_f32(x, B, in_channels, m->stem.w, m->stem.scale, m->stem.shift, s0, st)) return -1;
+        if (m->use_tc && m->stem_tc_on) {
+            // packed input planes live in X[0] (free until layer1): B * 8.6 MB of its B * 33.8 MB
+            if (stem_tc(x, B, in_channels, m->stem_wq, m->stem_aux, m->stem.shift,
+                        reinterpret_cast<unsigned short*>(m->X[0]), s0, st)) return -1;
+        } else if (stem_f32(x, B, in_channels, m->stem.w, m->stem.scale, m->stem.shift, s0, st)) return -1;
     }
     Act cur = mk(m->S1, B, 128, 256, 64);
     {
@@ -673,6 +684,14 @@ int hn_model_stage(hn_model* m, const char* stage, float* out, long long capacit
             dims[0] = B; dims[1] = C; dims[2] = H; dims[3] = W;
             return 0;
         }
+    if (s == "stem") {           // conv1 + bn1 + relu (model.py:73-75), before the max-pool; S0 is fp32 on both paths
+        const size_t n = (size_t)B * 64 * 256 * 512;
+        HN_CHECK((long long)n <= capacity, "hn_model_stage: output buffer too small");
+        nhwc_to_nchw_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->S0, out, B, 256, 512, 64, 1);
+        HN_LAUNCH_OK();
+        dims[0] = B; dims[1] = 64; dims[2] = 256; dims[3] = 512;
+        return 0;
+    }
     const size_t total = (size_t)256 * B * 1024;
     HN_CHECK((long long)total <= capacity, "hn_model_stage: output buffer too small");
     if (s == "feature") {

@@ -249,6 +249,12 @@ class HorizonNet(nn.Module):
         _lib.check(_lib.lib().hn_model_collect_host(h['ptr'], bon.data_ptr(), cor.data_ptr()), 'hn_model_collect_host')
         return bon, cor
 
+    def set_option(self, name, value):
+        """Library tuning switch on every live handle (e.g. 'stem_tc': 0 = fp32 CUDA-core stem, 1 = tcgen05 stem)."""
+        for h in self._handles.values():
+            _lib.check(_lib.lib().hn_model_set_option(h['ptr'], name.encode(), int(value)), 'set_option')
+        return self
+
     def debug_stage(self, name, device=None):
         """Intermediate result of the last forward in the reference's layout (test hook)."""
         lib = _lib.lib()

@@ -178,6 +178,36 @@ def test_forward_matches_oracle_and_is_batch_invariant(tensor_cores):
     assert torch.equal(bon3[1:2], bon1) and torch.equal(cor3[1:2], cor1)
 
 
+def test_tensor_core_stem_vs_oracle_and_fp32_stem():
+    """stem_tc_kernel (7x7 s2 conv as an implicit GEMM over packed pixel pairs) against the oracle's stem in fp64
+    and against the exact fp32 CUDA-core stem_kernel it replaces on the tensor-core path."""
+    import torch.nn.functional as F
+    sd = synthetic_state_dict(5, 'random')
+    net = _net(sd, True)
+    x = synthetic_panoramas(2, seed=33, channels=4)
+    e = 'feature_extractor.encoder.'
+    sd64 = {k: v.double() for k, v in sd.items() if k.startswith(e + 'conv1') or k.startswith(e + 'bn1.')}
+    xn = (x[:, :3].double() - torch.tensor(horizonnet_ref.X_MEAN).double().view(1, 3, 1, 1)) / \
+        torch.tensor(horizonnet_ref.X_STD).double().view(1, 3, 1, 1)
+    ref = F.relu(horizonnet_ref._bn(horizonnet_ref._circ_conv(xn, sd64[e + 'conv1.1.weight'], None, 2, 3, 3), sd64, e + 'bn1'))
+    scale = ref.abs().max().item()
+    got = {}
+    for mode in (1, 0):
+        with torch.no_grad():
+            net(x.to(DEV))                      # creates the handle on first use
+            net.set_option('stem_tc', mode)
+            bon, cor = net(x.to(DEV))
+        net.check()
+        stem = net.debug_stage('stem').cpu()
+        assert tuple(stem.shape) == (2, 64, 256, 512)
+        err = (stem.double() - ref).abs().max().item()
+        # split-precision products carry 22 significant bits per operand (measured 5.2e-6 at scale 3.3); fp32 FMA: 1.9e-6
+        assert err <= (4e-6 if mode else 1e-6) * scale + 1e-6, (mode, err, scale)
+        got[mode] = (stem, bon.cpu(), cor.cpu())
+    assert (got[1][1] - got[0][1]).abs().max().item() < 2e-5
+    assert (got[1][2] - got[0][2]).abs().max().item() < 2e-5
+
+
 def test_forward_host_equals_device_forward():
     sd = synthetic_state_dict(2, 'identity')
     net = _net(sd, True)
