@@ -188,6 +188,8 @@ struct TcArgs {
     size_t out_plane;         // elements per plane
     int relu;
     int seg;                  // K chunks per hi*hi accumulation segment
+    int dxr;                  // 1: 3x3 single-row tiles load each (dy, channel chunk) input row ONCE (130 pixels) and the three
+                              //    dx taps read it through row-shifted UMMA descriptors (L2->SM traffic per tap: 64 -> 43 KB)
     int rowbox;               // 1: the rows_per_tile output rows of a tile come from consecutive input rows of one image -> one TMA box
     int dbg;                  // HN_TC_DBG experiment bits: 1 skip residual reads, 2 skip output stores, 4 skip epilogue math
 };
@@ -222,7 +224,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tfull_bar = empty_bar + NST;       // [2] hi*hi segment accumulator ready
     uint64_t* tempty_bar = tfull_bar + 2;           // [2] hi*hi segment accumulator drained
     uint64_t* cempty_bar = tempty_bar + 2;          // [2] cross-product accumulator drained
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(cempty_bar + 2);
+    uint64_t* afull_bar = cempty_bar + 2;           // [2] dxr mode: input-row slot filled
+    uint64_t* aempty_bar = afull_bar + 2;           // [2] dxr mode: the three taps have read the input-row slot
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aempty_bar + 2);
+    // dxr mode re-partitions the operand ring: two input-row slots (hi + lo plane, 136 rows of 128 B each, 130 used)
+    // followed by NST weight-tile slots
+    constexpr int AX_PLANE = 17 * 1024;
+    constexpr int AX_SLOT = 2 * AX_PLANE;
+    constexpr int BX_OFF = 2 * AX_SLOT;
+    static_assert(BX_OFF + NST * 2 * S::B_PLANE <= NST * S::STAGE, "dxr layout does not fit the operand ring");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -232,6 +242,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(afull_bar + i, 1); mbar_init(aempty_bar + i, 1); }
         // accumulator hand-back: 8 epilogue warps per CTA arrive (for a pair: on the leader's barriers, 16 arrivals)
         for (int i = 0; i < 2; ++i) {
             mbar_init(tfull_bar + i, 1);
@@ -260,7 +271,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
-        if (lane == 0) {
+        if (lane == 0 && !PAIR && a.dxr) {
+            // 3x3 conv, one output row of 128 pixels per tile: per (dy, channel chunk) ONE box of 130 input pixels,
+            // then the three weight tiles of that (dy, chunk)
+            int ast = 0, bst = 0;
+            uint32_t aph = 0, bph = 0;
+            const int ndyc = a.num_kc / a.kw;
+            for (int tile = tile0; tile < a.num_tiles; tile += tstride) {
+                const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+                const int rg = mt / a.wsegs;
+                const int wo0 = (mt - rg * a.wsegs) * a.tw;
+                const int b = rg / a.Ho, ho = rg - b * a.Ho;
+                for (int dyc = 0; dyc < ndyc; ++dyc) {
+                    const int dy = dyc / a.kc_per_tap, cc = dyc - dy * a.kc_per_tap;
+                    const int hin = ho * a.sh + dy - a.ph;
+                    mbar_wait(aempty_bar + ast, aph ^ 1);
+                    uint8_t* sAx = smem + ast * AX_SLOT;
+                    mbar_expect_tx(afull_bar + ast, 2u * 130u * 128u);
+                    tma_load_4d(sAx, &tmA, afull_bar + ast, cc * BKC, wo0 + a.woff, hin, b);
+                    tma_load_4d(sAx + AX_PLANE, &tmA, afull_bar + ast, cc * BKC, wo0 + a.woff, hin, a.Bimg + b);
+                    if (++ast == 2) { ast = 0; aph ^= 1; }
+                    for (int dx = 0; dx < 3; ++dx) {
+                        mbar_wait(empty_bar + bst, bph ^ 1);
+                        uint8_t* sB = smem + BX_OFF + bst * 2 * S::B_PLANE;
+                        mbar_expect_tx(full_bar + bst, 2u * S::B_PLANE);
+                        const int kb = ((dy * a.kw + dx) * a.kc_per_tap + cc) * BKC;
+                        tma_load_3d(sB, &tmB, full_bar + bst, kb, nt * BN, 0);
+                        tma_load_3d(sB + S::B_PLANE, &tmB, full_bar + bst, kb, nt * BN, 1);
+                        if (++bst == NST) { bst = 0; bph ^= 1; }
+                    }
+                }
+            }
+        } else if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile0; tile < a.num_tiles; tile += tstride) {
@@ -351,7 +393,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // end.  So (1) the small cross products (hi*lo, lo*hi; 2^-11 of the result) get their own
         // accumulator, and (2) the hi*hi accumulator is restarted every `seg` K-chunks: the epilogue
         // warps drain each segment and add it to a register-resident fp32 sum with round-to-nearest.
-        if (lane == 0 && rank == 0) {                              // for a pair only the leader issues MMAs
+        if (lane == 0 && !PAIR && a.dxr) {
+            constexpr uint32_t idesc = umma_idesc(BN, 0, 0, BM);
+            int ast = 0, bst = 0;
+            uint32_t aph = 0, bph = 0;
+            int it = 0, g = 0;
+            const int ndyc = a.num_kc / a.kw;
+            for (int tile = tile0; tile < a.num_tiles; tile += tstride, ++it) {
+                const int cbuf = it & 1;
+                mbar_wait(cempty_bar + cbuf, ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_cross = tmem_base + (2 + cbuf) * BN;
+                uint32_t d_main = tmem_base;
+                int seg_pos = 0, mbuf = 0, kc = 0;
+                for (int dyc = 0; dyc < ndyc; ++dyc) {
+                    mbar_wait(afull_bar + ast, aph);
+                    tc_fence_after();
+                    const uint32_t sAx = smem_u32(smem + ast * AX_SLOT);
+                    for (int dx = 0; dx < 3; ++dx, ++kc) {
+                        if (seg_pos == 0) {
+                            mbuf = g & 1;
+                            mbar_wait(tempty_bar + mbuf, ((g >> 1) & 1) ^ 1);
+                            tc_fence_after();
+                            d_main = tmem_base + mbuf * BN;
+                        }
+                        mbar_wait(full_bar + bst, bph);
+                        tc_fence_after();
+                        const uint32_t sB = smem_u32(smem + BX_OFF + bst * 2 * S::B_PLANE);
+                        // tap dx = the same 130-pixel row read from pixel dx on: start address + dx rows of 128 B.
+                        // Measured: the 128-byte swizzle is applied to the absolute shared-memory address bits, so the
+                        // shifted start needs NO descriptor base offset (setting it to (start >> 7) & 7 gives wrong results).
+                        const uint64_t a_hi = umma_desc_sw128(sAx + dx * 128);
+                        const uint64_t a_lo = umma_desc_sw128(sAx + AX_PLANE + dx * 128);
+                        const uint64_t b_hi = umma_desc_sw128(sB), b_lo = umma_desc_sw128(sB + S::B_PLANE);
+#pragma unroll
+                        for (int k = 0; k < BKC / 16; ++k) {
+                            const uint64_t ko = (uint64_t)((k * 16 * 2) >> 4);
+                            umma_f16(d_main, a_hi + ko, b_hi + ko, idesc, (seg_pos | k) != 0);
+                            umma_f16(d_cross, a_hi + ko, b_lo + ko, idesc, (kc | k) != 0);
+                            umma_f16(d_cross, a_lo + ko, b_hi + ko, idesc, 1);
+                        }
+                        umma_commit(empty_bar + bst);
+                        if (++seg_pos == a.seg || kc == a.num_kc - 1) {
+                            umma_commit(tfull_bar + mbuf);
+                            seg_pos = 0;
+                            ++g;
+                        }
+                        if (++bst == NST) { bst = 0; bph ^= 1; }
+                    }
+                    umma_commit(aempty_bar + ast);           // the input-row slot is free once the three taps retire
+                    if (++ast == 2) { ast = 0; aph ^= 1; }
+                }
+            }
+        } else if (lane == 0 && rank == 0) {                       // for a pair only the leader issues MMAs
             constexpr uint32_t idesc = umma_idesc(BN, 0, 0, PAIR ? 2 * BM : BM);       // fp16 x fp16 -> fp32
             int stage = 0;
             uint32_t phase = 0;
@@ -1301,10 +1395,19 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
         const cuuint32_t boxrows = a.rowbox ? (cuuint32_t)(a.rows_per_tile * d.sh) : 1u;
         const int hs = (a.rowbox && d.sh == 2) ? 2 : 1;
         const cuuint64_t C2 = (cuuint64_t)d.Cin * 2, Wp = in.Wp();
+        // dx reuse (HN_TC_DXR=0 disables)
+        static const int dxr_mode = [] {
+            const char* p = getenv("HN_TC_PAIR");
+            if (p && atoi(p) == 1) return 0;                       // the CTA-pair experiment keeps per-tap boxes
+            const char* e = getenv("HN_TC_DXR");
+            return e ? atoi(e) : 1;
+        }();
+        a.dxr = (dxr_mode != 0 && !a.parity && d.kw == 3 && a.rows_per_tile == 1 && a.tw == BM &&
+                 (long long)a.wsegs * BM + a.woff + 2 <= (long long)Wp) ? 1 : 0;
         if (!a.parity) {
             cuuint64_t dims[4] = {(cuuint64_t)d.Cin, Wp, (cuuint64_t)in.H, (cuuint64_t)2 * in.B};
             cuuint64_t str[3] = {C2, C2 * Wp, C2 * Wp * in.H};
-            cuuint32_t box[4] = {BKC, (cuuint32_t)a.tw, boxrows, 1};
+            cuuint32_t box[4] = {BKC, a.dxr ? 130u : (cuuint32_t)a.tw, boxrows, 1};
             if (make_map(&tmA, in_planes, 4, dims, str, box, hs == 2 ? 2 : -1, hs)) return -1;
         } else {
             cuuint64_t dims[5] = {(cuuint64_t)d.Cin, 2, Wp / 2, (cuuint64_t)in.H, (cuuint64_t)2 * in.B};

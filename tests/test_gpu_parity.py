@@ -48,6 +48,8 @@ CONV_CASES = [
     (2, 512, 8, 32, 256, 3, (1, 1), False, True),      # large-K 3x3: CTA-pair (cta_group::2) kernel, conv mode
     (1, 512, 9, 62, 256, 1, (1, 1), True, True),       # K=512 1x1 with residual: CTA-pair kernel, GEMM mode, odd tile count
     (3, 256, 16, 64, 128, 3, (2, 1), False, True),     # stride (2,1), two rows per tile, pair kernel
+    (1, 64, 5, 256, 64, 3, (1, 1), False, True),       # W >= 128: single-row tiles, dx taps share one 130-pixel input row
+    (2, 128, 6, 128, 256, 3, (2, 1), True, True),      # same with stride (2,1) and bias (GHC on layer1/2 features)
 ]
 
 
