@@ -29,13 +29,16 @@ def main(csv_path, prev_path, out_path):
             'dram_pct': round(d['gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed'][0], 1),
             'dram_mb': round((d['dram__bytes_read.sum'][0] + d['dram__bytes_write.sum'][0]) / 1e6, 1),
         })
+        if 'lts__t_bytes.sum' in d:        # all L2 slice traffic (SM fills, stores, DRAM side): the large-K convs sit at the LTS cap
+            out[-1]['l2_gb'] = round(d['lts__t_bytes.sum'][0] / 1e9, 3)
+            out[-1]['l2_tbps'] = round(d['lts__t_bytes.sum'][0] / 1e9 / ms, 2)
     tot = sum(o['ms'] for o in out)
     tw = sum(o['ms'] * o['tensor_pipe_pct'] for o in out) / tot
     json.dump(out, open(out_path, 'w'), indent=0)
     print(f'{len(out)} launches, sum {tot:.3f} ms (prev {sum(o["ms_prev"] for o in out):.3f}), time-weighted tensor pipe {tw:.1f} %,'
           f' DRAM {sum(o["dram_mb"] for o in out) / 1e3:.2f} GB')
     for o in sorted(out, key=lambda o: -o['ms'])[:12]:
-        print(f"  {o['conv']:10s} {o['kernel']:15s} {o['ms']:.4f} ms (prev {o['ms_prev']:.4f})  tensor {o['tensor_pipe_pct']:5.1f} %  dram {o['dram_pct']:5.1f} %")
+        print(f"  {o['conv']:10s} {o['kernel']:15s} {o['ms']:.4f} ms (prev {o['ms_prev']:.4f})  tensor {o['tensor_pipe_pct']:5.1f} %  dram {o['dram_pct']:5.1f} %  L2 {o.get('l2_tbps', 0):.1f} TB/s")
 
 if __name__ == '__main__':
     main(*sys.argv[1:4])
