@@ -152,6 +152,9 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
+        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) off it
+        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() in ('VERSION', 'INFO') and not os.environ.get('NCCL_DEBUG_FILE'):
+            os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr' if os.environ.get('NCCL_DEBUG') else os.devnull
         dist.init_process_group('nccl', device_id=dev)
     if rank == 0:
         entry.build()
