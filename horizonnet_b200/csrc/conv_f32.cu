@@ -5,7 +5,7 @@
 //   model.py:129 ConvCompressH convs, and the LSTM input projections treated as 1x1 convs).
 //   Epilogue fuses eval-mode BN / conv bias (scale, shift), the residual add and ReLU, and writes the
 //   circular halo columns of the output.  This is the exact-fp32 path: it is the on-device
-//   reference the split-bf16 tcgen05 kernels (conv_tc.cu) are validated against, and the fallback
+//   reference the split-fp16 tcgen05 kernels (conv_tc.cu) are validated against, and the fallback
 //   geometry for shapes the tensor-core kernel does not cover.
 // stem_f32: 7x7 stride-2 conv on the NCHW fp32 input with the input normalisation
 //   (model.py:248-252), BN and ReLU fused (model.py:73-75).

@@ -38,7 +38,7 @@ namespace hn {
 namespace {
 
 constexpr int BM = 128;            // pixels per tile = UMMA M
-constexpr int BKC = 64;            // bf16 channels per K chunk = one 128-byte swizzle row
+constexpr int BKC = 64;            // fp16 channels per K chunk = one 128-byte swizzle row
 constexpr int STAGES = 3;
 constexpr int NTHREADS = 384;
 constexpr int EPI_WARP0 = 4;

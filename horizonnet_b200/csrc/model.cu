@@ -317,7 +317,7 @@ int run_conv(hn_model* m, const ConvLayer& c, const Act& in, const Act& out, con
     const double flops = 2.0 * (double)out.B * out.H * out.W * c.d.Cout * c.d.kh * c.d.kw * c.d.Cin;
     Scope sc(m, cls, flops, st);
     if (!m->use_tc) return conv_f32(c.d, in, out, res, st);
-    // tensor-core path: every activation buffer holds bf16 hi/lo planes (same bytes as fp32)
+    // tensor-core path: every activation buffer holds fp16 hi/lo planes (same bytes as fp32)
     if (!c.wq || !conv_tc_supported(c.d, in, out))
         return fail("hn_model_forward: a convolution of the graph is not covered by the tcgen05 kernel");
     return conv_tc_planes(c.d, c.wq, c.tc_scale, in, reinterpret_cast<const unsigned short*>(in.p), out,
@@ -536,7 +536,7 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
         Act a = mk(const_cast<float*>(lin), 1, 1, 256 * B, 1024, 0);
         Act xp = mk(m->XP, 1, 1, 256 * B, 4096, 0);
         if (m->use_tc && layer == 1) {
-            // layer-2 projection operand: the fp32 recurrence output as bf16 planes
+            // layer-2 projection operand: the fp32 recurrence output as fp16 hi/lo planes
             Scope sc(m, CLS_TAIL, 0.0, st);
             if (split_planes(m->R1, reinterpret_cast<unsigned short*>(m->R1S), (size_t)256 * B * 1024, st)) return -1;
             a.p = m->R1S;
@@ -673,7 +673,7 @@ int hn_model_stage(hn_model* m, const char* stage, float* out, long long capacit
             const size_t total = (size_t)B * C * H * W;
             HN_CHECK((long long)total <= capacity, "hn_model_stage: output buffer too small");
             const float* src = m->F[l];
-            if (m->use_tc) {       // F[l] holds bf16 planes: merge into T1 scratch first (free after the forward)
+            if (m->use_tc) {       // F[l] holds fp16 hi/lo planes: merge into T1 scratch first (free after the forward)
                 const size_t n = (size_t)B * H * (W + 2) * C;
                 float* tmp = (l == 0) ? m->X[0] : m->T1;
                 if (merge_planes(reinterpret_cast<const unsigned short*>(m->F[l]), tmp, n, st)) return -1;
@@ -696,7 +696,7 @@ int hn_model_stage(hn_model* m, const char* stage, float* out, long long capacit
     HN_CHECK((long long)total <= capacity, "hn_model_stage: output buffer too small");
     if (s == "feature") {
         const float* seq = m->SEQ;
-        if (m->use_tc) {      // SEQ holds bf16 planes; XP is dead after the forward and large enough
+        if (m->use_tc) {      // SEQ holds fp16 hi/lo planes; XP is dead after the forward and large enough
             if (merge_planes(reinterpret_cast<const unsigned short*>(m->SEQ), m->XP, total, st)) return -1;
             seq = m->XP;
         }

@@ -155,7 +155,7 @@ class HorizonNet(nn.Module):
             yield key, t
 
     def use_tensor_cores(self, enabled=True):
-        """True (default): split-bf16 tcgen05 kernels where supported; False: exact fp32 kernels."""
+        """True (default): split-fp16 (hi+lo planes, 3 products) tcgen05 kernels where supported; False: exact fp32 kernels."""
         object.__setattr__(self, '_tensor_cores', 1 if enabled else 0)
         for h in self._handles.values():
             h['sig'] = None

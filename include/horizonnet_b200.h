@@ -82,14 +82,16 @@ int hn_model_infer_tta(hn_model* m, const float* x_dev, int in_channels, int fli
                        int n_rotate, float* y_bon_pix_dev, float* y_cor_dev, void* stream);
 
 /* Test hook: copies an intermediate result of the LAST forward, converted to the reference's
- * layout, into `out_dev` (fp32).  Stages: "layer1".."layer4" (NCHW [B,C,H,W], model.py:78-81),
+ * layout, into `out_dev` (fp32).  Stages: "stem" (conv1+bn1+relu, NCHW [B,64,256,512], model.py:73-75),
+ * "layer1".."layer4" (NCHW [B,C,H,W], model.py:78-81),
  * "feature" ([B,1024,256], model.py:175-178), "rnn_out" ([256,B,1024], model.py:264).
  * dims receives the 4 (or 3, last = 0) extents. */
 int hn_model_stage(hn_model* m, const char* stage, float* out_dev, long long capacity, int dims[4],
                    void* stream);
 
 /* Options: "tensor_cores" = 1 routes every conv / projection GEMM the tcgen05 kernel supports
- * through the split-bf16 tensor-core path (default), 0 = exact fp32 CUDA-core kernels everywhere;
+ * through the split-fp16 tensor-core path (default), 0 = exact fp32 CUDA-core kernels everywhere;
+ * "stem_tc" = 1 (default; env HN_TC_STEM) runs the 7x7 stem on tcgen05 when "tensor_cores" is on, 0 = fp32 CUDA-core stem;
  * "profile" = 1 turns on per-launch CUDA-event timing (see hn_model_profile_read). */
 int hn_model_set_option(hn_model* m, const char* name, int value);
 
@@ -123,7 +125,7 @@ int hn_pano_stretch_host(const float* img_host, float* out_host, int n, int h, i
  * in:  [B][H][W + 2*in_halo][Cin]   out: [B][Ho][Wo + 2*out_halo][Cout]   (fp32, device)
  * w_packed: [kh*kw*Cin][Cout], k = (dy*kw + dx)*Cin + c;  scale/shift: [Cout];
  * ph = zero padding along H, pw = circular padding along W (<= in_halo).
- * impl: 0 = exact fp32 CUDA-core kernel, 1 = split-bf16 tcgen05 tensor-core kernel. */
+ * impl: 0 = exact fp32 CUDA-core kernel, 1 = split-fp16 tcgen05 tensor-core kernel. */
 int hn_conv2d(const float* in_dev, int B, int H, int W, int Cin, int in_halo,
               const float* w_packed_dev, const float* scale_dev, const float* shift_dev,
               const float* residual_dev, int Cout, int kh, int kw, int sh, int sw, int ph, int pw,
