@@ -316,7 +316,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     // a pair always loads full tiles (rows past the end are out-of-bounds boxes: zero fill, full byte count)
                     valid_rows = PAIR ? a.rows_per_tile : min(a.rows_per_tile, a.M - row0);
                 }
-                const uint32_t a_bytes = (a.mode == 0) ? 2u * S::A_PLANE : (uint32_t)(2 * valid_rows * a.tw * BKC * 2);
+                // a row box always delivers the full tile (rows past the end are out-of-bounds zero fill, full byte count)
+                const uint32_t a_bytes = (a.mode == 0) ? 2u * S::A_PLANE
+                                                       : (uint32_t)(2 * (a.rowbox ? a.rows_per_tile : valid_rows) * a.tw * BKC * 2);
                 for (int kc = 0; kc < a.num_kc; ++kc) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
                     uint8_t* sA = smem + stage * S::STAGE;
@@ -1389,10 +1391,16 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
         // one box for all rows of a tile when they are consecutive input rows of one image (stride 1 along H)
         static const bool rowbox_on = [] { const char* e = getenv("HN_TC_ROWBOX"); return !(e && atoi(e) == 0); }();
         static const bool rowbox2_on = [] { const char* e = getenv("HN_TC_ROWBOX2"); return !(e && atoi(e) == 0); }();
-        a.rowbox = (rowbox_on && a.rows_per_tile > 1 && (d.sh == 1 || (d.sh == 2 && rowbox2_on)) &&
-                    out.H % a.rows_per_tile == 0) ? 1 : 0;
-        // stride 2 along H (height-reduction convs): the box spans 2*R input rows and takes every second one
-        const cuuint32_t boxrows = a.rowbox ? (cuuint32_t)(a.rows_per_tile * d.sh) : 1u;
+        // ... or whole images when an image has fewer output rows than a tile (the last height-reduction convs):
+        // the box then spans R / Ho consecutive images of the plane
+        int box_rows = 1, box_imgs = 1;
+        a.rowbox = 0;
+        if (rowbox_on && a.rows_per_tile > 1 && (d.sh == 1 || (d.sh == 2 && rowbox2_on))) {
+            if (out.H % a.rows_per_tile == 0) { a.rowbox = 1; box_rows = a.rows_per_tile; }
+            else if (a.rows_per_tile % out.H == 0) { a.rowbox = 1; box_rows = out.H; box_imgs = a.rows_per_tile / out.H; }
+        }
+        // stride 2 along H (height-reduction convs): the box spans 2*rows input rows and takes every second one
+        const cuuint32_t boxrows = a.rowbox ? (cuuint32_t)(box_rows * d.sh) : 1u;
         const int hs = (a.rowbox && d.sh == 2) ? 2 : 1;
         const cuuint64_t C2 = (cuuint64_t)d.Cin * 2, Wp = in.Wp();
         // dx reuse (HN_TC_DXR=0 disables)
@@ -1407,12 +1415,12 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
         if (!a.parity) {
             cuuint64_t dims[4] = {(cuuint64_t)d.Cin, Wp, (cuuint64_t)in.H, (cuuint64_t)2 * in.B};
             cuuint64_t str[3] = {C2, C2 * Wp, C2 * Wp * in.H};
-            cuuint32_t box[4] = {BKC, a.dxr ? 130u : (cuuint32_t)a.tw, boxrows, 1};
+            cuuint32_t box[4] = {BKC, a.dxr ? 130u : (cuuint32_t)a.tw, boxrows, (cuuint32_t)box_imgs};
             if (make_map(&tmA, in_planes, 4, dims, str, box, hs == 2 ? 2 : -1, hs)) return -1;
         } else {
             cuuint64_t dims[5] = {(cuuint64_t)d.Cin, 2, Wp / 2, (cuuint64_t)in.H, (cuuint64_t)2 * in.B};
             cuuint64_t str[4] = {C2, 2 * C2, C2 * Wp, C2 * Wp * in.H};
-            cuuint32_t box[5] = {BKC, 1, (cuuint32_t)a.tw, boxrows, 1};
+            cuuint32_t box[5] = {BKC, 1, (cuuint32_t)a.tw, boxrows, (cuuint32_t)box_imgs};
             if (make_map(&tmA, in_planes, 5, dims, str, box, hs == 2 ? 3 : -1, hs)) return -1;
         }
         m_tiles = (long long)((a.M + a.rows_per_tile - 1) / a.rows_per_tile) * a.wsegs;
