@@ -22,6 +22,7 @@
 // Batches larger than 32 are processed in chunks of 32 (independent sequences).
 #include <cooperative_groups.h>
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include "hn_common.cuh"
 #include "ptx.cuh"
 
@@ -304,8 +305,18 @@ size_t lstm_scratch_bytes() { return 1024 + (size_t)2 * 2 * 32 * 2 * HID * sizeo
 
 // One LSTM layer, both directions.  xproj [T][B][4096], out [T][B][1024].
 // scratch: lstm_scratch_bytes() bytes (arrival counters in the first 1 KB, then the h exchange planes).
+int lstm_layer_cluster(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, float* out, int T, int B,
+                       cudaStream_t st);      // lstm_cluster.cu
+
 int lstm_layer(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, float* out, int T, int B,
                void* scratch, int* error_flag, cudaStream_t st) {
+    // preferred: 16-CTA clusters exchanging h through distributed shared memory (HN_LSTM_CLUSTER=0: the L2-exchange
+    // kernel below, which is also the fallback when the device cannot co-schedule such clusters)
+    static const bool cluster_on = [] { const char* e = getenv("HN_LSTM_CLUSTER"); return !(e && atoi(e) == 0); }();
+    if (cluster_on) {
+        const int r = lstm_layer_cluster(xproj, w_hh_fwd, w_hh_bwd, out, T, B, st);
+        if (r <= 0) return r;
+    }
     HN_CUDA_OK(cudaFuncSetAttribute(lstm_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL));
     unsigned int* counters = reinterpret_cast<unsigned int*>(scratch);
     for (int b0 = 0; b0 < B; b0 += BCHUNK) {

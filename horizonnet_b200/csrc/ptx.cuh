@@ -48,6 +48,30 @@ __device__ __forceinline__ void bulk_load_1d(void* dst_smem, const void* src_gme
                  "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// ---- thread-block clusters / distributed shared memory
+__device__ __forceinline__ uint32_t cl_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t cl_map(uint32_t smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cl_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// bulk copy from this CTA's shared memory into a peer's (shared::cluster addresses); the bytes are counted on the
+// PEER's mbarrier
+__device__ __forceinline__ void cl_bulk_copy(uint32_t dst_cluster, const void* src_smem, uint32_t bytes, uint32_t bar_cluster) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     dst_cluster),
+                 "r"(smem_u32(src_smem)), "r"(bytes), "r"(bar_cluster)
+                 : "memory");
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, const uint4& v) {
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
