@@ -8,8 +8,10 @@
 // never talk to each other:
 //   cluster = 16 CTAs x 32 hidden units;  CTA = 32 units x 4 gates = 128 rows of W_hh
 //   W_hh    = fp16 hi plane as mma.sync A fragments in REGISTERS (128 per thread) for the whole sequence,
-//             fp16 lo plane as ready-made fragments in shared memory (128 KB, one LDS.128 per MMA); per-row
-//             power-of-two scale (11 + 11 significant bits)
+//             fp16 lo plane as ready-made fragments in TENSOR MEMORY (128 KB = 256 columns, written once with
+//             tcgen05.st, read back 32 registers at a time with tcgen05.ld: TMEM as a register-file extension for
+//             a constant operand -- from shared memory the same fragments cost 128 KB of LDS traffic per step);
+//             per-row power-of-two scale (11 + 11 significant bits)
 //   step    = D[128 rows x 8 cols] = W[128 x 512] h[512 x 8]: three products Whi*hhi + Whi*hlo + Wlo*hhi with
 //             mma.sync.m16n8k16, K split over the 8 warps, partial sums reduced through shared memory; thread
 //             (column = warp, unit = lane) finishes one cell in fp32, writes the fp32 output and the fp16 hi/lo planes
@@ -18,7 +20,10 @@
 //             completing on the destination's mbarrier.  Receive / staging buffers are double-buffered by step
 //             parity; a peer can only send h_{t+1} after it has received this CTA's h_t, which makes that safe
 //             without any further handshake.
-//   grid    = 2 directions x ceil(B/8) clusters; B = 32 -> 8 clusters = 128 CTAs, one cluster per GPC.
+//   groups  = a B200 co-schedules 7 such clusters (cudaOccupancyMaxActiveClusters), bs32 has 2 x 4 (direction,
+//             column group) units: a cluster then takes TWO column groups and interleaves them step by step, so the
+//             exchange of one group travels while the other group computes.
+//   grid    = 2 directions x ceil(ceil(B/8) / groups-per-cluster) clusters.
 #include <cuda_fp16.h>
 #include <cstdlib>
 #include "hn_common.cuh"
@@ -38,19 +43,21 @@ constexpr int COLP = 144;               // bytes per column of an exchange block
 constexpr int BLK = NCOL * COLP;        // 1152 B: one CTA's h of one step (32 units x 8 columns, hi + lo)
 constexpr int PCOL = 132;               // floats per column of a partial-sum block: 128 rows + 4 pad (bank spread)
 
-constexpr int SM_WLO = 0;                                      // [8 warps][8 m][4 kt][32 lanes] uint4 A fragments (lo plane)
-constexpr int SM_RECV = SM_WLO + 8 * 8 * 4 * 32 * 16;          // [2 parity][16 source CTAs][BLK]
-constexpr int SM_STAGE = SM_RECV + 2 * CL * BLK;               // [2 parity][BLK]
-constexpr int SM_PART = SM_STAGE + 2 * BLK;                    // [8 warps][NCOL][PCOL] fp32 (init: per-row maxima)
-constexpr int SM_BAR = SM_PART + 8 * NCOL * PCOL * 4;          // full[2]
+constexpr int MAXG = 2;                                        // column groups interleaved by one cluster
+constexpr int SM_RECV = 0;                                     // [MAXG][2 parity][16 source CTAs][BLK]
+constexpr int SM_STAGE = SM_RECV + MAXG * 2 * CL * BLK;        // [MAXG][2 parity][BLK]
+constexpr int SM_PART = SM_STAGE + MAXG * 2 * BLK;             // [8 warps][NCOL][PCOL] fp32 (init: per-row maxima)
+constexpr int SM_BAR = SM_PART + 8 * NCOL * PCOL * 4;          // full[MAXG][2], TMEM base slot
 constexpr int SM_TOTAL = SM_BAR + 64;
+constexpr int TMEM_COLS = 256;                                 // W_hh lo fragments: warps 0-3 columns [0,128), warps 4-7 [128,256)
 static_assert(SM_RECV % 16 == 0 && SM_STAGE % 16 == 0 && SM_PART % 16 == 0 && SM_BAR % 8 == 0, "alignment");
 
 struct ClArgs {
     const float* xproj;      // [T][B][4096]  (dir*2048 + gate*512 + unit), bias already added
     const float* w_hh[2];    // [2048][512] per direction (PyTorch layout, row = gate*512 + unit)
     float* out;              // [T][B][1024]  (dir*512 + unit)
-    int T, B, ngroups;
+    int T, B, ngroups;      // ngroups = ceil(B / 8) column groups
+    int gpc;                // column groups per cluster (1 or 2)
 };
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -65,6 +72,26 @@ __device__ __forceinline__ uint32_t pack_h2(float lo_elem, float hi_elem) {
     const __half2 h = __floats2half2_rn(lo_elem, hi_elem);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3])
+                 : "memory");
+}
+// 32 consecutive columns of this warp's 32 TMEM lanes -> 32 registers (load + wait in one statement: the registers
+// are valid when it returns)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n\t"
+        "tcgen05.wait::ld.sync.aligned;"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
 // power-of-two scale that puts max|w| of a row into (2^13, 2^14]
 __device__ __forceinline__ float row_scale(float absmax) {
     if (!(absmax > 0.f) || !isfinite(absmax)) return 1.f;
@@ -75,25 +102,31 @@ __device__ __forceinline__ float row_scale(float absmax) {
 
 __global__ void __launch_bounds__(NT, 1) lstm_cluster_kernel(const ClArgs a) {
     extern __shared__ __align__(128) uint8_t smem[];
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM_BAR);    // [2]: h of step parity p has arrived from all 16 CTAs
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM_BAR);    // [MAXG][2]: h of (group, step parity) arrived from all 16 CTAs
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(full_bar + MAXG * 2);
     float* part = reinterpret_cast<float*>(smem + SM_PART);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int gid = lane >> 2, tig = lane & 3;
     const uint32_t rank = cl_rank();
     const int cid = blockIdx.x / CL;
-    const int dir = cid % 2, grp = cid / 2;
-    const int col0 = grp * NCOL;
-    const int nb = min(NCOL, a.B - col0);                 // valid columns of this cluster
+    const int dir = cid % 2;
+    const int g_first = (cid / 2) * a.gpc;                              // first column group of this cluster
+    const int ng = min(a.gpc, a.ngroups - g_first);                     // column groups this cluster interleaves (1 or 2)
     const int tstep = dir ? -1 : 1;
     const int t_first = dir ? a.T - 1 : 0;
 
     if (tid == 0) {
-        mbar_init(full_bar + 0, 1);
-        mbar_init(full_bar + 1, 1);
+        for (int i = 0; i < MAXG * 2; ++i) mbar_init(full_bar + i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
 
-    // ---- W_hh slice -> fp16 hi (registers) / lo (shared) A fragments.  Warp w owns k in [64w, 64w + 64); local row
+    // ---- W_hh slice -> fp16 hi (registers) / lo (tensor memory) A fragments.  Warp w owns k in [64w, 64w + 64); local row
     // lr = gate*32 + unit = 16m + 8rs + gid.  Fragment register (rs + 2hf): row 16m + 8rs + gid, k = 64w + 16kt + 2tig + 8hf (+1).
     uint32_t a_hi[8][4][4];
     float* rowbuf = part;                                  // [8 warps][128 rows] during init
@@ -115,7 +148,11 @@ __global__ void __launch_bounds__(NT, 1) lstm_cluster_kernel(const ClArgs a) {
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
             if (tig == 0) rowbuf[warp * 128 + lr] = mx;
         }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    // this warp's window of tensor memory: its lane quarter, 128 columns; column = (m*4 + kt)*4 + fragment register
+    const uint32_t tm_w = *tmem_slot + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 128);
     // the cell this thread finishes every step: column `warp`, unit `lane`
     float unscale[4];
 #pragma unroll
@@ -124,126 +161,142 @@ __global__ void __launch_bounds__(NT, 1) lstm_cluster_kernel(const ClArgs a) {
         for (int w8 = 0; w8 < 8; ++w8) mx = fmaxf(mx, rowbuf[w8 * 128 + g * 32 + lane]);
         unscale[g] = 1.f / (row_scale(mx) * H_SCALE);
     }
-    {
-        uint4* wlo = reinterpret_cast<uint4*>(smem + SM_WLO) + (size_t)warp * 8 * 4 * 32 + lane;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) {
-            float sc[2];
+    for (int m = 0; m < 8; ++m) {
+        float sc[2];
+#pragma unroll
+        for (int rs = 0; rs < 2; ++rs) {
+            float mx = 0.f;
+            for (int w8 = 0; w8 < 8; ++w8) mx = fmaxf(mx, rowbuf[w8 * 128 + 16 * m + 8 * rs + gid]);
+            sc[rs] = row_scale(mx);
+        }
+#pragma unroll
+        for (int kt = 0; kt < 4; ++kt) {
+            uint32_t lo[4];
 #pragma unroll
             for (int rs = 0; rs < 2; ++rs) {
-                float mx = 0.f;
-                for (int w8 = 0; w8 < 8; ++w8) mx = fmaxf(mx, rowbuf[w8 * 128 + 16 * m + 8 * rs + gid]);
-                sc[rs] = row_scale(mx);
-            }
+                const int lr = 16 * m + 8 * rs + gid;
+                const float* wrow = a.w_hh[dir] + (size_t)((lr >> 5) * HID + rank * UNITS + (lr & 31)) * HID;
 #pragma unroll
-            for (int kt = 0; kt < 4; ++kt) {
-                uint32_t lo[4];
-#pragma unroll
-                for (int rs = 0; rs < 2; ++rs) {
-                    const int lr = 16 * m + 8 * rs + gid;
-                    const float* wrow = a.w_hh[dir] + (size_t)((lr >> 5) * HID + rank * UNITS + (lr & 31)) * HID;
-#pragma unroll
-                    for (int hf = 0; hf < 2; ++hf) {
-                        const float2 v = __ldg(reinterpret_cast<const float2*>(wrow + 64 * warp + 16 * kt + tig * 2 + 8 * hf));
-                        const float s0 = v.x * sc[rs], s1 = v.y * sc[rs];
-                        const __half2 h = __floats2half2_rn(s0, s1);
-                        const float2 b = __half22float2(h);
-                        a_hi[m][kt][rs + 2 * hf] = *reinterpret_cast<const uint32_t*>(&h);
-                        lo[rs + 2 * hf] = pack_h2(s0 - b.x, s1 - b.y);
-                    }
+                for (int hf = 0; hf < 2; ++hf) {
+                    const float2 v = __ldg(reinterpret_cast<const float2*>(wrow + 64 * warp + 16 * kt + tig * 2 + 8 * hf));
+                    const float s0 = v.x * sc[rs], s1 = v.y * sc[rs];
+                    const __half2 h = __floats2half2_rn(s0, s1);
+                    const float2 b = __half22float2(h);
+                    a_hi[m][kt][rs + 2 * hf] = *reinterpret_cast<const uint32_t*>(&h);
+                    lo[rs + 2 * hf] = pack_h2(s0 - b.x, s1 - b.y);
                 }
-                wlo[(m * 4 + kt) * 32] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
+            tmem_st4(tm_w + (uint32_t)((m * 4 + kt) * 4), lo);
         }
     }
-    if (tid == 0 && a.T >= 2) mbar_expect_tx(full_bar + 0, (uint32_t)(CL * BLK));     // h_0 will arrive here
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    if (tid == 0 && a.T >= 2)
+        for (int g2 = 0; g2 < ng; ++g2) mbar_expect_tx(full_bar + g2 * 2 + 0, (uint32_t)(CL * BLK));     // h_0 will arrive here
     __syncthreads();          // rowbuf (aliases the partial sums) is dead from here on
     cl_sync();                // every CTA of the cluster has its barriers initialised and armed
 
-    float c_state = 0.f;
-    const int col = warp;                              // this thread's cell: (column `warp`, unit `lane`)
-    const int bcol = col0 + min(col, nb - 1);          // clamped batch index for loads
-    const uint4* wlo = reinterpret_cast<const uint4*>(smem + SM_WLO) + (size_t)warp * 8 * 4 * 32 + lane;
+    float c_state[MAXG] = {0.f, 0.f};
+    const int col = warp;                              // this thread's cell: (column `warp`, unit `lane`) of each group
 
     for (int step = 0; step < a.T; ++step) {
         const int t = t_first + step * tstep;
-        float xp[4];
-        {
-            const float* xb = a.xproj + ((size_t)t * a.B + bcol) * 4096 + dir * 2048 + rank * UNITS + lane;
 #pragma unroll
-            for (int g = 0; g < 4; ++g) xp[g] = __ldg(xb + g * HID);
-        }
-        if (step > 0) {
-            float d[8][4];
+        for (int g2 = 0; g2 < MAXG; ++g2) {
+            if (g2 >= ng) break;
+            const int col0 = (g_first + g2) * NCOL;
+            const int nb = min(NCOL, a.B - col0);                  // valid columns of this group
+            float xp[4];
+            {
+                const float* xb = a.xproj + ((size_t)t * a.B + col0 + min(col, nb - 1)) * 4096 + dir * 2048 + rank * UNITS + lane;
 #pragma unroll
-            for (int m = 0; m < 8; ++m)
-#pragma unroll
-                for (int e = 0; e < 4; ++e) d[m][e] = 0.f;
-            const int par = (step - 1) & 1;
-            mbar_wait(full_bar + par, ((step - 1) >> 1) & 1);
-            const uint8_t* rb = smem + SM_RECV + par * (CL * BLK);
-#pragma unroll
-            for (int kt = 0; kt < 4; ++kt) {
-                // k = 64*warp + 16*kt + 2*tig (+8): source CTA k/32, unit k%32; B fragment = column gid
-                const uint8_t* hb = rb + (2 * warp + (kt >> 1)) * BLK + gid * COLP + ((kt & 1) * 16 + tig * 2) * 2;
-                const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(hb);
-                const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(hb + 16);
-                const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(hb + 64);
-                const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(hb + 64 + 16);
-#pragma unroll
-                for (int m = 0; m < 8; ++m) {
-                    const uint4 al4 = wlo[(m * 4 + kt) * 32];
-                    const uint32_t al[4] = {al4.x, al4.y, al4.z, al4.w};
-                    mma16816(d[m], a_hi[m][kt], bh0, bh1);
-                    mma16816(d[m], a_hi[m][kt], bl0, bl1);
-                    mma16816(d[m], al, bh0, bh1);
-                }
+                for (int g = 0; g < 4; ++g) xp[g] = __ldg(xb + g * HID);
             }
-            // partial sums of this warp's k-range: part[warp][column][row]
-            float* pw = part + warp * (NCOL * PCOL);
-#pragma unroll
-            for (int m = 0; m < 8; ++m) {
-                pw[(tig * 2) * PCOL + 16 * m + gid] = d[m][0];
-                pw[(tig * 2 + 1) * PCOL + 16 * m + gid] = d[m][1];
-                pw[(tig * 2) * PCOL + 16 * m + gid + 8] = d[m][2];
-                pw[(tig * 2 + 1) * PCOL + 16 * m + gid + 8] = d[m][3];
-            }
-            __syncthreads();
-        }
-        float pre[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-            float s = 0.f;
             if (step > 0) {
+                const int par = (step - 1) & 1;
+                mbar_wait(full_bar + g2 * 2 + par, ((step - 1) >> 1) & 1);
+                const uint8_t* rb = smem + SM_RECV + (g2 * 2 + par) * (CL * BLK);
+                float* pw = part + warp * (NCOL * PCOL);
 #pragma unroll
-                for (int w8 = 0; w8 < 8; ++w8) s += part[(w8 * NCOL + col) * PCOL + g * 32 + lane];
+                for (int mp = 0; mp < 4; ++mp) {                   // two m-tiles per tensor-memory read
+                    uint32_t al[32];
+                    tmem_ld32(tm_w + (uint32_t)(mp * 32), al);
+                    // six independent accumulators (2 m-tiles x 3 products): consecutive MMAs never depend on each other
+                    float d[2][3][4];
+#pragma unroll
+                    for (int mm = 0; mm < 2; ++mm)
+#pragma unroll
+                        for (int pr = 0; pr < 3; ++pr)
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) d[mm][pr][e] = 0.f;
+#pragma unroll
+                    for (int kt = 0; kt < 4; ++kt) {
+                        // B fragments: k = 64*warp + 16*kt + 2*tig (+8) -> source CTA k/32, unit k%32; column gid
+                        const uint8_t* hb = rb + (2 * warp + (kt >> 1)) * BLK + gid * COLP + ((kt & 1) * 16 + tig * 2) * 2;
+                        const uint32_t bh0 = *reinterpret_cast<const uint32_t*>(hb);
+                        const uint32_t bh1 = *reinterpret_cast<const uint32_t*>(hb + 16);
+                        const uint32_t bl0 = *reinterpret_cast<const uint32_t*>(hb + 64);
+                        const uint32_t bl1 = *reinterpret_cast<const uint32_t*>(hb + 64 + 16);
+#pragma unroll
+                        for (int mm = 0; mm < 2; ++mm) {
+                            const int m = mp * 2 + mm;
+                            const uint32_t alo[4] = {al[(mm * 4 + kt) * 4 + 0], al[(mm * 4 + kt) * 4 + 1],
+                                                     al[(mm * 4 + kt) * 4 + 2], al[(mm * 4 + kt) * 4 + 3]};
+                            mma16816(d[mm][0], a_hi[m][kt], bh0, bh1);
+                            mma16816(d[mm][1], a_hi[m][kt], bl0, bl1);
+                            mma16816(d[mm][2], alo, bh0, bh1);
+                        }
+                    }
+                    // partial sums of this warp's k-range: part[warp][column][row]
+#pragma unroll
+                    for (int mm = 0; mm < 2; ++mm) {
+                        const int m = mp * 2 + mm;
+                        pw[(tig * 2) * PCOL + 16 * m + gid] = d[mm][0][0] + (d[mm][1][0] + d[mm][2][0]);
+                        pw[(tig * 2 + 1) * PCOL + 16 * m + gid] = d[mm][0][1] + (d[mm][1][1] + d[mm][2][1]);
+                        pw[(tig * 2) * PCOL + 16 * m + gid + 8] = d[mm][0][2] + (d[mm][1][2] + d[mm][2][2]);
+                        pw[(tig * 2 + 1) * PCOL + 16 * m + gid + 8] = d[mm][0][3] + (d[mm][1][3] + d[mm][2][3]);
+                    }
+                }
+                __syncthreads();
             }
-            pre[g] = fmaf(s, unscale[g], xp[g]);
-        }
-        const float c_new = sigmoidf_(pre[1]) * c_state + sigmoidf_(pre[0]) * tanhf(pre[2]);
-        c_state = c_new;
-        const float h_new = sigmoidf_(pre[3]) * tanhf(c_new);
-        if (col < nb) a.out[((size_t)t * a.B + col0 + col) * 1024 + dir * HID + rank * UNITS + lane] = h_new;
-        if (step + 1 < a.T) {
-            // exchange planes of 256*h for the next step's MMAs
-            const float hs = h_new * H_SCALE;
-            const __half hh = __float2half_rn(hs);
-            __half* sg = reinterpret_cast<__half*>(smem + SM_STAGE + (step & 1) * BLK + col * COLP) + lane;
-            sg[0] = hh;
-            sg[32] = __float2half_rn(hs - __half2float(hh));
+            float pre[4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                float sum = 0.f;
+                if (step > 0) {
+#pragma unroll
+                    for (int w8 = 0; w8 < 8; ++w8) sum += part[(w8 * NCOL + col) * PCOL + g * 32 + lane];
+                }
+                pre[g] = fmaf(sum, unscale[g], xp[g]);
+            }
+            const float c_new = sigmoidf_(pre[1]) * c_state[g2] + sigmoidf_(pre[0]) * tanhf(pre[2]);
+            c_state[g2] = c_new;
+            const float h_new = sigmoidf_(pre[3]) * tanhf(c_new);
+            if (col < nb) a.out[((size_t)t * a.B + col0 + col) * 1024 + dir * HID + rank * UNITS + lane] = h_new;
+            {
+                // exchange planes of 256*h for the next step's MMAs
+                const float hs = h_new * H_SCALE;
+                const __half hh = __float2half_rn(hs);
+                __half* sg = reinterpret_cast<__half*>(smem + SM_STAGE + (g2 * 2 + (step & 1)) * BLK + col * COLP) + lane;
+                sg[0] = hh;
+                sg[32] = __float2half_rn(hs - __half2float(hh));
+            }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> bulk-copy engine
             __syncthreads();       // staging block complete; all reads of the partial sums / receive buffer are done
-            if (tid == 0) {
-                if (step + 2 < a.T) mbar_expect_tx(full_bar + ((step + 1) & 1), (uint32_t)(CL * BLK));   // arm for h_{step+1}
-                const uint32_t dst = smem_u32(smem + SM_RECV + (step & 1) * (CL * BLK) + rank * BLK);
-                const uint32_t bar = smem_u32(full_bar + (step & 1));
-                const uint8_t* src = smem + SM_STAGE + (step & 1) * BLK;
+            if (tid == 0 && step + 1 < a.T) {
+                if (step + 2 < a.T) mbar_expect_tx(full_bar + g2 * 2 + ((step + 1) & 1), (uint32_t)(CL * BLK));   // arm for h_{step+1}
+                const uint32_t dst = smem_u32(smem + SM_RECV + (g2 * 2 + (step & 1)) * (CL * BLK) + rank * BLK);
+                const uint32_t bar = smem_u32(full_bar + g2 * 2 + (step & 1));
+                const uint8_t* src = smem + SM_STAGE + (g2 * 2 + (step & 1)) * BLK;
 #pragma unroll 1
                 for (uint32_t p = 0; p < (uint32_t)CL; ++p) cl_bulk_copy(cl_map(dst, p), src, BLK, cl_map(bar, p));
             }
         }
     }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cl_sync();     // nobody leaves while a peer's copy may still read this CTA's staging block
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
 }
 
 }  // namespace
@@ -276,8 +329,11 @@ int lstm_layer_cluster(const float* xproj, const float* w_hh_fwd, const float* w
     ClArgs a;
     a.xproj = xproj; a.w_hh[0] = w_hh_fwd; a.w_hh[1] = w_hh_bwd; a.out = out;
     a.T = T; a.B = B; a.ngroups = (B + NCOL - 1) / NCOL;
+    // one wave of clusters if possible: a cluster interleaves two column groups when 2 x groups exceeds what fits
+    a.gpc = (2 * a.ngroups <= max_clusters) ? 1 : MAXG;
+    const int nclusters = 2 * ((a.ngroups + a.gpc - 1) / a.gpc);
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * a.ngroups * CL);
+    cfg.gridDim = dim3(nclusters * CL);
     cfg.blockDim = dim3(NT);
     cfg.dynamicSmemBytes = SM_TOTAL;
     cfg.stream = st;
