@@ -123,7 +123,7 @@ def run_reference(args):
     value = args.steps * 1 / dt
     cores = torch.get_num_threads()
     sample = '1 panorama per step (bounded sample of the batch-32 workload), fp32 CPU torch ops'
-    print(json.dumps({
+    emit_json({
         'impl': 'reference', 'metric': 'panoramas/sec', 'value': value, 'unit': 'panoramas/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': dt / args.steps * 1e3,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
@@ -131,7 +131,7 @@ def run_reference(args):
         'cpu_baseline': {'value': value, 'unit': 'panoramas/s', 'cores': cores, 'kind': 'port', 'sample': sample},
         'e2e': {'value': value, 'unit': 'panoramas/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
-    }))
+    })
 
 
 def run_ours(args):
@@ -152,9 +152,6 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
-        # stdout carries exactly one JSON line: keep NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION/INFO) off it
-        if os.environ.get('NCCL_DEBUG', 'VERSION').upper() in ('VERSION', 'INFO') and not os.environ.get('NCCL_DEBUG_FILE'):
-            os.environ['NCCL_DEBUG_FILE'] = '/dev/stderr' if os.environ.get('NCCL_DEBUG') else os.devnull
         dist.init_process_group('nccl', device_id=dev)
     if rank == 0:
         entry.build()
@@ -336,12 +333,33 @@ def run_ours(args):
         'tflops_algorithmic': round(value * GFLOP_PER_PANO / 1e3, 2),
         'aux': aux,
     }
-    print(json.dumps(line))
+    emit_json(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout must carry exactly ONE JSON line: keep a private duplicate of fd 1 for it and point fd 1 at stderr, so
+    that anything else written to stdout at the C level (e.g. NCCL's "NCCL version ..." banner) lands on stderr."""
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit_json(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
