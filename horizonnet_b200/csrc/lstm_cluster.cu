@@ -305,25 +305,33 @@ __global__ void __launch_bounds__(NT, 1) lstm_cluster_kernel(const ClArgs a) {
 // such clusters (the caller then uses the L2-exchange kernel of lstm.cu), -1 on error.
 int lstm_layer_cluster(const float* xproj, const float* w_hh_fwd, const float* w_hh_bwd, float* out, int T, int B,
                        cudaStream_t st) {
-    static int max_clusters = -1;
+    // function attributes are per device: set them on every call (cheap); the occupancy answer is cached per device
+    int dev = 0;
+    HN_CUDA_OK(cudaGetDevice(&dev));
+    const bool attr_ok =
+        cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) == cudaSuccess &&
+        cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess;
+    if (!attr_ok) { (void)cudaGetLastError(); return 1; }
+    static int cached[64];
+    static bool cached_init = false;
+    if (!cached_init) { for (int i = 0; i < 64; ++i) cached[i] = -1; cached_init = true; }
+    int max_clusters = (dev >= 0 && dev < 64) ? cached[dev] : -1;
     if (max_clusters < 0) {
         max_clusters = 0;
-        if (cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL) == cudaSuccess &&
-            cudaFuncSetAttribute(lstm_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
-            cudaLaunchConfig_t q = {};
-            q.gridDim = dim3(2 * 4 * CL);
-            q.blockDim = dim3(NT);
-            q.dynamicSmemBytes = SM_TOTAL;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            q.attrs = at; q.numAttrs = 1;
-            int n = 0;
-            if (cudaOccupancyMaxActiveClusters(&n, lstm_cluster_kernel, &q) == cudaSuccess) max_clusters = n;
-        }
+        cudaLaunchConfig_t q = {};
+        q.gridDim = dim3(2 * 4 * CL);
+        q.blockDim = dim3(NT);
+        q.dynamicSmemBytes = SM_TOTAL;
+        cudaLaunchAttribute qa[1];
+        qa[0].id = cudaLaunchAttributeClusterDimension;
+        qa[0].val.clusterDim.x = CL; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+        q.attrs = qa; q.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, lstm_cluster_kernel, &q) == cudaSuccess) max_clusters = n;
         (void)cudaGetLastError();
+        if (dev >= 0 && dev < 64) cached[dev] = max_clusters;
         if (const char* e = getenv("HN_LSTM_VERBOSE"))
-            if (atoi(e)) fprintf(stderr, "lstm_cluster: max active 16-CTA clusters = %d\n", max_clusters);
+            if (atoi(e)) fprintf(stderr, "lstm_cluster: device %d: max active 16-CTA clusters = %d\n", dev, max_clusters);
     }
     if (max_clusters < 2) return 1;
     ClArgs a;
