@@ -89,3 +89,21 @@ def test_missing_device_is_reported_not_hidden(lib):
     p = ctypes.c_void_p()
     assert lib.hn_model_create(0, 1, ctypes.byref(p)) != 0
     assert b'no CUDA device' in lib.hn_last_error()
+
+
+def test_bench_reference_arm_prints_exactly_one_json_line():
+    """bench.py contract: stdout carries ONE JSON line (the driver parses it); the reference arm runs on CPU.
+    Everything else (progress, library banners) must go to stderr."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d['impl'] == 'reference' and d['metric'] == 'panoramas/sec' and d['unit'] == 'panoramas/s'
+    assert d['value'] > 0 and d['higher_is_better'] is True
+    assert d['cpu_baseline']['kind'] == 'port' and d['e2e']['h2d_bytes_per_step'] == 0
