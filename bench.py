@@ -111,6 +111,8 @@ def run_reference(args):
     import torch
     from oracle import horizonnet_ref
     from horizonnet_b200.weights import synthetic_state_dict, synthetic_panoramas
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm is the only rank doing work: use every host thread
+    torch.set_num_threads(max(torch.get_num_threads(), os.cpu_count() or 1))
     sd = synthetic_state_dict(0, 'random')
     x = synthetic_panoramas(1, seed=11)
     with torch.no_grad():
