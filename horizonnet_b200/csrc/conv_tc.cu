@@ -6,23 +6,33 @@
 // is carried as two fp16 planes of its 2^-4-scaled value:  hi = fp16(s), lo = fp16(s - hi)
 // (11 + 11 significant bits, same 4 B/element as fp32, see conv_tc.cuh), and the product is
 //     Ahi*Bhi + Ahi*Blo + Alo*Bhi            (the dropped Alo*Blo term is 2^-22 relative)
-// accumulated in one fp32 TMEM accumulator: 2e-6 .. 1e-5 max-abs end to end.  The planes are
+// accumulated in fp32 tensor memory (segmented, see below): 2.4e-6 .. 3.9e-6 max-abs end to end.  The planes are
 // written by the producing kernel's epilogue, so every operand tile is MMA-ready when TMA drops
 // it into shared memory (no in-kernel conversion pass).
 //
-// Kernel shape (persistent, warp-specialised, one CTA per SM):
-//   warp 0     TMA producer: per 64-channel K chunk it loads A (hi, lo: 128 pixels x 64 ch, 128B
-//              swizzle) with one box per output row of the tile from the halo-NHWC planes -- the
-//              3x3 taps are just shifted box coordinates, zero H padding is TMA out-of-bounds
-//              fill, circular W padding is the halo column, stride-2 in W reads a parity view --
-//              and B (hi, lo: BN x 64 weights, K-major);   3-stage mbarrier ring (64 KB / stage)
-//   warp 1     MMA issuer: one thread issues 12 tcgen05.mma (3 products x 4 K-steps of 16) per
-//              chunk into one of two TMEM accumulators; tcgen05.commit frees the smem stage and,
-//              at the end of the tile, publishes the accumulator
-//   warp 2     TMEM allocator
-//   warps 4-11 epilogue: tcgen05.ld (lane quarter = warp%4, column half = (warp-4)/4), folded
-//              BN scale/shift, residual add, ReLU, re-split into hi/lo planes (or fp32), vector
-//              stores incl. the circular halo columns; overlaps the next tile's MMAs.
+// Kernels in this file (all persistent, warp-specialised, one CTA per SM, 384 threads):
+//   conv_tc_kernel<BN>  3x3 / strided / large-K 1x1 convs and the LSTM input projections
+//   gemm_tc_kernel      1x1 stride-1 convs with K <= 256 (TMA-prefetched residual, in-place epilogue, TMA store)
+//   stem_tc_kernel      the 7x7 stride-2 stem over packed pixel pairs (no-swizzle UMMA operand with overlapping rows)
+//
+// conv_tc_kernel:
+//   warp 0     TMA producer: per 64-channel K chunk it loads A (hi, lo: 128 pixels x 64 ch, 128B swizzle) from the
+//              halo-NHWC planes with ONE box per plane -- {64 ch, tw pixels, R rows} for multi-row tiles (traversal
+//              stride 2 along H for the stride-(2,1) convs, whole images when an image has fewer rows than a tile);
+//              the 3x3 taps are shifted box coordinates, zero H padding is TMA out-of-bounds fill, circular W padding
+//              is the halo column, stride-2 in W reads a parity view -- and B (hi, lo: BN x 64 weights, K-major);
+//              3-stage mbarrier ring of 64 KB stages (4 stages of 48 KB for BN <= 64).
+//              "dxr" mode (3x3, one 128-pixel row per tile): one 130-pixel box per (dy, chunk) feeds all three dx taps
+//              through UMMA descriptors whose start address is shifted by dx rows (the swizzle is a function of the
+//              absolute shared-memory address) -- the large-K convs were bound by L2 -> SM fill (12.5 TB/s).
+//   warp 1     MMA issuer: one thread issues 12 tcgen05.mma (3 products x 4 K-steps of 16) per chunk: hi*hi into a
+//              segment accumulator that is restarted every `seg` chunks, hi*lo and lo*hi into a cross accumulator
+//              (tcgen05 accumulates with truncation, see the comment at the issue loop); tcgen05.commit frees the
+//              smem stage and publishes segments / tiles
+//   warp 2     TMEM allocator (2 segment + 2 cross accumulators = 4*BN columns)
+//   warps 4-11 epilogue: tcgen05.ld (lane quarter = warp%4, column half = (warp-4)/4), segment promotion in fp32
+//              registers, folded BN scale/shift, residual add, ReLU, re-split into hi/lo planes (or fp32), coalesced
+//              stores through a warp-private staging buffer incl. the circular halo columns; overlaps the next tile's MMAs.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cstdlib>
