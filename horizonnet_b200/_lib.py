@@ -8,7 +8,7 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libhorizonnet_b200.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _lib = None
 _lock = threading.Lock()
@@ -22,6 +22,7 @@ vp = ctypes.c_void_p
 SIGNATURES = {
     'hn_last_error': (ctypes.c_char_p, []),
     'hn_abi_version': (ctypes.c_int, []),
+    'hn_build_digest': (ctypes.c_char_p, []),
     'hn_kernel_launches': (ctypes.c_longlong, []),
     'hn_model_create': (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.POINTER(vp)]),
     'hn_model_num_tensors': (ctypes.c_int, [vp]),
@@ -30,6 +31,8 @@ SIGNATURES = {
     'hn_model_set_tensor': (ctypes.c_int, [vp, ctypes.c_char_p, vp, ctypes.c_longlong, ctypes.c_int]),
     'hn_model_finalize': (ctypes.c_int, [vp]),
     'hn_model_forward': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
+    'hn_model_forward_async': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
+    'hn_model_flush': (ctypes.c_int, [vp, vp]),
     'hn_model_forward_host': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp]),
     'hn_model_submit_host': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int]),
     'hn_model_collect_host': (ctypes.c_int, [vp, vp, vp]),
@@ -68,6 +71,12 @@ def lib():
             fn.argtypes = args
         if l.hn_abi_version() != ABI_VERSION:
             raise RuntimeError('libhorizonnet_b200 ABI version mismatch; rebuild')
+        # a binary built from other sources than the ones checked out (e.g. a stale .so after `git pull`) must not run
+        from . import build as _build
+        have, want = l.hn_build_digest().decode(), _build.source_digest()
+        if have != want:
+            raise RuntimeError(f'libhorizonnet_b200.so was built from different sources (digest {have[:12]} != '
+                               f'{want[:12]}); run `python -c "import __graft_entry__ as g; g.build()"`')
         _lib = l
     return _lib
 

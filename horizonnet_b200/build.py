@@ -1,6 +1,8 @@
 """Builds libhorizonnet_b200.so in-tree with nvcc for sm_100a (no torch extension machinery:
 the boundary is a plain C ABI loaded with ctypes).  The .so is git-ignored but travels to the GPU
-box with the gpurun snapshot."""
+box with the gpurun snapshot.  The digest of the sources is embedded in the binary (hn_build_digest) and the
+binding compares it with the checked-out sources, so a stale binary can never be loaded silently; the
+`.sha256` stamp beside the .so (untracked, like the .so) only decides whether a rebuild is needed."""
 import hashlib
 import os
 import subprocess
@@ -32,6 +34,11 @@ def _digest():
     return h.hexdigest()
 
 
+def source_digest():
+    """Digest of the CUDA sources, headers and flags; embedded in the .so as hn_build_digest()."""
+    return _digest()
+
+
 def build(force=False, verbose=False):
     """Compile every .cu of the package for sm_100a and link the shared library."""
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
@@ -45,7 +52,8 @@ def build(force=False, verbose=False):
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace('.cu', '.o'))
-        cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
+        extra = ['-DHN_BUILD_DIGEST="%s"' % digest] if src == 'model.cu' else []
+        cmd = [nvcc] + NVCC_FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-c', os.path.join(CSRC, src), '-o', obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     objs = []
     for src, obj, p in procs:

@@ -14,6 +14,9 @@
 #include "../../include/horizonnet_b200.h"
 
 #define HN_NUM_CLASSES 8
+#ifndef HN_BUILD_DIGEST
+#define HN_BUILD_DIGEST "unknown"
+#endif
 
 namespace hn {
 
@@ -37,6 +40,21 @@ int pano_stretch_device(const float* img, float* out, int n, int H, int W, int C
                         const double* ky_dev, double* scratch, int order, cudaStream_t st);
 
 namespace {
+
+// Entry points run on the model's device and restore the caller's current device on return (a multi-GPU
+// single-process caller must not find its current device switched by a forward on another GPU).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define HN_ON_DEVICE(dev)                                                                  \
+    DeviceGuard _dg(dev);                                                                  \
+    if (!_dg.ok) return ::hn::fail("cudaSetDevice failed for the model's device")
 
 // ---- packing kernels ---------------------------------------------------------------------------
 // OIHW [Cout][Cin][kh][kw] -> [K = (dy*kw+dx)*Cin + c][Cout]
@@ -162,6 +180,16 @@ struct hn_model {
     cudaEvent_t slot_ready[2] = {nullptr, nullptr};
     int slot_batch[2] = {0, 0};
     int submit_count = 0, collect_count = 0;
+    float* bon_slot[2] = {nullptr, nullptr};        // device outputs of the two host-pipeline slots
+    float* cor_slot[2] = {nullptr, nullptr};
+    // Two-stream schedule of the throughput entry points (hn_model_forward_async, submit/collect): the encoder +
+    // height reduction of batch i+1 run on enc_stream while the bi-LSTM + head of batch i (64 of the 148 SMs,
+    // latency-bound) run on the high-priority rnn_stream.
+    cudaStream_t enc_stream = nullptr, rnn_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_xfree = nullptr, ev_seq = nullptr, ev_rnn_last = nullptr, ev_plain_done = nullptr;
+    cudaEvent_t async_done[2] = {nullptr, nullptr}, slot_done[2] = {nullptr, nullptr};
+    bool rnn_inflight = false, plain_recorded = false;
+    long long async_count = 0;
     int* tta_ints = nullptr;                        // [2][64] view modes / shifts for hn_model_infer_tta
     int last_batch = 0;
 
@@ -175,13 +203,21 @@ struct hn_model {
     long long prof_launches[HN_NUM_CLASSES] = {0};
 
     ~hn_model() {
+        int prev_dev = -1;
+        if (cudaGetDevice(&prev_dev) != cudaSuccess) prev_dev = -1;
         cudaSetDevice(device);
         for (auto& sp : spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
         for (auto e : free_events) cudaEventDestroy(e);
         for (int i = 0; i < 2; ++i) if (slot_ready[i]) cudaEventDestroy(slot_ready[i]);
         if (copy_stream) cudaStreamDestroy(copy_stream);
         if (compute_stream) cudaStreamDestroy(compute_stream);
+        for (cudaEvent_t e : {ev_in, ev_xfree, ev_seq, ev_rnn_last, ev_plain_done, async_done[0], async_done[1],
+                              slot_done[0], slot_done[1]})
+            if (e) cudaEventDestroy(e);
+        if (enc_stream) cudaStreamDestroy(enc_stream);
+        if (rnn_stream) cudaStreamDestroy(rnn_stream);
         for (void* p : allocs) cudaFree(p);
+        if (prev_dev >= 0) cudaSetDevice(prev_dev);
     }
     cudaEvent_t get_event() {
         if (!free_events.empty()) { cudaEvent_t e = free_events.back(); free_events.pop_back(); return e; }
@@ -331,7 +367,8 @@ int run_conv(hn_model* m, const ConvLayer& c, const Act& in, const Act& out, con
 extern "C" {
 
 const char* hn_last_error(void) { return g_err.c_str(); }
-int hn_abi_version(void) { return 1; }
+int hn_abi_version(void) { return 2; }
+const char* hn_build_digest(void) { return HN_BUILD_DIGEST; }
 long long hn_kernel_launches(void) { return g_launches.load(); }
 
 int hn_model_create(int device, int max_batch, hn_model** out) {
@@ -341,7 +378,7 @@ int hn_model_create(int device, int max_batch, hn_model** out) {
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         return fail("hn_model_create: no CUDA device -- libhorizonnet_b200 has no CPU path");
     HN_CHECK(device >= 0 && device < ndev, "hn_model_create: bad device index");
-    HN_CUDA_OK(cudaSetDevice(device));
+    HN_ON_DEVICE(device);
     cudaDeviceProp prop;
     HN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
     HN_CHECK(prop.major == 10, "hn_model_create: this library is built for sm_100a (B200) only");
@@ -363,6 +400,7 @@ int hn_model_create(int device, int max_batch, hn_model** out) {
         {&m->XP, (256 * B * 4096 > (size_t)4096 * 1024) ? 256 * B * 4096 : (size_t)4096 * 1024},       {&m->R1, 256 * B * 1024},       {&m->R2, 256 * B * 1024},       {&m->R1S, 256 * B * 1024},
         {&m->x_in, B * 3 * 512 * 1024}, {&m->bon_out, B * 2 * 1024},    {&m->cor_out, B * 1024},
         {&m->x_slot[1], B * 3 * 512 * 1024},
+        {&m->bon_slot[1], B * 2 * 1024},  {&m->cor_slot[1], B * 1024},
         {&m->head_w, 12 * 1024},        {&m->head_b, 12},
     };
     for (auto& b : bufs)
@@ -372,9 +410,23 @@ int hn_model_create(int device, int max_batch, hn_model** out) {
     if (m->alloc_t(&m->tta_ints, 128)) return -1;
     HN_CUDA_OK(cudaMemset(m->error_flag, 0, sizeof(int)));
     m->x_slot[0] = m->x_in;
+    m->bon_slot[0] = m->bon_out; m->cor_slot[0] = m->cor_out;
     HN_CUDA_OK(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
     HN_CUDA_OK(cudaStreamCreateWithFlags(&m->compute_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) HN_CUDA_OK(cudaEventCreateWithFlags(&m->slot_ready[i], cudaEventDisableTiming));
+    {
+        int prio_lo = 0, prio_hi = 0;
+        HN_CUDA_OK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        HN_CUDA_OK(cudaStreamCreateWithPriority(&m->enc_stream, cudaStreamNonBlocking, prio_lo));
+        // the recurrence's 16-CTA clusters must get their SMs as soon as a convolution kernel retires
+        HN_CUDA_OK(cudaStreamCreateWithPriority(&m->rnn_stream, cudaStreamNonBlocking, prio_hi));
+    }
+    for (int i = 0; i < 2; ++i) {
+        HN_CUDA_OK(cudaEventCreateWithFlags(&m->slot_ready[i], cudaEventDisableTiming));
+        HN_CUDA_OK(cudaEventCreateWithFlags(&m->slot_done[i], cudaEventDisableTiming));
+        HN_CUDA_OK(cudaEventCreateWithFlags(&m->async_done[i], cudaEventDisableTiming));
+    }
+    for (cudaEvent_t* e : {&m->ev_in, &m->ev_xfree, &m->ev_seq, &m->ev_rnn_last, &m->ev_plain_done})
+        HN_CUDA_OK(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
     *out = m.release();
     return 0;
 }
@@ -398,7 +450,7 @@ int hn_model_set_tensor(hn_model* m, const char* key, const float* data, long lo
     if (numel != s.numel)
         return fail(std::string("hn_model_set_tensor: size mismatch for '") + key + "': got " + std::to_string(numel) +
                     ", expected " + std::to_string(s.numel));
-    HN_CUDA_OK(cudaSetDevice(m->device));
+    HN_ON_DEVICE(m->device);
     HN_CUDA_OK(cudaMemcpy(s.dev, data, (size_t)numel * sizeof(float),
                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
     s.set = true;
@@ -418,7 +470,7 @@ int hn_model_finalize(hn_model* m) {
     HN_CHECK(m, "hn_model_finalize: NULL model");
     for (auto& s : m->slots)
         if (!s.set && !s.ignored) return fail("hn_model_finalize: missing key '" + s.key + "' (strict load, utils.py:64)");
-    HN_CUDA_OK(cudaSetDevice(m->device));
+    HN_ON_DEVICE(m->device);
     cudaStream_t st = 0;
     if (pack_conv(m, m->stem, st)) return -1;
     if (!m->stem_wq && (m->alloc_t(&m->stem_wq, (size_t)2 * 64 * 224) || m->alloc_t(&m->stem_aux, 3 * 64 + 1))) return -1;
@@ -462,14 +514,10 @@ int hn_model_finalize(hn_model* m) {
     return 0;
 }
 
-int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float* bon, float* cor, void* stream) {
-    HN_CHECK(m && x && bon && cor, "hn_model_forward: NULL argument");
-    HN_CHECK(m->finalized, "hn_model_forward: call hn_model_finalize after setting all tensors");
-    HN_CHECK(B >= 1 && B <= m->max_batch, "hn_model_forward: batch exceeds max_batch given at create");
-    HN_CUDA_OK(cudaSetDevice(m->device));
-    cudaStream_t st = (cudaStream_t)stream;
-    m->last_batch = B;
-
+// ---- the three parts of HorizonNet.forward (model.py:254-281); static helpers (no extern "C" linkage needed)
+// (1) normalise + stem + max-pool + layer1..4 + the 16 height-reduction convs: leaves gout[] in GO[0..3]
+static int forward_encoder(hn_model* m, const float* x, int B, int in_channels, Act gout[4], cudaStream_t st,
+                           cudaEvent_t x_consumed) {
     // model.py:248-252 + :73-76: normalise, stem conv/BN/ReLU, max-pool
     Act s0 = mk(m->S0, B, 256, 512, 64);
     {
@@ -480,6 +528,7 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
                         reinterpret_cast<unsigned short*>(m->X[0]), s0, st)) return -1;
         } else if (stem_f32(x, B, in_channels, m->stem.w, m->stem.scale, m->stem.shift, s0, st)) return -1;
     }
+    if (x_consumed) HN_CUDA_OK(cudaEventRecord(x_consumed, st));       // the input batch is not read after the stem
     Act cur = mk(m->S1, B, 128, 256, 64);
     {
         Scope sc(m, CLS_POOL, 0.0, st);
@@ -512,7 +561,6 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
     }
 
     // model.py:148-151: 4 x (3x3 stride (2,1) conv + bias + BN + ReLU) per scale
-    Act gout[4];
     for (int s = 0; s < 4; ++s) {
         Act g = feats[s];
         for (int j = 0; j < 4; ++j) {
@@ -523,13 +571,17 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
         }
         gout[s] = g;
     }
-    // model.py:152-155 + :175-178 + :263 -> [T=256][B][1024]
-    {
-        Scope sc(m, CLS_TAIL, 0.0, st);
-        if (ghc_to_sequence(gout, m->SEQ, st, m->use_tc != 0)) return -1;
-    }
+    return 0;
+}
 
-    // model.py:264: 2-layer bidirectional LSTM (eval: dropout = identity)
+// (2) model.py:152-155 + :175-178 + :263: upsample + flatten + concat + permute -> SEQ [T=256][B][1024]
+static int forward_sequence(hn_model* m, const Act gout[4], cudaStream_t st) {
+    Scope sc(m, CLS_TAIL, 0.0, st);
+    return ghc_to_sequence(gout, m->SEQ, st, m->use_tc != 0);
+}
+
+// (3) model.py:264-281: 2-layer bidirectional LSTM (eval: dropout = identity), linear head, reshape, split
+static int forward_rnn(hn_model* m, int B, float* bon, float* cor, cudaStream_t st) {
     const float* lin = m->SEQ;
     float* louts[2] = {m->R1, m->R2};
     for (int layer = 0; layer < 2; ++layer) {
@@ -550,7 +602,6 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
         }
         lin = louts[layer];
     }
-    // model.py:265-281: dropout (id), linear, reshape, split
     {
         Scope sc(m, CLS_HEAD, 2.0 * 256 * B * 12 * 1024, st);
         if (linear_head(m->R2, m->head_w, m->head_b, bon, cor, 256, B, st)) return -1;
@@ -558,9 +609,80 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
     return 0;
 }
 
+static int forward_args_ok(hn_model* m, const void* x, int B, const void* bon, const void* cor, const char* who) {
+    if (!(m && x && bon && cor)) return fail(std::string(who) + ": NULL argument");
+    if (!m->finalized) return fail(std::string(who) + ": call hn_model_finalize after setting all tensors");
+    if (!(B >= 1 && B <= m->max_batch)) return fail(std::string(who) + ": batch exceeds max_batch given at create");
+    return 0;
+}
+
+// Two-stream enqueue of one forward: encoder + height reduction on enc_stream (the caller has already made
+// enc_stream wait for the input), sequence assembly once the previous batch's recurrence no longer reads SEQ,
+// then projections + recurrence + head on rnn_stream.  `done` (optional) is recorded when bon/cor are complete.
+static int enqueue_two_stream(hn_model* m, const float* x, int B, int in_channels, float* bon, float* cor,
+                              cudaEvent_t done) {
+    if (m->plain_recorded) {      // a plain hn_model_forward on a caller stream may still use the workspace
+        HN_CUDA_OK(cudaStreamWaitEvent(m->enc_stream, m->ev_plain_done, 0));
+        HN_CUDA_OK(cudaStreamWaitEvent(m->rnn_stream, m->ev_plain_done, 0));
+        m->plain_recorded = false;
+    }
+    Act gout[4];
+    if (forward_encoder(m, x, B, in_channels, gout, m->enc_stream, m->ev_xfree)) return -1;
+    if (m->rnn_inflight) HN_CUDA_OK(cudaStreamWaitEvent(m->enc_stream, m->ev_rnn_last, 0));
+    if (forward_sequence(m, gout, m->enc_stream)) return -1;
+    HN_CUDA_OK(cudaEventRecord(m->ev_seq, m->enc_stream));
+    HN_CUDA_OK(cudaStreamWaitEvent(m->rnn_stream, m->ev_seq, 0));
+    if (forward_rnn(m, B, bon, cor, m->rnn_stream)) return -1;
+    HN_CUDA_OK(cudaEventRecord(m->ev_rnn_last, m->rnn_stream));
+    if (done) HN_CUDA_OK(cudaEventRecord(done, m->rnn_stream));
+    m->rnn_inflight = true;
+    m->last_batch = B;
+    return 0;
+}
+
+int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float* bon, float* cor, void* stream) {
+    if (forward_args_ok(m, x, B, bon, cor, "hn_model_forward")) return -1;
+    HN_ON_DEVICE(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->rnn_inflight) {        // join batches still in flight on the internal streams (they share the workspace)
+        HN_CUDA_OK(cudaStreamWaitEvent(st, m->ev_rnn_last, 0));
+        m->rnn_inflight = false;
+    }
+    m->last_batch = B;
+    Act gout[4];
+    if (forward_encoder(m, x, B, in_channels, gout, st, nullptr)) return -1;
+    if (forward_sequence(m, gout, st)) return -1;
+    if (forward_rnn(m, B, bon, cor, st)) return -1;
+    HN_CUDA_OK(cudaEventRecord(m->ev_plain_done, st));
+    m->plain_recorded = true;
+    return 0;
+}
+
+int hn_model_forward_async(hn_model* m, const float* x, int B, int in_channels, float* bon, float* cor, void* stream) {
+    if (forward_args_ok(m, x, B, bon, cor, "hn_model_forward_async")) return -1;
+    HN_ON_DEVICE(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    HN_CUDA_OK(cudaEventRecord(m->ev_in, st));                          // x (and everything before it on st) is ready
+    HN_CUDA_OK(cudaStreamWaitEvent(m->enc_stream, m->ev_in, 0));
+    const int slot = (int)(m->async_count & 1);
+    const bool had_prev = m->async_count > 0;
+    if (enqueue_two_stream(m, x, B, in_channels, bon, cor, m->async_done[slot])) return -1;
+    HN_CUDA_OK(cudaStreamWaitEvent(st, m->ev_xfree, 0));                // x may be overwritten by later work on st
+    if (had_prev) HN_CUDA_OK(cudaStreamWaitEvent(st, m->async_done[slot ^ 1], 0));   // outputs of the PREVIOUS call
+    ++m->async_count;
+    return 0;
+}
+
+int hn_model_flush(hn_model* m, void* stream) {
+    HN_CHECK(m, "hn_model_flush: NULL model");
+    HN_ON_DEVICE(m->device);
+    if (m->rnn_inflight) HN_CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, m->ev_rnn_last, 0));
+    return 0;
+}
+
 int hn_model_profile_read(hn_model* m, double* ms, double* flops, long long* launches, int reset) {
     HN_CHECK(m, "hn_model_profile_read: NULL model");
-    HN_CUDA_OK(cudaSetDevice(m->device));
+    HN_ON_DEVICE(m->device);
     for (auto& sp : m->spans) {
         HN_CUDA_OK(cudaEventSynchronize(sp.b));
         float t = 0.f;
@@ -581,6 +703,7 @@ int hn_model_profile_read(hn_model* m, double* ms, double* flops, long long* lau
 int hn_model_check(hn_model* m) {
     // surfaces device-side failures (LSTM spin timeout) after a synchronisation point
     HN_CHECK(m, "hn_model_check: NULL model");
+    HN_ON_DEVICE(m->device);
     int flag = 0;
     HN_CUDA_OK(cudaMemcpy(&flag, m->error_flag, sizeof(int), cudaMemcpyDeviceToHost));
     if (flag) {
@@ -594,7 +717,8 @@ int hn_model_forward_host(hn_model* m, const float* x, int B, int in_channels, f
     HN_CHECK(m && x && bon && cor, "hn_model_forward_host: NULL argument");
     HN_CHECK(B >= 1 && B <= m->max_batch, "hn_model_forward_host: batch exceeds max_batch");
     HN_CHECK(in_channels >= 3, "hn_model_forward_host: need >= 3 channels");
-    HN_CUDA_OK(cudaSetDevice(m->device));
+    HN_CHECK(m->submit_count == m->collect_count, "hn_model_forward_host: collect the submitted batches first");
+    HN_ON_DEVICE(m->device);
     cudaStream_t st = 0;
     // only the first 3 channels are used (model.py:252): copy them image by image
     for (int b = 0; b < B; ++b)
@@ -609,15 +733,20 @@ int hn_model_forward_host(hn_model* m, const float* x, int B, int in_channels, f
 
 int hn_model_submit_host(hn_model* m, const float* x, int B, int in_channels) {
     HN_CHECK(m && x, "hn_model_submit_host: NULL argument");
+    HN_CHECK(m->finalized, "hn_model_submit_host: call hn_model_finalize after setting all tensors");
     HN_CHECK(B >= 1 && B <= m->max_batch, "hn_model_submit_host: batch exceeds max_batch");
     HN_CHECK(in_channels >= 3, "hn_model_submit_host: need >= 3 channels");
     HN_CHECK(m->submit_count - m->collect_count < 2, "hn_model_submit_host: both input slots are in flight (collect first)");
-    HN_CUDA_OK(cudaSetDevice(m->device));
+    HN_ON_DEVICE(m->device);
     const int slot = m->submit_count & 1;
+    // the slot's previous batch was collected (fully synchronised), so its input buffer is free
     for (int b = 0; b < B; ++b)
         HN_CUDA_OK(cudaMemcpyAsync(m->x_slot[slot] + (size_t)b * 3 * 512 * 1024, x + (size_t)b * in_channels * 512 * 1024,
                                    (size_t)3 * 512 * 1024 * sizeof(float), cudaMemcpyHostToDevice, m->copy_stream));
     HN_CUDA_OK(cudaEventRecord(m->slot_ready[slot], m->copy_stream));
+    // the forward is enqueued right away: the encoder of this batch overlaps the recurrence of the previous one
+    HN_CUDA_OK(cudaStreamWaitEvent(m->enc_stream, m->slot_ready[slot], 0));
+    if (enqueue_two_stream(m, m->x_slot[slot], B, 3, m->bon_slot[slot], m->cor_slot[slot], m->slot_done[slot])) return -1;
     m->slot_batch[slot] = B;
     ++m->submit_count;
     return 0;
@@ -626,16 +755,23 @@ int hn_model_submit_host(hn_model* m, const float* x, int B, int in_channels) {
 int hn_model_collect_host(hn_model* m, float* bon, float* cor) {
     HN_CHECK(m && bon && cor, "hn_model_collect_host: NULL argument");
     HN_CHECK(m->collect_count < m->submit_count, "hn_model_collect_host: nothing submitted");
-    HN_CUDA_OK(cudaSetDevice(m->device));
+    HN_ON_DEVICE(m->device);
     const int slot = m->collect_count & 1;
     const int B = m->slot_batch[slot];
     cudaStream_t st = m->compute_stream;
-    HN_CUDA_OK(cudaStreamWaitEvent(st, m->slot_ready[slot], 0));
-    if (hn_model_forward(m, m->x_slot[slot], B, 3, m->bon_out, m->cor_out, st)) return -1;
-    HN_CUDA_OK(cudaMemcpyAsync(bon, m->bon_out, (size_t)B * 2 * 1024 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    HN_CUDA_OK(cudaMemcpyAsync(cor, m->cor_out, (size_t)B * 1024 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HN_CUDA_OK(cudaStreamWaitEvent(st, m->slot_done[slot], 0));
+    HN_CUDA_OK(cudaMemcpyAsync(bon, m->bon_slot[slot], (size_t)B * 2 * 1024 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    HN_CUDA_OK(cudaMemcpyAsync(cor, m->cor_slot[slot], (size_t)B * 1024 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    // a device-side LSTM timeout of this batch is surfaced here (the flag is written before the outputs complete)
+    int flag = 0;
+    HN_CUDA_OK(cudaMemcpyAsync(&flag, m->error_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
     HN_CUDA_OK(cudaStreamSynchronize(st));
     ++m->collect_count;
+    if (flag) {
+        cudaMemsetAsync(m->error_flag, 0, sizeof(int), st);
+        cudaStreamSynchronize(st);
+        return fail("hn_model: the persistent LSTM kernel timed out waiting for a peer CTA");
+    }
     return 0;
 }
 
@@ -646,7 +782,8 @@ int hn_model_infer_tta(hn_model* m, const float* x, int in_channels, int flip, c
     HN_CHECK(n_rotate >= 0 && n_rotate <= 32 && (n_rotate == 0 || shifts), "hn_model_infer_tta: bad rotate list");
     const int V = 1 + (flip ? 1 : 0) + n_rotate;
     HN_CHECK(V <= m->max_batch && V <= 64, "hn_model_infer_tta: views exceed max_batch");
-    HN_CUDA_OK(cudaSetDevice(m->device));
+    HN_CHECK(m->submit_count == m->collect_count, "hn_model_infer_tta: collect the submitted batches first");
+    HN_ON_DEVICE(m->device);
     cudaStream_t st = (cudaStream_t)stream;
     int host[128];
     int v = 0;
@@ -663,8 +800,9 @@ int hn_model_infer_tta(hn_model* m, const float* x, int in_channels, int flip, c
 int hn_model_stage(hn_model* m, const char* stage, float* out, long long capacity, int dims[4], void* stream) {
     HN_CHECK(m && stage && out && dims, "hn_model_stage: NULL argument");
     HN_CHECK(m->last_batch > 0, "hn_model_stage: no forward has run yet");
-    HN_CUDA_OK(cudaSetDevice(m->device));
+    HN_ON_DEVICE(m->device);
     cudaStream_t st = (cudaStream_t)stream;
+    if (m->rnn_inflight) HN_CUDA_OK(cudaStreamWaitEvent(st, m->ev_rnn_last, 0));
     const int B = m->last_batch;
     const std::string s(stage);
     for (int l = 0; l < 4; ++l)
@@ -673,9 +811,10 @@ int hn_model_stage(hn_model* m, const char* stage, float* out, long long capacit
             const size_t total = (size_t)B * C * H * W;
             HN_CHECK((long long)total <= capacity, "hn_model_stage: output buffer too small");
             const float* src = m->F[l];
-            if (m->use_tc) {       // F[l] holds fp16 hi/lo planes: merge into T1 scratch first (free after the forward)
+            if (m->use_tc) {       // F[l] holds fp16 hi/lo planes: merge into X[0] (free after the forward)
                 const size_t n = (size_t)B * H * (W + 2) * C;
-                float* tmp = (l == 0) ? m->X[0] : m->T1;
+                float* tmp = m->X[0];
+                HN_CHECK(n <= (size_t)m->max_batch * 128 * 258 * 256, "hn_model_stage: scratch buffer too small");
                 if (merge_planes(reinterpret_cast<const unsigned short*>(m->F[l]), tmp, n, st)) return -1;
                 src = tmp;
             }

@@ -134,6 +134,7 @@ class HorizonNet(nn.Module):
         object.__setattr__(self, '_handles', {})
         object.__setattr__(self, '_lock', threading.Lock())
         object.__setattr__(self, '_tensor_cores', 1)
+        object.__setattr__(self, '_refresh_epoch', 0)
         self._slots = None
 
     # ---- weights -> device library --------------------------------------------------------------
@@ -153,6 +154,26 @@ class HorizonNet(nn.Module):
             if t is None:
                 t = mod._buffers[leaf]
             yield key, t
+
+    def _weight_signature(self):
+        """Identity of the current weights: (storage pointer, in-place version counter) of every tensor.  Edits made
+        through ``param.data`` do not bump the version counter -- call refresh_weights() after such edits."""
+        if self._slots is None:
+            list(self._state_tensors())
+        sig = [self._tensor_cores, self._refresh_epoch]
+        for _, mod, leaf in self._slots:
+            t = mod._parameters.get(leaf)
+            if t is None:
+                t = mod._buffers[leaf]
+            sig.append(t.data_ptr())
+            sig.append(t._version)
+        return tuple(sig)
+
+    def refresh_weights(self):
+        """Force a re-upload of all weights on the next forward (needed after edits through ``.data`` / raw pointers,
+        which PyTorch's version counter does not see)."""
+        object.__setattr__(self, '_refresh_epoch', self._refresh_epoch + 1)
+        return self
 
     def use_tensor_cores(self, enabled=True):
         """True (default): split-fp16 (hi+lo planes, 3 products) tcgen05 kernels where supported; False: exact fp32 kernels."""
@@ -175,10 +196,9 @@ class HorizonNet(nn.Module):
                 _lib.check(lib.hn_model_create(key, max_batch, ctypes.byref(ptr)), 'hn_model_create')
                 h = {'ptr': ptr, 'max_batch': max_batch, 'sig': None}
                 self._handles[key] = h
-            tensors = list(self._state_tensors())
-            sig = tuple((t.data_ptr(), t._version) for _, t in tensors) + (self._tensor_cores,)
+            sig = self._weight_signature()
             if h['sig'] != sig:
-                for k, t in tensors:
+                for k, t in self._state_tensors():
                     if not t.is_floating_point():
                         _lib.check(lib.hn_model_set_tensor(h['ptr'], k.encode(), None, 1, 1), k)
                         continue
@@ -193,12 +213,21 @@ class HorizonNet(nn.Module):
         raise RuntimeError('input normalisation is fused into the stem kernel; call forward()')
 
     def forward(self, x):
+        x, B, C, h, bon, cor, stream = self._forward_prologue(x)
+        _lib.check(_lib.lib().hn_model_forward(h['ptr'], x.data_ptr(), B, C, bon.data_ptr(), cor.data_ptr(), stream),
+                   'hn_model_forward')
+        return bon, cor
+
+    def _forward_prologue(self, x):
         if x.shape[2] != PANO_H or x.shape[3] != PANO_W:
             raise NotImplementedError()                                   # model.py:255-256
+        if self.training:
+            # train mode means batch-statistics BN and dropout in the reference (train.py:52); running the eval graph
+            # instead would diverge silently, with or without grad
+            raise NotImplementedError('horizonnet_b200 implements the inference forward only: call .eval() '
+                                      '(train-mode BN / dropout / backward are the "next" row f1)')
         if not x.is_cuda:
             raise RuntimeError('horizonnet_b200.HorizonNet has no CPU path: move the input to a B200 (cuda) device')
-        if self.training and torch.is_grad_enabled():
-            raise NotImplementedError('horizonnet_b200 implements the inference forward (eval / no_grad) only')
         if x.shape[1] < 3:
             raise RuntimeError('input needs at least 3 channels (model.py:252 reads x[:, :3])')
         x = x.detach().to(torch.float32).contiguous()
@@ -207,9 +236,26 @@ class HorizonNet(nn.Module):
         bon = torch.empty(B, 2, PANO_W, device=x.device, dtype=torch.float32)
         cor = torch.empty(B, 1, PANO_W, device=x.device, dtype=torch.float32)
         stream = torch.cuda.current_stream(x.device).cuda_stream
-        _lib.check(_lib.lib().hn_model_forward(h['ptr'], x.data_ptr(), B, C, bon.data_ptr(), cor.data_ptr(), stream),
-                   'hn_model_forward')
+        return x, B, C, h, bon, cor, stream
+
+    def forward_pipelined(self, x):
+        """Throughput form of forward() for streams of batches (hn_model_forward_async): the encoder of this batch
+        overlaps the bi-LSTM of the previous one on internal streams.  Returns (bon, cor) like forward(); in the order
+        of the current CUDA stream they are complete after the NEXT forward_pipelined() call or after flush().
+        Values are bit-identical to forward()."""
+        x, B, C, h, bon, cor, stream = self._forward_prologue(x)
+        _lib.check(_lib.lib().hn_model_forward_async(h['ptr'], x.data_ptr(), B, C, bon.data_ptr(), cor.data_ptr(), stream),
+                   'hn_model_forward_async')
+        # the caching allocator must not hand these buffers to another stream-ordered user before the internal
+        # streams are done with them: keep them referenced until the next call / flush
+        h['inflight'] = (h.get('inflight', ()) + ((x, bon, cor),))[-2:]
         return bon, cor
+
+    def flush(self):
+        """Make the current CUDA stream wait for every forward_pipelined() issued so far."""
+        for key, h in self._handles.items():
+            stream = torch.cuda.current_stream(torch.device('cuda', key)).cuda_stream
+            _lib.check(_lib.lib().hn_model_flush(h['ptr'], stream), 'hn_model_flush')
 
     def forward_host(self, x_host, device=0):
         """End-to-end call on HOST arrays through the C ABI (H2D + forward + D2H inside the

@@ -27,6 +27,9 @@ typedef struct hn_model hn_model;
 const char* hn_last_error(void);
 /* ABI version (bumped on any signature change). */
 int hn_abi_version(void);
+/* Digest of the sources this binary was built from (horizonnet_b200/build.py embeds it; the Python binding
+ * refuses to run a binary whose digest differs from the checked-out sources). */
+const char* hn_build_digest(void);
 /* Number of kernels this library has launched in this process (bench.py "gpu_launches"). */
 long long hn_kernel_launches(void);
 
@@ -58,6 +61,18 @@ int hn_model_finalize(hn_model* m);
 int hn_model_forward(hn_model* m, const float* x_nchw_dev, int batch, int in_channels,
                      float* bon_dev, float* cor_dev, void* stream);
 
+/* Throughput form of hn_model_forward for streams of batches.  The forward is split over two internal streams:
+ * the encoder + height reduction of call i+1 (all 148 SMs, tensor-core bound) run while the bi-LSTM recurrence + head
+ * of call i (16-CTA clusters on 64 SMs, latency-bound: 512 dependent steps) are still in flight.  Ordering contract
+ * on `stream`: x must be ready in stream order at the call; x may be reused by work enqueued on `stream` after the
+ * call returns; bon/cor of call i are complete for work enqueued on `stream` after call i+1 returns, or after
+ * hn_model_flush(m, stream).  Results are bit-identical to hn_model_forward.  Keep bon/cor of consecutive calls in
+ * distinct buffers. */
+int hn_model_forward_async(hn_model* m, const float* x_nchw_dev, int batch, int in_channels,
+                           float* bon_dev, float* cor_dev, void* stream);
+/* Makes `stream` wait for every forward enqueued so far by hn_model_forward_async. */
+int hn_model_flush(hn_model* m, void* stream);
+
 /* Same call with HOST buffers: H2D of x, forward, D2H of bon/cor, synchronous.  This is what
  * inference.py:78-79 (`net(x.to(device))` + `.cpu()`) amounts to. */
 int hn_model_forward_host(hn_model* m, const float* x_nchw_host, int batch, int in_channels,
@@ -65,10 +80,11 @@ int hn_model_forward_host(hn_model* m, const float* x_nchw_host, int batch, int 
 
 /* Pipelined form of the host call for streams of batches: hn_model_submit_host enqueues the H2D
  * copy of a batch (pinned memory recommended) on an internal copy stream into one of two input
- * slots and returns; hn_model_collect_host runs the forward of the OLDEST submitted batch on an
- * internal compute stream, copies bon/cor back and synchronises.  Calling submit(i+1) before
- * collect(i) overlaps the upload of the next batch with the forward of the current one
- * (at most 2 batches in flight).  Results are identical to hn_model_forward_host. */
+ * slots, enqueues its forward behind it (two-stream schedule of hn_model_forward_async) and returns;
+ * hn_model_collect_host waits for the OLDEST submitted batch, copies bon/cor back and synchronises
+ * (a device-side failure of that batch is reported here).  Calling submit(i+1) before collect(i)
+ * overlaps the upload and the encoder of the next batch with the forward / recurrence of the current
+ * one (at most 2 batches in flight).  Results are identical to hn_model_forward_host. */
 int hn_model_submit_host(hn_model* m, const float* x_nchw_host, int batch, int in_channels);
 int hn_model_collect_host(hn_model* m, float* bon_host, float* cor_host);
 

@@ -82,10 +82,17 @@ def stretch_corners(corners, h, w, kx, ky):
     return np.stack([(u / (2 * np.pi) + 0.5) * w - 0.5, (v / np.pi + 0.5) * h - 0.5], axis=-1)
 
 
-def pano_stretch(img, corners, kx, ky, order=1):
-    """Same signature and return convention as reference panostretch.py:81."""
+def pano_stretch(img, corners, kx, ky, order=1, use_scipy=False):
+    """Same signature and return convention as reference panostretch.py:81.  ``use_scipy=True`` samples with the real
+    ``scipy.ndimage.map_coordinates`` (the third-party routine the reference calls at :99-102) instead of the numpy
+    restatement above: that is the reference's actual CPU cost, used by bench.py's CPU baseline."""
     h, w = img.shape[:2]
     refy, refx = stretch_coords(h, w, kx, ky)
+    if use_scipy:
+        from scipy.ndimage import map_coordinates
+        out = np.stack([map_coordinates(img[..., i], [refy, refx], order=order, mode='wrap')
+                        for i in range(img.shape[-1])], axis=-1)
+        return out, stretch_corners(corners, h, w, kx, ky)
     out = np.stack([map_coordinates_wrap(img[..., i], refy, refx, order)
                     for i in range(img.shape[-1])], axis=-1)
     return out, stretch_corners(corners, h, w, kx, ky)

@@ -49,6 +49,39 @@ def test_checkpoint_layout_round_trip():
         assert torch.equal(v, sd[k]), k
 
 
+def test_checkpoint_round_trip_through_the_real_reference_utils(tmp_path):
+    """With /root/reference present (build container only): the reference's OWN save_model / load_trained_model
+    (misc/utils.py:49-65) applied to our class, unmodified."""
+    ref = '/root/reference'
+    if not os.path.isdir(ref):
+        pytest.skip('reference checkout not present on this box')
+    import importlib.util
+    import types
+    spec = importlib.util.spec_from_file_location('_ref_utils', os.path.join(ref, 'misc', 'utils.py'))
+    utils = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(utils)
+    sd = synthetic_state_dict(4, 'random')
+    net = HorizonNet('resnet50', True)
+    net.load_state_dict(sd, strict=True)
+    path = str(tmp_path / 'ck.pth')
+    utils.save_model(net, path, types.SimpleNamespace(lr=1e-4))          # utils.py:49-58 (args is vars()'d)
+    net2 = utils.load_trained_model(HorizonNet, path)                      # utils.py:61-65 (strict load)
+    assert isinstance(net2, HorizonNet) and net2.backbone == 'resnet50' and net2.use_rnn is True
+    assert list(net2.state_dict().keys()) == list(sd.keys())
+    for k, v in net2.state_dict().items():
+        assert torch.equal(v, sd[k]), k
+
+
+def test_train_mode_forward_is_refused_not_silently_run_in_eval_mode():
+    """net.train() under torch.no_grad() must not run the eval graph (the reference would use batch
+    statistics and dropout there, train.py:52)."""
+    net = HorizonNet('resnet50', True).train()
+    with torch.no_grad(), pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 3, 512, 1024))
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 3, 512, 1024))
+
+
 def test_module_surface_used_by_reference_callers():
     net = HorizonNet('resnet50', True)
     blocks = net.feature_extractor.list_blocks()            # train.py:202-208
@@ -98,7 +131,7 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0'],
+    r = subprocess.run([sys.executable, os.path.join(root, 'bench.py'), '--impl', 'reference', '--steps', '1', '--warmup', '0', '--quick-cpu'],
                        capture_output=True, text=True, timeout=600, cwd=root)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
@@ -107,3 +140,6 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     assert d['impl'] == 'reference' and d['metric'] == 'panoramas/sec' and d['unit'] == 'panoramas/s'
     assert d['value'] > 0 and d['higher_is_better'] is True
     assert d['cpu_baseline']['kind'] == 'port' and d['e2e']['h2d_bytes_per_step'] == 0
+    # threads = CPUs this process may use, capped at physical cores and the cgroup quota (never os.cpu_count() blindly)
+    ht = d['cpu_baseline']['host_threads']
+    assert 1 <= d['cpu_baseline']['cores'] == ht['used'] <= ht['affinity']

@@ -180,6 +180,89 @@ def test_forward_matches_oracle_and_is_batch_invariant(tensor_cores):
     assert torch.equal(bon3[1:2], bon1) and torch.equal(cor3[1:2], cor1)
 
 
+def test_forward_bs32_rows_equal_bs1_bitwise_and_match_oracle():
+    """The BENCHMARKED configuration (BASELINE configs[1]: batch 32, tensor cores): tile selection at B=32 differs from
+    the small-batch tests (narrow tiles, whole-image row boxes, two column groups per LSTM cluster), so check it
+    directly: rows {0, 13, 31} of the batch-32 forward are bit-equal to their batch-1 forwards and within 1e-4 of the CPU
+    oracle."""
+    sd = synthetic_state_dict(0, 'random')           # the bench's weights
+    net = _net(sd, True)
+    x = synthetic_panoramas(32, seed=1000)           # the bench's first batch
+    with torch.no_grad():
+        bon32, cor32 = net(x.to(DEV))
+    net.check()
+    assert torch.isfinite(bon32).all() and torch.isfinite(cor32).all()
+    for r in (0, 13, 31):
+        with torch.no_grad():
+            b1, c1 = net(x[r:r + 1].to(DEV))
+            rb, rc = horizonnet_ref.forward(sd, x[r:r + 1])
+        assert torch.equal(bon32[r:r + 1], b1) and torch.equal(cor32[r:r + 1], c1), r
+        assert (b1.cpu() - rb).abs().max().item() < 1e-4, r
+        assert (c1.cpu() - rc).abs().max().item() < 1e-4, r
+
+
+def test_forward_pipelined_is_bitwise_equal_to_forward():
+    """hn_model_forward_async (encoder of batch i+1 overlapping the bi-LSTM of batch i on internal streams) must give
+    exactly the plain forward's results, for a stream of batches of different sizes, mixed with plain calls."""
+    sd = synthetic_state_dict(3, 'random')
+    net = _net(sd, True)
+    xs = [synthetic_panoramas(b, seed=50 + i).to(DEV) for i, b in enumerate((2, 3, 1, 2))]
+    with torch.no_grad():
+        ref = [net(x) for x in xs]
+        outs = [net.forward_pipelined(x) for x in xs]
+        net.flush()
+        torch.cuda.synchronize()
+        for (rb, rc), (ob, oc) in zip(ref, outs):
+            assert torch.equal(rb, ob) and torch.equal(rc, oc)
+        # plain forward right after pipelined calls (joins the internal streams), then pipelined again
+        o1 = net.forward_pipelined(xs[0])
+        p2 = net(xs[1])
+        o3 = net.forward_pipelined(xs[2])
+        net.flush()
+        torch.cuda.synchronize()
+    net.check()
+    assert torch.equal(o1[0], ref[0][0]) and torch.equal(p2[0], ref[1][0]) and torch.equal(o3[1], ref[2][1])
+
+
+def test_nccl_gather_of_real_forward_outputs_world1():
+    """SURVEY 8d config 4 on NCCL: gather_outputs (all_gather_into_tensor into preallocated buffers) returns, bit for
+    bit, what the local forward produced.  One rank (the -m gpu box has one GPU); bench.py --gpus N repeats the check
+    across N ranks (config.selfcheck) and the gloo world-2 tests cover the multi-rank ordering."""
+    import torch.distributed as dist
+    from horizonnet_b200.parallel import gather_outputs
+    if dist.is_initialized():
+        pytest.skip('a process group already exists in this process')
+    os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+    os.environ.setdefault('MASTER_PORT', '29533')
+    dist.init_process_group('nccl', rank=0, world_size=1, device_id=torch.device(DEV))
+    try:
+        sd = synthetic_state_dict(1, 'random')
+        net = _net(sd, True)
+        x = synthetic_panoramas(2, seed=61).to(DEV)
+        with torch.no_grad():
+            bon, cor = net(x)
+            gb, gc = gather_outputs(bon, cor)
+            pb, pc = net.forward_pipelined(x)
+            net.flush()
+            hb, hc = gather_outputs(pb, pc)
+        torch.cuda.synchronize()
+        assert torch.equal(gb, bon) and torch.equal(gc, cor)
+        assert torch.equal(hb, bon) and torch.equal(hc, cor)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_forward_on_does_not_switch_the_current_device():
+    """the C entry points restore the caller's current device."""
+    import ctypes
+    sd = synthetic_state_dict(2, 'identity')
+    net = _net(sd, True)
+    with torch.no_grad():
+        net(synthetic_panoramas(1, seed=2).to(DEV))
+    assert torch.cuda.current_device() == 0
+    assert _lib.lib().hn_build_digest().decode() == __import__('horizonnet_b200.build', fromlist=['x']).source_digest()
+
+
 def test_tensor_core_stem_vs_oracle_and_fp32_stem():
     """stem_tc_kernel (7x7 s2 conv as an implicit GEMM over packed pixel pairs) against the oracle's stem in fp64
     and against the exact fp32 CUDA-core stem_kernel it replaces on the tensor-core path."""

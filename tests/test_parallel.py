@@ -37,6 +37,27 @@ def test_gather_of_shards_equals_full_batch_world2():
     mp.spawn(_worker, args=(2, _free_port(), 8), nprocs=2, join=True)
 
 
+def _worker_uneven(rank, world, port, total):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        g = torch.Generator().manual_seed(321)
+        bon_full = torch.randn(total, 2, 1024, generator=g)
+        cor_full = torch.randn(total, 1, 1024, generator=g)
+        lo, hi = shard_bounds(total, rank, world)
+        for _ in range(3):        # the rotating result buffers must not alias a result still in use
+            bon_all, cor_all = gather_outputs(bon_full[lo:hi].clone(), cor_full[lo:hi].clone(), total=total)
+            assert torch.equal(bon_all, bon_full) and torch.equal(cor_all, cor_full)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gather_of_uneven_shards_world2():
+    """total % world != 0: shards are padded for the collective and trimmed after."""
+    mp.spawn(_worker_uneven, args=(2, _free_port(), 7), nprocs=2, join=True)
+
+
 def test_shard_bounds_cover_everything_once():
     for total in (0, 1, 7, 32, 256):
         for world in (1, 2, 3, 8):
