@@ -38,6 +38,10 @@ int tta_merge(const float* bon, const float* cor, int V, const int* modes_dev, c
               float* y_cor, cudaStream_t st);
 int pano_stretch_device(const float* img, float* out, int n, int H, int W, int C, const double* kx_dev,
                         const double* ky_dev, double* scratch, int order, cudaStream_t st);
+int augment_device(const unsigned char* img, float* out, int n, int H, int W, const double* kx_dev, const double* ky_dev,
+                   const int* params_dev, double* scratch, cudaStream_t st);
+int rotate_panorama_device(const void* img, int in_f64, double* out, int n, int H, int W, int C, const double* rinv,
+                           cudaStream_t st);
 
 namespace {
 
@@ -893,6 +897,56 @@ int hn_pano_stretch_host(const float* img, float* out, int n, int h, int w, int 
     cudaFree(d_in);
     cudaFree(d_out);
     return rc;
+}
+
+// ---- training augmentation, image path (reference dataset.py:53, 69-105, 124) ----------------------
+int hn_augment(const unsigned char* img, float* out, int n, int h, int w, const double* kx, const double* ky,
+               const int* flip, const int* dx, const float* gamma, void* stream) {
+    HN_CHECK(n >= 0 && h >= 1 && w >= 1, "hn_augment: bad geometry");
+    if (n == 0) return 0;
+    HN_CHECK(img && out, "hn_augment: NULL argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("hn_augment: no CUDA device -- libhorizonnet_b200 has no CPU path");
+    std::vector<double> k((size_t)2 * n, 1.0);
+    std::vector<int> prm((size_t)4 * n, 0);
+    for (int i = 0; i < n; ++i) {
+        const bool stretch = kx && ky && kx[i] > 0 && ky[i] > 0;
+        if (kx && ky) HN_CHECK((kx[i] > 0) == (ky[i] > 0), "hn_augment: kx and ky must both be positive, or both <= 0 (no stretch)");
+        if (stretch) { k[i] = kx[i]; k[(size_t)n + i] = ky[i]; }
+        const int d = dx ? dx[i] : 0;
+        HN_CHECK(d >= 0 && d < w, "hn_augment: dx must be in [0, W) (dataset.py:95 np.random.randint(W))");
+        const float g = gamma ? gamma[i] : 0.f;
+        prm[(size_t)4 * i + 0] = (flip && flip[i]) ? 1 : 0;
+        prm[(size_t)4 * i + 1] = d;
+        std::memcpy(&prm[(size_t)4 * i + 2], &g, sizeof(float));
+        prm[(size_t)4 * i + 3] = stretch ? 1 : 0;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    double* scratch = nullptr;
+    const size_t nd = (size_t)2 * n + (size_t)4 * n * w + h + (size_t)2 * n + 2;     // kx, ky, tables, params (4 ints = 2 doubles)
+    HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&scratch), nd * sizeof(double), st));
+    double* tables = scratch + 2 * (size_t)n;
+    int* prm_dev = reinterpret_cast<int*>(tables + (size_t)4 * n * w + h);
+    int rc = 0;
+    if (cudaMemcpyAsync(scratch, k.data(), (size_t)2 * n * sizeof(double), cudaMemcpyHostToDevice, st) != cudaSuccess ||
+        cudaMemcpyAsync(prm_dev, prm.data(), (size_t)4 * n * sizeof(int), cudaMemcpyHostToDevice, st) != cudaSuccess)
+        rc = fail("hn_augment: parameter upload failed");
+    // the host vectors are pageable: the runtime has staged them when cudaMemcpyAsync returns
+    if (!rc) rc = augment_device(img, out, n, h, w, scratch, scratch + n, prm_dev, tables, st);
+    cudaFreeAsync(scratch, st);
+    return rc;
+}
+
+// ---- misc.pano_lsd_align.rotatePanorama (reference misc/pano_lsd_align.py:125-171) -------------------
+int hn_rotate_panorama(const void* img, int in_is_f64, double* out, int n, int h, int w, int c, const double* rinv,
+                       void* stream) {
+    if (n == 0) return 0;
+    HN_CHECK(img && out && rinv, "hn_rotate_panorama: NULL argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail("hn_rotate_panorama: no CUDA device -- libhorizonnet_b200 has no CPU path");
+    return rotate_panorama_device(img, in_is_f64, out, n, h, w, c, rinv, (cudaStream_t)stream);
 }
 
 // ---- kernel-level entry points -----------------------------------------------------------------

@@ -69,22 +69,39 @@ __global__ void stretch_tables_kernel(const double* __restrict__ kx, const doubl
 
 struct RowTaps {       // vertical taps of one output row: resolved once, shared by both mirrored columns
     int r0, r1;        // element offsets y0*W*C, y1*W*C
-    int rn;            // nearest row offset (order 0)
     double ty;
 };
+
+// floor() of a coordinate in [0, 2^31) without the conversion unit: adding 1.5 * 2^52 leaves round-to-nearest(c) in
+// the low mantissa word; one compare turns round-to-nearest into floor.  (ncu, round 1: F2F/F2I/I2F/FRND on the XU pipe
+// were the top stall reason of this kernel -- 23 XU instructions per pixel.)
+constexpr double MAGIC_RN = 6755399441055744.0;
+__device__ __forceinline__ int floor_nonneg(double c, double& fl) {
+    const double s = c + MAGIC_RN;
+    int i = __double2loint(s);
+    fl = s - MAGIC_RN;
+    if (fl > c) { i -= 1; fl -= 1.0; }
+    return i;
+}
 
 template <int C>
 __device__ __forceinline__ RowTaps resolve_row(double cy, int H, int W) {
     cy = legacy_wrap(cy, H);
-    const int y0 = (int)floor(cy);
+    double fl;
+    const int y0 = floor_nonneg(cy, fl);
     RowTaps t;
-    t.ty = cy - (double)y0;
+    t.ty = cy - fl;
     // index y0+1 == H only happens with weight exactly 0; fold it like scipy does (period n-1)
     const int y1 = (y0 + 1 > H - 1) ? (H > 1 ? y0 + 1 - (H - 1) : 0) : y0 + 1;
     t.r0 = y0 * W * C;
     t.r1 = y1 * W * C;
-    t.rn = min((int)floor(cy + 0.5), H - 1) * W * C;
     return t;
+}
+
+template <int C>
+__device__ __forceinline__ int nearest_row(double cy, int H, int W) {
+    double fl;
+    return min(floor_nonneg(legacy_wrap(cy, H) + 0.5, fl), H - 1) * W * C;
 }
 
 // grid: (ceil(ceil(W/2)/128), ceil(H/2), n); thread = column pair (x, W-1-x) x row pair (y, H-1-y).
@@ -113,10 +130,11 @@ __global__ void __launch_bounds__(128) stretch_kernel(const float* __restrict__ 
     const int ocol[2] = {x * C, xm * C};
     const int nside = (xm == x) ? 1 : 2, nvert = (ym == y) ? 1 : 2;
     if (order == 0) {
+        const int rn[2] = {nearest_row<C>(ry, H, W), nearest_row<C>((double)(H - 1) - ry, H, W)};
         for (int sd = 0; sd < nside; ++sd)
             for (int vt = 0; vt < nvert; ++vt)
 #pragma unroll
-                for (int c = 0; c < C; ++c) dst[orow[vt] + ocol[sd] + c] = __ldg(src + rt[vt].rn + e[sd].xn * C + c);
+                for (int c = 0; c < C; ++c) dst[orow[vt] + ocol[sd] + c] = __ldg(src + rn[vt] + e[sd].xn * C + c);
         return;
     }
     float tap[2][2][4][C];                       // [side][vert][tap][channel]
@@ -143,17 +161,112 @@ __global__ void __launch_bounds__(128) stretch_kernel(const float* __restrict__ 
         for (int vt = 0; vt < 2; ++vt) {
             if (vt >= nvert) break;
             const double ty = rt[vt].ty, tx = e[sd].tx;
-            const double w00 = __dmul_rn(1.0 - ty, 1.0 - tx), w01 = __dmul_rn(1.0 - ty, tx);
-            const double w10 = __dmul_rn(ty, 1.0 - tx), w11 = __dmul_rn(ty, tx);
+            const double uy = 1.0 - ty, ux = 1.0 - tx;
+            const double w00 = uy * ux, w01 = uy * tx, w10 = ty * ux, w11 = ty * tx;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
-                // same accumulation order as scipy (no FMA contraction): (y0,x0) (y0,x1) (y1,x0) (y1,x1)
-                double acc = __dmul_rn(w00, (double)tap[sd][vt][0][c]);
-                acc = __dadd_rn(acc, __dmul_rn(w01, (double)tap[sd][vt][1][c]));
-                acc = __dadd_rn(acc, __dmul_rn(w10, (double)tap[sd][vt][2][c]));
-                acc = __dadd_rn(acc, __dmul_rn(w11, (double)tap[sd][vt][3][c]));
+                // scipy accumulates (y0,x0) (y0,x1) (y1,x0) (y1,x1) in double with separately rounded products; the fused
+                // chain differs from that by < 2^-52 relative, i.e. after the cast to fp32 in at most a last-bit rounding
+                // flip (the contract is 1 fp32 ulp = 1.2e-7), and costs 4 instead of 7 fp64 instructions per channel
+                double acc = w00 * (double)tap[sd][vt][0][c];
+                acc = fma(w01, (double)tap[sd][vt][1][c], acc);
+                acc = fma(w10, (double)tap[sd][vt][2][c], acc);
+                acc = fma(w11, (double)tap[sd][vt][3][c], acc);
                 dst[orow[vt] + ocol[sd] + c] = (float)acc;
             }
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// augment_kernel ("next" row f3): the image path of the reference's training augmentation, reference
+// dataset.py:53 + :69-105 + :124, in ONE gather pass from the uint8 HWC panorama to the float32 CHW network input:
+//     img = uint8 / 255 (float32)  ->  pano_stretch(kx, ky)  ->  flip  ->  roll(dx)  ->  img ** p  ->  CHW
+// The reference materialises a float32 HWC image after every step in a DataLoader worker (~70 ms per image on one CPU
+// core, dominated by pano_stretch).  Here output pixel (y, xo) is traced back through roll and flip to column xs of
+// the stretched image, sampled bilinearly from the uint8 source (fp64 coordinates and blend, scipy legacy 'wrap'; the
+// taps are read through a 256-entry table of double(float32(v) / 255f), so there is no per-tap conversion), raised to
+// the power p in fp32 and written to the three channel planes.  Rows y and H-1-y share the column entry and the atan.
+// Algorithmic bytes per panorama: H*W*3 (uint8 in) + H*W*3*4 (float32 out).
+struct AugParams {
+    int flip;        // dataset.py:88-91
+    int dx;          // dataset.py:95-98, 0 <= dx < W
+    float gamma;     // dataset.py:102-105 exponent p; <= 0: no gamma
+    int stretch;     // 0: no stretch (self.stretch False): kx, ky are not used
+};
+
+__global__ void __launch_bounds__(128) augment_kernel(const unsigned char* __restrict__ img, float* __restrict__ out,
+                                                      const ColEntry* __restrict__ cols,
+                                                      const double* __restrict__ tanv,
+                                                      const AugParams* __restrict__ params, int H, int W) {
+    __shared__ double lut[256];
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (double)__fdiv_rn((float)i, 255.f);   // dataset.py:53
+    __syncthreads();
+    const int xo = blockIdx.x * 128 + threadIdx.x;
+    const int y = blockIdx.y;
+    const int n = blockIdx.z;
+    if (xo >= W) return;
+    const AugParams pr = params[n];
+    // un-roll (np.roll(img, dx, axis=1): out[x] = in[(x - dx) mod W]), then un-flip (np.flip: in[j] = st[W-1-j])
+    int xs = xo - pr.dx;
+    if (xs < 0) xs += W;
+    if (pr.flip) xs = W - 1 - xs;
+    const size_t plane = (size_t)H * W;
+    const unsigned char* src = img + (size_t)n * plane * 3;
+    float* dst = out + (size_t)n * plane * 3;
+    const int ym = H - 1 - y;
+    const int nvert = (ym == y) ? 1 : 2;
+    float val[2][3];
+    if (!pr.stretch) {
+#pragma unroll
+        for (int vt = 0; vt < 2; ++vt) {
+            const unsigned char* p = src + ((size_t)(vt ? ym : y) * W + xs) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) val[vt][c] = (float)lut[p[c]];
+        }
+    } else {
+        const ColEntry e = cols[(size_t)n * W + xs];
+        const double v0 = atan(tanv[y] * e.g);                                    // panostretch.py:93
+        const double ry = (v0 / PI_D + 0.5) * (double)H - 0.5;                     // :96
+        const RowTaps rt[2] = {resolve_row<3>(ry, H, W), resolve_row<3>((double)(H - 1) - ry, H, W)};
+        unsigned char tap[2][4][3];
+#pragma unroll
+        for (int vt = 0; vt < 2; ++vt) {
+            const unsigned char* p00 = src + rt[vt].r0 + e.x0 * 3;
+            const unsigned char* p01 = src + rt[vt].r0 + e.x1 * 3;
+            const unsigned char* p10 = src + rt[vt].r1 + e.x0 * 3;
+            const unsigned char* p11 = src + rt[vt].r1 + e.x1 * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                tap[vt][0][c] = __ldg(p00 + c); tap[vt][1][c] = __ldg(p01 + c);
+                tap[vt][2][c] = __ldg(p10 + c); tap[vt][3][c] = __ldg(p11 + c);
+            }
+        }
+#pragma unroll
+        for (int vt = 0; vt < 2; ++vt) {
+            const double ty = rt[vt].ty, tx = e.tx;
+            const double uy = 1.0 - ty, ux = 1.0 - tx;
+            const double w00 = uy * ux, w01 = uy * tx, w10 = ty * ux, w11 = ty * tx;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                double acc = w00 * lut[tap[vt][0][c]];
+                acc = fma(w01, lut[tap[vt][1][c]], acc);
+                acc = fma(w10, lut[tap[vt][2][c]], acc);
+                acc = fma(w11, lut[tap[vt][3][c]], acc);
+                val[vt][c] = (float)acc;                                          // map_coordinates output dtype = float32
+            }
+        }
+    }
+#pragma unroll
+    for (int vt = 0; vt < 2; ++vt) {
+        if (vt >= nvert) break;
+        const int yy = vt ? ym : y;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            float v = val[vt][c];
+            if (pr.gamma > 0.f) v = powf(v, pr.gamma);                             // dataset.py:105 (float32 ** float32)
+            dst[(size_t)c * plane + (size_t)yy * W + xo] = v;                      // dataset.py:124 HWC -> CHW
         }
     }
 }
@@ -183,6 +296,26 @@ int pano_stretch_device(const float* img, float* out, int n, int H, int W, int C
         case 3: stretch_kernel<3><<<g, 128, 0, st>>>(img, out, cols, tanv, H, W, order); break;
         default: stretch_kernel<4><<<g, 128, 0, st>>>(img, out, cols, tanv, H, W, order); break;
     }
+    HN_LAUNCH_OK();
+    return 0;
+}
+
+// img: n uint8 images [H][W][3]; out: n float32 images [3][H][W]; kx/ky: n doubles on the device (entries of images without
+// stretch must still be positive); params_dev: n AugParams {flip, dx, gamma, stretch}; scratch as for pano_stretch_device.
+int augment_device(const unsigned char* img, float* out, int n, int H, int W, const double* kx_dev, const double* ky_dev,
+                   const int* params_dev, double* scratch, cudaStream_t st) {
+    HN_CHECK(n >= 0 && H >= 1 && W >= 1, "augment: bad geometry");
+    if (n == 0) return 0;
+    HN_CHECK((long long)H * W * 3 < (1ll << 31), "augment: image too large");
+    HN_CHECK(n <= 65535 && H <= 2 * 65535, "augment: at most 65535 images per call");
+    static_assert(sizeof(AugParams) == 16, "AugParams layout");
+    ColEntry* cols = reinterpret_cast<ColEntry*>(scratch);
+    double* tanv = scratch + 4 * (size_t)n * W;
+    const int tot = (n * W > H) ? n * W : H;
+    stretch_tables_kernel<<<(tot + 255) / 256, 256, 0, st>>>(kx_dev, ky_dev, cols, tanv, n, H, W);
+    HN_LAUNCH_OK();
+    dim3 g((W + 127) / 128, (H + 1) / 2, n);
+    augment_kernel<<<g, 128, 0, st>>>(img, out, cols, tanv, reinterpret_cast<const AugParams*>(params_dev), H, W);
     HN_LAUNCH_OK();
     return 0;
 }

@@ -135,6 +135,26 @@ int hn_pano_stretch(const float* img_dev, float* out_dev, int n, int h, int w, i
 int hn_pano_stretch_host(const float* img_host, float* out_host, int n, int h, int w, int c,
                          const double* kx_host, const double* ky_host, int order);
 
+/* ---- dataset.PanoCorBonDataset.__getitem__, image path (reference dataset.py:53, 69-105, 124) ------
+ *
+ * One fused gather pass per image:  uint8 HWC / 255 -> pano_stretch(kx, ky) -> flip -> roll(dx) -> ** gamma -> CHW:
+ * n uint8 images [h][w][3] on the device -> n float32 images [3][h][w] on the device (the network input layout,
+ * dataset.py:124).  Host arrays of n entries: kx/ky (dataset.py:71-82; NULL or <= 0: no stretch for that image),
+ * flip (dataset.py:88-91; NULL: none), dx (np.roll shift, dataset.py:95-98, 0 <= dx < w; NULL: 0),
+ * gamma (exponent p of dataset.py:102-105; NULL or <= 0: none).  The random draws and the corner / boundary label
+ * bookkeeping stay with the caller (horizonnet_b200/dataset.py mirrors them). */
+int hn_augment(const unsigned char* img_u8_dev, float* out_chw_dev, int n, int h, int w,
+               const double* kx_host, const double* ky_host, const int* flip_host, const int* dx_host,
+               const float* gamma_host, void* stream);
+
+/* ---- misc.pano_lsd_align.rotatePanorama (reference misc/pano_lsd_align.py:125-171, warpImageFast :101-122) ----
+ *
+ * n images [h][w][c] on the device, float32 (in_is_f64 = 0) or float64 (1) -> n float64 images [h][w][c] rotated by
+ * R; rinv_host = 9 doubles, row-major inverse of the reference's R (= vp.T when called with a vanishing-point
+ * matrix, pano_lsd_align.py:143).  w must be even (the reference's padding rule, :160-163). */
+int hn_rotate_panorama(const void* img_dev, int in_is_f64, double* out_dev, int n, int h, int w, int c,
+                       const double* rinv_host, void* stream);
+
 /* ---- kernel-level entry points (unit tests; halo-NHWC activations) ------------ */
 
 /* One convolution + folded BN/bias + optional residual + optional ReLU.

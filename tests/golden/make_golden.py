@@ -3,7 +3,7 @@
 Run in the build container only (the GPU box has no /root/reference):
     python tests/golden/make_golden.py
 Outputs (committed): tests/golden/forward_identity.npz, forward_randombn.npz,
-panostretch_small.npz, panostretch_rows.npz.  The two shims are the ones SURVEY.md section 8c
+panostretch_small.npz, panostretch_rows.npz, tta_randombn.npz, augment.npz (row f3), rotate.npz (row f4).  The two shims are the ones SURVEY.md section 8c
 describes: torchvision.resnet50 is forced to weights=None (no network), nothing else is patched.
 Weights/inputs come from horizonnet_b200.weights (numpy RandomState => reproducible on any box).
 """
@@ -134,7 +134,107 @@ def golden_tta():
     print('tta golden', y_bon_.min(), y_bon_.max(), float(y_cor_.max()))
 
 
+def synthetic_u8(h, w, seed):
+    """Smooth-ish synthetic uint8 RGB panorama (reproducible on any box)."""
+    return np.random.RandomState(seed).randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+
+
+def golden_augment():
+    """'next' row f3: the image tensor of the REAL dataset.PanoCorBonDataset.__getitem__ (dataset.py:48-134) with
+    stretch + flip + rotate + gamma on, for a synthetic PNG and the README's 12-corner label.  np.random is seeded and
+    the draws are replayed (same order as dataset.py:71-81, 88, 95, 102-104) to recover (kx, ky, flip, dx, p)."""
+    import tempfile
+    import types
+    from PIL import Image
+    for name in ('shapely', 'shapely.geometry'):
+        sys.modules.setdefault(name, types.ModuleType(name))
+
+    class _LineString:                               # occlusion labels only (dataset.py:182-195); not on the image path
+        def __init__(self, pts): pass
+        def intersects(self, other): return False
+    sys.modules['shapely.geometry'].LineString = _LineString
+    sys.modules['shapely.geometry'].Polygon = object
+    import dataset as ref_ds                         # reference dataset.py
+    _cdist = ref_ds.cdist                            # scipy >= 1.9 rejects p= for the default metric; label path only
+    ref_ds.cdist = lambda a, b, p=1: _cdist(a, b, 'minkowski', p=p)
+    out = {}
+    sel = np.array([0, 1, 7, 100, 255, 256, 300, 411, 510, 511])
+    out['rows'] = sel
+    cases = []
+    for case, (h, w, seed) in enumerate([(64, 128, 11), (512, 1024, 12), (512, 1024, 13), (512, 1024, 14)]):
+        with tempfile.TemporaryDirectory() as root:
+            os.makedirs(os.path.join(root, 'img')); os.makedirs(os.path.join(root, 'label_cor'))
+            img = synthetic_u8(h, w, 500 + seed)
+            Image.fromarray(img).save(os.path.join(root, 'img', 'pano.png'))
+            cor = CORNERS * np.array([w / 1024, h / 512], np.float32)
+            with open(os.path.join(root, 'label_cor', 'pano.txt'), 'w') as f:
+                for x, y in cor:
+                    f.write('%d %d\n' % (round(float(x)), round(float(y))))
+            ds = ref_ds.PanoCorBonDataset(root, flip=True, rotate=True, gamma=True, stretch=True, return_cor=True)
+            np.random.seed(seed)
+            x, bon, y_cor, cor_out = ds[0]
+            # replay the draws
+            np.random.seed(seed)
+            with open(os.path.join(root, 'label_cor', 'pano.txt')) as f:
+                c0 = np.array([l.strip().split() for l in f if l.strip()], np.float32)
+            c0 = np.roll(c0[:, :2], -2 * np.argmin(c0[::2, 0]), 0)
+            xmin, ymin, xmax, ymax = ref_ds.cor2xybound(c0)
+            kx = np.random.uniform(1.0, 2.0); ky = np.random.uniform(1.0, 2.0)
+            kx = max(1 / kx, min(0.5 / xmin, 1.0)) if np.random.randint(2) == 0 else min(kx, max(10.0 / xmax, 1.0))
+            ky = max(1 / ky, min(0.5 / ymin, 1.0)) if np.random.randint(2) == 0 else min(ky, max(10.0 / ymax, 1.0))
+            flip = np.random.randint(2) == 0
+            dx = np.random.randint(w)
+            p = np.random.uniform(1, 2)
+            if np.random.randint(2) == 0:
+                p = 1 / p
+        x = x.numpy()
+        out[f'c{case}_hw'] = np.array([h, w]); out[f'c{case}_img_seed'] = 500 + seed
+        out[f'c{case}_params'] = np.array([kx, ky, float(flip), float(dx), p], np.float64)
+        out[f'c{case}_cor_in'] = c0; out[f'c{case}_cor_out'] = np.asarray(cor_out, np.float64)
+        out[f'c{case}_sum'] = np.float64(x.astype(np.float64).sum()); out[f'c{case}_sq'] = np.float64((x.astype(np.float64) ** 2).sum())
+        out[f'c{case}_x'] = x if h < 512 else x[:, sel]
+        cases.append((h, w, kx, ky, flip, dx, p))
+    out['n_cases'] = len(cases)
+    np.savez_compressed(os.path.join(HERE, 'augment.npz'), **out)
+    print('augment golden', cases)
+
+
+def golden_rotate():
+    """'next' row f4: the REAL misc/pano_lsd_align.rotatePanorama (only `pylsd` is stubbed: not installed, LSD line
+    detection is not on this path)."""
+    import types
+    m = types.ModuleType('pylsd'); m.lsd = lambda *a, **k: None
+    sys.modules.setdefault('pylsd', m)
+    from misc import pano_lsd_align as ref_pl
+    out = {}
+    rs = np.random.RandomState(21)
+    q, _ = np.linalg.qr(rs.randn(3, 3))
+    small = rs.random_sample((32, 64, 3))
+    out['small_img'] = small; out['small_R'] = q
+    out['small_out'] = ref_pl.rotatePanorama(small, R=q)
+    out['small_out_vp'] = ref_pl.rotatePanorama(small, q[2::-1])             # preprocess.py:65 call form
+    img = np.random.RandomState(22).random_sample((512, 1024, 3)).astype(np.float32)
+    sel = np.array([0, 1, 2, 77, 255, 256, 400, 509, 510, 511])
+    out['rows'] = sel
+    # a small tilt (the typical vanishing-point alignment) and a large rotation
+    th = np.deg2rad(3.0)
+    r_small = np.array([[np.cos(th), 0, np.sin(th)], [0, 1, 0], [-np.sin(th), 0, np.cos(th)]]) @ \
+        np.array([[1, 0, 0], [0, np.cos(th / 2), -np.sin(th / 2)], [0, np.sin(th / 2), np.cos(th / 2)]])
+    for name, R in (('tilt', r_small), ('big', q)):
+        o = ref_pl.rotatePanorama(img, R=R)
+        out[f'{name}_R'] = R; out[f'{name}_rows'] = o[sel]
+        out[f'{name}_sum'] = np.float64(o.sum()); out[f'{name}_sq'] = np.float64((o ** 2).sum())
+    np.savez_compressed(os.path.join(HERE, 'rotate.npz'), **out)
+    print('rotate golden written')
+
+
 if __name__ == '__main__':
+    if len(sys.argv) > 1 and sys.argv[1] == 'next':        # only the fixtures of the "next" rows f3 / f4
+        golden_augment()
+        golden_rotate()
+        sys.exit(0)
+    golden_augment()
+    golden_rotate()
     golden_tta()
     golden_panostretch()
     golden_forward('identity', seed=0, bn='identity', batch=2)

@@ -143,3 +143,19 @@ def test_bench_reference_arm_prints_exactly_one_json_line():
     # threads = CPUs this process may use, capped at physical cores and the cgroup quota (never os.cpu_count() blindly)
     ht = d['cpu_baseline']['host_threads']
     assert 1 <= d['cpu_baseline']['cores'] == ht['used'] <= ht['affinity']
+
+
+def test_augmentation_draws_and_corner_bookkeeping_replay_the_reference(golden_dir):
+    """Host logic of row f3 (no GPU): draw_params consumes np.random exactly like dataset.py:69-105 (the golden stores
+    what the REAL dataset drew for these seeds) and augment_corners follows dataset.py:82, 91, 98."""
+    from horizonnet_b200 import augment
+    g = np.load(os.path.join(golden_dir, 'augment.npz'))
+    for c, seed in enumerate((11, 12, 13, 14)):
+        h, w = (int(v) for v in g[f'c{c}_hw'])
+        pr = augment.draw_params(g[f'c{c}_cor_in'], w, rng=np.random.RandomState(seed))
+        kx, ky, flip, dx, p = g[f'c{c}_params']
+        assert (pr['kx'], pr['ky'], float(pr['flip']), float(pr['dx']), pr['p']) == (kx, ky, flip, dx, p)
+        cor = augment.augment_corners(g[f'c{c}_cor_in'], h, w, pr['kx'], pr['ky'], pr['flip'], pr['dx'])
+        assert np.abs(cor - g[f'c{c}_cor_out']).max() < 1e-3
+    off = augment.draw_params(g['c0_cor_in'], 128, stretch=False, flip=False, rotate=False, gamma=False)
+    assert off == dict(kx=None, ky=None, flip=False, dx=0, p=None)

@@ -419,3 +419,76 @@ def test_pano_stretch_rejects_bad_arguments():
         pano_stretch(np.zeros((8, 16, 3), np.float32), np.zeros((1, 2)), -1.0, 1.0)
     empty = pano_stretch_batch(torch.zeros(0, 8, 16, 3, device=DEV), [], [])
     assert empty.shape == (0, 8, 16, 3)
+
+
+# ------------------------------------------------------------------------------- "next" row f3: fused augmentation
+def _synthetic_u8(h, w, seed):
+    return np.random.RandomState(seed).randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+
+
+def test_augment_matches_the_real_dataset_pipeline_golden(golden_dir):
+    """hn_augment (uint8 HWC -> stretch -> flip -> roll -> gamma -> float32 CHW in one pass) against the tensor the
+    REAL dataset.PanoCorBonDataset.__getitem__ produced (tests/golden/augment.npz).  Tolerance 3e-7: one fp32 ulp of the
+    bilinear result (1.2e-7, as for pano_stretch) carried through x**p plus CUDA powf vs numpy's float32 power (a few ulp)."""
+    from horizonnet_b200.augment import augment_batch
+    g = np.load(os.path.join(golden_dir, 'augment.npz'))
+    for c in range(int(g['n_cases'])):
+        h, w = (int(v) for v in g[f'c{c}_hw'])
+        kx, ky, flip, dx, p = (float(v) for v in g[f'c{c}_params'])
+        img = _synthetic_u8(h, w, int(g[f'c{c}_img_seed']))
+        x = augment_batch(img[None], [kx], [ky], [bool(flip)], [int(dx)], [p])[0].cpu().numpy()
+        assert x.shape == (3, h, w) and x.dtype == np.float32
+        got = x if h < 512 else x[:, g['rows']]
+        assert np.abs(got - g[f'c{c}_x']).max() <= 3e-7, (c, np.abs(got - g[f'c{c}_x']).max())
+        assert abs(x.astype(np.float64).sum() - float(g[f'c{c}_sum'])) < 0.05, c
+
+
+def test_augment_option_combinations_vs_oracle():
+    """Every on/off combination of the four augmentations (per image, in one batch) against oracle/augment_ref.py; without
+    gamma the result is the float32 bilinear value itself: 1.2e-7 like pano_stretch; identity = uint8 / 255 exactly."""
+    from horizonnet_b200.augment import augment_batch
+    from oracle import augment_ref
+    h, w = 48, 96
+    imgs = np.stack([_synthetic_u8(h, w, 70 + i) for i in range(16)])
+    rs = np.random.RandomState(9)
+    kx, ky, flip, dx, gam = [], [], [], [], []
+    for i in range(16):
+        st = bool(i & 1)
+        kx.append(float(rs.uniform(0.5, 2.0)) if st else None); ky.append(float(rs.uniform(0.5, 2.0)) if st else None)
+        flip.append(bool(i & 2)); dx.append(int(rs.randint(w)) if i & 4 else 0)
+        gam.append(float(rs.uniform(0.5, 2.0)) if i & 8 else None)
+    x = augment_batch(imgs, kx, ky, flip, dx, gam).cpu().numpy()
+    for i in range(16):
+        ref = augment_ref.augment_image(imgs[i], kx[i], ky[i], flip[i], dx[i], gam[i])
+        tol = 3e-7 if gam[i] is not None else 1.2e-7
+        assert np.abs(x[i] - ref).max() <= tol, (i, np.abs(x[i] - ref).max())
+    assert np.array_equal(x[0], (imgs[0].astype(np.float32) / np.float32(255.)).transpose(2, 0, 1))
+    with pytest.raises(RuntimeError):
+        augment_batch(imgs[:1], dx=[w])                       # dx out of range (np.random.randint(W) never yields W)
+    with pytest.raises(TypeError):
+        augment_batch(imgs[:1].astype(np.float32))
+
+
+# ------------------------------------------------------------------------------- "next" row f4: rotatePanorama
+def test_rotate_panorama_matches_the_real_reference_golden(golden_dir):
+    from horizonnet_b200.misc.pano_lsd_align import rotatePanorama, rotate_panorama_batch
+    from oracle import panorotate_ref
+    g = np.load(os.path.join(golden_dir, 'rotate.npz'))
+    out = rotatePanorama(g['small_img'], R=g['small_R'])
+    assert out.dtype == np.float64 and out.shape == g['small_out'].shape
+    assert np.abs(out - g['small_out']).max() < 1e-12
+    assert np.abs(rotatePanorama(g['small_img'], g['small_R'][2::-1]) - g['small_out_vp']).max() < 1e-12
+    img = np.random.RandomState(22).random_sample((512, 1024, 3)).astype(np.float32)
+    batch = torch.from_numpy(img).to(DEV).unsqueeze(0)
+    for name in ('tilt', 'big'):
+        o = rotate_panorama_batch(batch, R=g[f'{name}_R'])[0].cpu().numpy()
+        assert np.abs(o[g['rows']] - g[f'{name}_rows']).max() < 1e-12, name
+        assert abs(o.sum() - float(g[f'{name}_sum'])) < 1e-6 and abs((o ** 2).sum() - float(g[f'{name}_sq'])) < 1e-6, name
+    # identity rotation reproduces the image (the padding never contributes); odd sizes / 1 channel vs the oracle
+    ident = rotatePanorama(g['small_img'], R=np.eye(3))
+    assert np.abs(ident - g['small_img']).max() < 1e-12
+    img1 = np.random.RandomState(5).random_sample((17, 30, 1))
+    q, _ = np.linalg.qr(np.random.RandomState(6).randn(3, 3))
+    assert np.abs(rotatePanorama(img1, R=q) - panorotate_ref.rotate_panorama(img1, R=q)).max() < 1e-12
+    with pytest.raises(RuntimeError):
+        rotatePanorama(np.zeros((8, 15, 3)), R=np.eye(3))         # odd width: the reference's padding rule is undefined

@@ -104,3 +104,40 @@ def test_tta_oracle_matches_reference(golden_dir):
     assert np.abs(y_bon - g['y_bon']).max() < 5e-3          # pixel rows: 1e-5 rad * 512 / pi
     assert np.abs(y_cor - g['y_cor']).max() < 2e-5
     assert np.abs(g['cor_id'][0::2, 1] * 512 - y_bon[0]).max() < 5e-3
+
+
+# ------------------------------------------------------------------------------- "next" rows f3 / f4
+def _synthetic_u8(h, w, seed):
+    return np.random.RandomState(seed).randint(0, 256, size=(h, w, 3)).astype(np.uint8)
+
+
+def test_augment_oracle_matches_the_real_dataset_pipeline(golden_dir):
+    """oracle/augment_ref.py against the tensor the REAL dataset.PanoCorBonDataset.__getitem__ produced
+    (dataset.py:48-134, stretch + flip + rotate + gamma on).  1.2e-7 = one fp32 ulp below 1."""
+    from oracle import augment_ref
+    g = np.load(os.path.join(golden_dir, 'augment.npz'))
+    for c in range(int(g['n_cases'])):
+        h, w = (int(v) for v in g[f'c{c}_hw'])
+        kx, ky, flip, dx, p = (float(v) for v in g[f'c{c}_params'])
+        img = _synthetic_u8(h, w, int(g[f'c{c}_img_seed']))
+        x = augment_ref.augment_image(img, kx, ky, bool(flip), int(dx), p)
+        assert x.shape == (3, h, w) and x.dtype == np.float32
+        got = x if h < 512 else x[:, g['rows']]
+        assert np.abs(got - g[f'c{c}_x']).max() <= 1.2e-7, c
+        assert abs(x.astype(np.float64).sum() - float(g[f'c{c}_sum'])) < 0.05, c
+        cor = augment_ref.augment_corners(g[f'c{c}_cor_in'], h, w, kx, ky, bool(flip), int(dx))
+        assert np.abs(cor - g[f'c{c}_cor_out']).max() < 1e-3, c          # float32 bookkeeping in the reference
+
+
+def test_rotate_oracle_matches_the_real_rotatePanorama(golden_dir):
+    from oracle import panorotate_ref
+    g = np.load(os.path.join(golden_dir, 'rotate.npz'))
+    out = panorotate_ref.rotate_panorama(g['small_img'], R=g['small_R'])
+    assert out.dtype == np.float64 and np.abs(out - g['small_out']).max() < 1e-12
+    out = panorotate_ref.rotate_panorama(g['small_img'], g['small_R'][2::-1])
+    assert np.abs(out - g['small_out_vp']).max() < 1e-12
+    img = np.random.RandomState(22).random_sample((512, 1024, 3)).astype(np.float32)
+    for name in ('tilt', 'big'):
+        o = panorotate_ref.rotate_panorama(img, R=g[f'{name}_R'])
+        assert np.abs(o[g['rows']] - g[f'{name}_rows']).max() < 1e-12, name
+        assert abs(o.sum() - float(g[f'{name}_sum'])) < 1e-6, name
