@@ -1210,6 +1210,410 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ================================================================================================
+// bott_tc_kernel: conv2 (3x3, stride 1, 64 -> 64) + BN + ReLU  FUSED WITH  conv3 (1x1, 64 -> 256) + BN + identity + ReLU
+// of a layer1 bottleneck (torchvision Bottleneck.forward; reference model.py:78).
+//
+// Unfused, conv2 is bound by shared-memory operand reads (N = 64 tiles: 30 % tensor pipe, 16 % DRAM) and conv3 by HBM
+// (its 256-channel residual read + output write: 72 % DRAM, 12 % tensor pipe), and they run one after the other.  Here one
+// CTA computes, per tile of 128 pixels of one output row:
+//   stage 1   the conv2 tile exactly as conv_tc_kernel<64> in "dxr" mode does (same MMA order, segments, epilogue maths),
+//             but its epilogue writes the BN+ReLU'd result as hi/lo planes into SHARED memory (t2, [128 px][64 ch] rows of
+//             128 B, 128-byte swizzle: exactly a K-major UMMA A operand) instead of HBM;
+//   stage 2   conv3 as four 128 x 64 GEMM tiles with A = t2, B = conv3 weights, the residual tile TMA-prefetched into an
+//             epilogue buffer, updated in place and TMA-stored (as gemm_tc_kernel does), halo columns by direct stores.
+// The 64-channel intermediate never visits HBM (-0.54 GB per block) and, more importantly, conv2's MMAs of tile i+1 overlap
+// conv3's HBM traffic of tile i.  The MMA warp issues  c2(0), c2(1), c3(0), c2(2), c3(1), ...  so that the tensor pipe
+// never waits for the conv2 epilogue.  Results are bit-identical to the unfused kernels (same products, same
+// accumulator structure, same epilogue arithmetic); HN_TC_FUSE=0 selects the unfused path.
+//   warp 0      TMA producer (input rows, conv2 / conv3 weight tiles through one ring, residual tiles)
+//   warp 1      MMA issuer          warp 2   TMEM allocator (512 columns)          warp 3   TMA store
+//   warps 4-7   conv2 epilogue (lane quarter = warp % 4, all 64 columns)
+//   warps 8-11  conv3 epilogue (lane quarter = warp % 4, all 64 columns of each of the four n-tiles)
+struct BottArgs {
+    int Ho, Wo, Wop, wsegs, Bimg;
+    int num_tiles;
+    int n3;                              // conv3 n-tiles of 64 channels (Cout3 / 64)
+    int C3;                              // conv3 output channels
+    int seg;
+    const float* scale2; const float* shift2;     // conv2: accumulator -> plane units, shift in plane units
+    const float* scale3; const float* shift3;     // conv3
+    unsigned short* out; size_t out_plane;        // output planes (halo-column stores)
+};
+
+struct BtSmem {
+    static constexpr int AX_PLANE = 17 * 1024;            // 130 input pixels x 128 B (136 rows reserved)
+    static constexpr int AX_SLOT = 2 * AX_PLANE;          // hi + lo
+    static constexpr int NB = 3;                          // weight-tile ring
+    static constexpr int B_PLANE = 64 * BKC * 2;          // 8 KB
+    static constexpr int B_STAGE = 2 * B_PLANE;           // 16 KB
+    static constexpr int B_OFF = 2 * AX_SLOT;             // 68 KB
+    static constexpr int T2_OFF = B_OFF + NB * B_STAGE;   // 116 KB (1024-aligned)
+    static constexpr int T_PLANE = BM * BKC * 2;          // 16 KB
+    static constexpr int E_OFF = T2_OFF + 2 * T_PLANE;    // 148 KB
+    static constexpr int E_PLANE = BM * 64 * 2;           // 16 KB
+    static constexpr int EBUF = 2 * E_PLANE;
+    static constexpr int BAR_OFF = E_OFF + 2 * EBUF;      // 212 KB
+    static constexpr int TOTAL = BAR_OFF + 512 + 1024;
+    static constexpr int TMEM_COLS = 512;                 // c2: 2 main + 2 cross, c3: 2 main + 2 cross accumulators of 64 columns
+};
+static_assert(BtSmem::T2_OFF % 1024 == 0 && BtSmem::E_OFF % 1024 == 0 && BtSmem::B_OFF % 1024 == 0, "swizzle atoms need 1024-byte alignment");
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB2,
+               const __grid_constant__ CUtensorMap tmB3, const __grid_constant__ CUtensorMap tmR,
+               const __grid_constant__ CUtensorMap tmO, const BottArgs a) {
+    using S = BtSmem;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // [NB] weight tile landed
+    uint64_t* empty_bar = full_bar + S::NB;         // [NB] weight tile consumed
+    uint64_t* afull_bar = empty_bar + S::NB;        // [2] input-row slot filled
+    uint64_t* aempty_bar = afull_bar + 2;           // [2] input-row slot consumed
+    uint64_t* tfull_bar = aempty_bar + 2;           // [2] conv2 hi*hi segment ready
+    uint64_t* tempty_bar = tfull_bar + 2;           // [2] conv2 segment drained
+    uint64_t* cempty_bar = tempty_bar + 2;          // [2] conv2 cross accumulator drained
+    uint64_t* t2ready_bar = cempty_bar + 2;         // [1] conv2 epilogue has written t2
+    uint64_t* t2free_bar = t2ready_bar + 1;         // [1] conv3 MMAs of the tile have read t2
+    uint64_t* dfull_bar = t2free_bar + 1;           // [2] conv3 accumulators ready
+    uint64_t* dempty_bar = dfull_bar + 2;           // [2] conv3 accumulators drained
+    uint64_t* rfull_bar = dempty_bar + 2;           // [2] residual tile landed in the epilogue buffer
+    uint64_t* oready_bar = rfull_bar + 2;           // [2] output tile complete in the epilogue buffer
+    uint64_t* efree_bar = oready_bar + 2;           // [2] TMA store has read the epilogue buffer
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(efree_bar + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB2)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmB3)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmR)) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmO)) : "memory");
+    }
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < S::NB; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(afull_bar + i, 1); mbar_init(aempty_bar + i, 1);
+            mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 4); mbar_init(cempty_bar + i, 4);
+            mbar_init(dfull_bar + i, 1); mbar_init(dempty_bar + i, 4);
+            mbar_init(rfull_bar + i, 1); mbar_init(oready_bar + i, 4); mbar_init(efree_bar + i, 1);
+        }
+        mbar_init(t2ready_bar, 4); mbar_init(t2free_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    // TMEM columns: conv2 main [0,64) [64,128), conv2 cross [128,192) [192,256); conv3 main [256,320) [320,384), cross [384,448) [448,512)
+    const int n_local = (a.num_tiles > (int)blockIdx.x) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n3 = a.n3;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            int ast = 0, bst = 0, g3 = 0;
+            uint32_t aph = 0, bph = 0;
+            auto load_c3 = [&](int tile) {            // conv3 weight tiles + residual tiles of one pixel tile
+                const int rg = tile / a.wsegs;
+                const int pix0 = rg * a.Wop + 1 + (tile - rg * a.wsegs) * BM;
+                for (int j = 0; j < n3; ++j, ++g3) {
+                    mbar_wait(empty_bar + bst, bph ^ 1);
+                    uint8_t* sB = smem + S::B_OFF + bst * S::B_STAGE;
+                    mbar_expect_tx(full_bar + bst, (uint32_t)S::B_STAGE);
+                    tma_load_3d(sB, &tmB3, full_bar + bst, 0, j * 64, 0);
+                    tma_load_3d(sB + S::B_PLANE, &tmB3, full_bar + bst, 0, j * 64, 1);
+                    if (++bst == S::NB) { bst = 0; bph ^= 1; }
+                    const int eb = g3 & 1;
+                    mbar_wait(efree_bar + eb, ((g3 >> 1) & 1) ^ 1);
+                    uint8_t* ebuf = smem + S::E_OFF + eb * S::EBUF;
+                    mbar_expect_tx(rfull_bar + eb, 2u * S::E_PLANE);
+                    tma_load_3d(ebuf, &tmR, rfull_bar + eb, j * 64, pix0, 0);
+                    tma_load_3d(ebuf + S::E_PLANE, &tmR, rfull_bar + eb, j * 64, pix0, 1);
+                }
+            };
+            int prev = -1;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+                const int rg = tile / a.wsegs;
+                const int wo0 = (tile - rg * a.wsegs) * BM;
+                const int b = rg / a.Ho, ho = rg - b * a.Ho;
+                for (int dy = 0; dy < 3; ++dy) {
+                    const int hin = ho + dy - 1;
+                    mbar_wait(aempty_bar + ast, aph ^ 1);
+                    uint8_t* sAx = smem + ast * S::AX_SLOT;
+                    mbar_expect_tx(afull_bar + ast, 2u * 130u * 128u);
+                    tma_load_4d(sAx, &tmA, afull_bar + ast, 0, wo0, hin, b);
+                    tma_load_4d(sAx + S::AX_PLANE, &tmA, afull_bar + ast, 0, wo0, hin, a.Bimg + b);
+                    if (++ast == 2) { ast = 0; aph ^= 1; }
+                    for (int dx = 0; dx < 3; ++dx) {
+                        mbar_wait(empty_bar + bst, bph ^ 1);
+                        uint8_t* sB = smem + S::B_OFF + bst * S::B_STAGE;
+                        mbar_expect_tx(full_bar + bst, (uint32_t)S::B_STAGE);
+                        const int kb = (dy * 3 + dx) * BKC;
+                        tma_load_3d(sB, &tmB2, full_bar + bst, kb, 0, 0);
+                        tma_load_3d(sB + S::B_PLANE, &tmB2, full_bar + bst, kb, 0, 1);
+                        if (++bst == S::NB) { bst = 0; bph ^= 1; }
+                    }
+                }
+                if (prev >= 0) load_c3(prev);
+                prev = tile;
+            }
+            if (prev >= 0) load_c3(prev);
+        }
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(64, 0, 0, BM);
+            int ast = 0, bst = 0, g = 0, g3 = 0;
+            uint32_t aph = 0, bph = 0;
+            const uint32_t t2 = smem_u32(smem + S::T2_OFF);
+            auto conv3 = [&](int k) {                // conv3 of local tile k: A = t2 (hi, lo), B = weight ring
+                mbar_wait(t2ready_bar, (uint32_t)(k & 1));
+                tc_fence_after();
+                const uint64_t a_hi = umma_desc_sw128(t2), a_lo = umma_desc_sw128(t2 + S::T_PLANE);
+                for (int j = 0; j < n3; ++j, ++g3) {
+                    const int db = g3 & 1;
+                    mbar_wait(dempty_bar + db, ((g3 >> 1) & 1) ^ 1);
+                    mbar_wait(full_bar + bst, bph);
+                    tc_fence_after();
+                    const uint32_t sB = smem_u32(smem + S::B_OFF + bst * S::B_STAGE);
+                    const uint64_t b_hi = umma_desc_sw128(sB), b_lo = umma_desc_sw128(sB + S::B_PLANE);
+                    const uint32_t d_main = tmem_base + 256 + db * 64, d_cross = tmem_base + 384 + db * 64;
+#pragma unroll
+                    for (int kk = 0; kk < BKC / 16; ++kk) {
+                        const uint64_t ko = (uint64_t)((kk * 16 * 2) >> 4);
+                        umma_f16(d_main, a_hi + ko, b_hi + ko, idesc, kk != 0);
+                        umma_f16(d_cross, a_hi + ko, b_lo + ko, idesc, kk != 0);
+                        umma_f16(d_cross, a_lo + ko, b_hi + ko, idesc, 1);
+                    }
+                    umma_commit(empty_bar + bst);
+                    umma_commit(dfull_bar + db);
+                    if (++bst == S::NB) { bst = 0; bph ^= 1; }
+                }
+                umma_commit(t2free_bar);
+            };
+            for (int it = 0; it < n_local; ++it) {
+                // ---- conv2 of local tile `it` (identical to conv_tc_kernel<64> in dxr mode)
+                const int cbuf = it & 1;
+                mbar_wait(cempty_bar + cbuf, ((it >> 1) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t d_cross = tmem_base + 128 + cbuf * 64;
+                uint32_t d_main = tmem_base;
+                int seg_pos = 0, mbuf = 0, kc = 0;
+                for (int dy = 0; dy < 3; ++dy) {
+                    mbar_wait(afull_bar + ast, aph);
+                    tc_fence_after();
+                    const uint32_t sAx = smem_u32(smem + ast * S::AX_SLOT);
+                    for (int dx = 0; dx < 3; ++dx, ++kc) {
+                        if (seg_pos == 0) {
+                            mbuf = g & 1;
+                            mbar_wait(tempty_bar + mbuf, ((g >> 1) & 1) ^ 1);
+                            tc_fence_after();
+                            d_main = tmem_base + mbuf * 64;
+                        }
+                        mbar_wait(full_bar + bst, bph);
+                        tc_fence_after();
+                        const uint32_t sB = smem_u32(smem + S::B_OFF + bst * S::B_STAGE);
+                        const uint64_t a_hi = umma_desc_sw128(sAx + dx * 128);
+                        const uint64_t a_lo = umma_desc_sw128(sAx + S::AX_PLANE + dx * 128);
+                        const uint64_t b_hi = umma_desc_sw128(sB), b_lo = umma_desc_sw128(sB + S::B_PLANE);
+#pragma unroll
+                        for (int kk = 0; kk < BKC / 16; ++kk) {
+                            const uint64_t ko = (uint64_t)((kk * 16 * 2) >> 4);
+                            umma_f16(d_main, a_hi + ko, b_hi + ko, idesc, (seg_pos | kk) != 0);
+                            umma_f16(d_cross, a_hi + ko, b_lo + ko, idesc, (kc | kk) != 0);
+                            umma_f16(d_cross, a_lo + ko, b_hi + ko, idesc, 1);
+                        }
+                        umma_commit(empty_bar + bst);
+                        if (++seg_pos == a.seg || kc == 8) {
+                            umma_commit(tfull_bar + mbuf);
+                            seg_pos = 0;
+                            ++g;
+                        }
+                        if (++bst == S::NB) { bst = 0; bph ^= 1; }
+                    }
+                    umma_commit(aempty_bar + ast);
+                    if (++ast == 2) { ast = 0; aph ^= 1; }
+                }
+                if (it > 0) conv3(it - 1);
+            }
+            if (n_local > 0) conv3(n_local - 1);
+        }
+    } else if (warp == 3) {
+        // =============================== store warp ===============================
+        if (lane == 0) {
+            int g3 = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+                const int rg = tile / a.wsegs;
+                const int pix0 = rg * a.Wop + 1 + (tile - rg * a.wsegs) * BM;
+                for (int j = 0; j < n3; ++j, ++g3) {
+                    const int eb = g3 & 1;
+                    mbar_wait(oready_bar + eb, (g3 >> 1) & 1);
+                    const uint8_t* ebuf = smem + S::E_OFF + eb * S::EBUF;
+                    tma_store_3d(&tmO, ebuf, j * 64, pix0, 0);
+                    tma_store_3d(&tmO, ebuf + S::E_PLANE, j * 64, pix0, 1);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    mbar_arrive(efree_bar + eb);
+                }
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // =============================== conv2 epilogue -> t2 in shared memory ===============================
+        const int q = warp & 3;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int r = q * 32 + lane;                     // pixel of the tile = row of t2
+        const int nseg = (9 + a.seg - 1) / a.seg;
+        const uint32_t t_hi = smem_u32(smem + S::T2_OFF) + r * 128, t_lo = t_hi + S::T_PLANE;
+        int g = 0;
+        for (int it = 0; it < n_local; ++it) {
+            const int cbuf = it & 1;
+            float sum[64];
+#pragma unroll
+            for (int j = 0; j < 64; ++j) sum[j] = 0.f;
+            for (int sgi = 0; sgi < nseg; ++sgi, ++g) {
+                const int mbuf = g & 1;
+                mbar_wait(tfull_bar + mbuf, (g >> 1) & 1);
+                tc_fence_after();
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)(mbuf * 64 + ch * 32), v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) sum[ch * 32 + j] += __uint_as_float(v[j]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar + mbuf);
+            }
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_base + (uint32_t)(128 + cbuf * 64 + ch * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale2 + ch * 32 + j));
+                    const float4 sf = __ldg(reinterpret_cast<const float4*>(a.shift2 + ch * 32 + j));
+                    sum[ch * 32 + j + 0] = fmaxf(fmaf(sum[ch * 32 + j + 0] + __uint_as_float(v[j + 0]), sc.x, sf.x), 0.f);
+                    sum[ch * 32 + j + 1] = fmaxf(fmaf(sum[ch * 32 + j + 1] + __uint_as_float(v[j + 1]), sc.y, sf.y), 0.f);
+                    sum[ch * 32 + j + 2] = fmaxf(fmaf(sum[ch * 32 + j + 2] + __uint_as_float(v[j + 2]), sc.z, sf.z), 0.f);
+                    sum[ch * 32 + j + 3] = fmaxf(fmaf(sum[ch * 32 + j + 3] + __uint_as_float(v[j + 3]), sc.w, sf.w), 0.f);
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(cempty_bar + cbuf);
+            // t2 may be overwritten once conv3 of the previous tile has read it
+            if (it > 0) mbar_wait(t2free_bar, (uint32_t)((it - 1) & 1));
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split2_scaled(sum[c * 8 + 2 * e], sum[c * 8 + 2 * e + 1], ph[e], pl[e]);
+                const uint32_t off = (uint32_t)((c ^ (r & 7)) << 4);
+                st_shared_v4(t_hi + off, make_uint4(ph[0], ph[1], ph[2], ph[3]));
+                st_shared_v4(t_lo + off, make_uint4(pl[0], pl[1], pl[2], pl[3]));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core (async proxy) reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t2ready_bar);
+        }
+    } else if (warp >= 8) {
+        // =============================== conv3 epilogue (as gemm_tc_kernel) ===============================
+        const int q = warp & 3;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int r = q * 32 + lane;
+        int g3 = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+            const int rg = tile / a.wsegs;
+            const int wo0 = (tile - rg * a.wsegs) * BM;
+            // circular halo columns of the output row (hn_common.cuh): wp = Wo + 1 copies wo = 0, wp = 0 copies wo = Wo - 1
+            long long halo_pix = -1;
+            if (wo0 + r == 0) halo_pix = (long long)rg * a.Wop + a.Wo + 1;
+            else if (wo0 + r == a.Wo - 1) halo_pix = (long long)rg * a.Wop;
+            for (int j = 0; j < n3; ++j, ++g3) {
+                const int db = g3 & 1, eb = g3 & 1;
+                mbar_wait(dfull_bar + db, (g3 >> 1) & 1);
+                tc_fence_after();
+                float sum[64];
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)(256 + db * 64 + ch * 32), v);
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) sum[ch * 32 + jj] = 0.f + __uint_as_float(v[jj]);
+                }
+#pragma unroll
+                for (int ch = 0; ch < 2; ++ch) {
+                    uint32_t v[32];
+                    tmem_ld32(tmem_base + lane_base + (uint32_t)(384 + db * 64 + ch * 32), v);
+#pragma unroll
+                    for (int jj = 0; jj < 32; ++jj) sum[ch * 32 + jj] += __uint_as_float(v[jj]);
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(dempty_bar + db);
+                const int n0 = j * 64;
+#pragma unroll
+                for (int jj = 0; jj < 64; jj += 4) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale3 + n0 + jj));
+                    const float4 sf = __ldg(reinterpret_cast<const float4*>(a.shift3 + n0 + jj));
+                    sum[jj + 0] = fmaf(sum[jj + 0], sc.x, sf.x);
+                    sum[jj + 1] = fmaf(sum[jj + 1], sc.y, sf.y);
+                    sum[jj + 2] = fmaf(sum[jj + 2], sc.z, sf.z);
+                    sum[jj + 3] = fmaf(sum[jj + 3], sc.w, sf.w);
+                }
+                mbar_wait(rfull_bar + eb, (g3 >> 1) & 1);
+                const uint32_t e_hi = smem_u32(smem + S::E_OFF + eb * S::EBUF) + r * 128;
+                const uint32_t e_lo = e_hi + S::E_PLANE;
+                unsigned short* hrow = (halo_pix >= 0) ? a.out + (size_t)halo_pix * a.C3 + n0 : nullptr;
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const uint32_t off = (uint32_t)((c ^ (r & 7)) << 4);
+                    float* y = sum + c * 8;
+                    const uint4 h = ld_shared_v4(e_hi + off), l = ld_shared_v4(e_lo + off);
+                    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 fh = unpack_half2(hw[e]), fl = unpack_half2(lw[e]);
+                        y[2 * e + 0] += fh.x + fl.x;
+                        y[2 * e + 1] += fh.y + fl.y;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) y[e] = fmaxf(y[e], 0.f);
+                    uint32_t ph[4], pl[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) split2_scaled(y[2 * e], y[2 * e + 1], ph[e], pl[e]);
+                    const uint4 oh = make_uint4(ph[0], ph[1], ph[2], ph[3]), ol = make_uint4(pl[0], pl[1], pl[2], pl[3]);
+                    st_shared_v4(e_hi + off, oh);
+                    st_shared_v4(e_lo + off, ol);
+                    if (hrow) {
+                        *reinterpret_cast<uint4*>(hrow + c * 8) = oh;
+                        *reinterpret_cast<uint4*>(hrow + a.out_plane + c * 8) = ol;
+                    }
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(oready_bar + eb);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
+    }
+}
+
 // -------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1460,6 +1864,74 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
     }
 }
 
+
+// ---------------------------------------------------------------------- fused conv2 + conv3 of a bottleneck (host side)
+bool bott_tc_supported(const ConvDesc& d2, const ConvDesc& d3, const Act& in, const Act& out) {
+    static const bool on = [] { const char* e = getenv("HN_TC_FUSE"); return !(e && atoi(e) == 0); }();
+    if (!on) return false;
+    return d2.kh == 3 && d2.kw == 3 && d2.sh == 1 && d2.sw == 1 && d2.ph == 1 && d2.pw == 1 && d2.Cin == 64 && d2.Cout == 64 &&
+           d2.relu && d3.kh == 1 && d3.kw == 1 && d3.sh == 1 && d3.sw == 1 && d3.Cin == 64 && d3.Cout % 64 == 0 && d3.relu &&
+           in.halo == 1 && out.halo == 1 && in.H == out.H && in.W == out.W && in.B == out.B && out.W % BM == 0 &&
+           in.C == 64 && out.C == d3.Cout;
+}
+
+// in: conv2 input planes [B][H][W+2][64]; res / out: [B][H][W+2][C3] planes (res = the block's identity); wq2 / aux2, wq3 / aux3
+// as produced by pack_weight_tc for the two convolutions.
+int bott_tc_planes(const ConvDesc& d2, const unsigned short* wq2, const float* aux2, const ConvDesc& d3,
+                   const unsigned short* wq3, const float* aux3, const Act& in, const unsigned short* in_planes, const Act& out,
+                   unsigned short* out_planes, const unsigned short* res_planes, cudaStream_t st) {
+    HN_CHECK(bott_tc_supported(d2, d3, in, out), "bott_tc: unsupported shape");
+    HN_CHECK(res_planes != nullptr, "bott_tc: the fused kernel expects the block's identity");
+    const size_t in_plane = in.numel(), out_plane = out.numel();
+    const cuuint64_t Wp = in.Wp();
+    CUtensorMap tmA, tmB2, tmB3, tmR, tmO;
+    {
+        cuuint64_t dims[4] = {64, Wp, (cuuint64_t)in.H, (cuuint64_t)2 * in.B};
+        cuuint64_t str[3] = {128, 128 * Wp, 128 * Wp * in.H};
+        cuuint32_t box[4] = {BKC, 130, 1, 1};
+        if (make_map(&tmA, in_planes, 4, dims, str, box)) return -1;
+        (void)in_plane;
+    }
+    {
+        cuuint64_t dims[3] = {576, 64, 2};
+        cuuint64_t str[2] = {576 * 2, 576 * 64 * 2};
+        cuuint32_t box[3] = {BKC, 64, 1};
+        if (make_map(&tmB2, wq2, 3, dims, str, box)) return -1;
+    }
+    {
+        cuuint64_t dims[3] = {64, (cuuint64_t)d3.Cout, 2};
+        cuuint64_t str[2] = {64 * 2, (cuuint64_t)64 * d3.Cout * 2};
+        cuuint32_t box[3] = {BKC, 64, 1};
+        if (make_map(&tmB3, wq3, 3, dims, str, box)) return -1;
+    }
+    {
+        const cuuint64_t Mtot = (cuuint64_t)out.B * out.H * out.Wp();
+        cuuint64_t dims[3] = {(cuuint64_t)d3.Cout, Mtot, 2};
+        cuuint64_t str[2] = {(cuuint64_t)d3.Cout * 2, (cuuint64_t)out_plane * 2};
+        cuuint32_t box[3] = {64, BM, 1};
+        if (make_map(&tmO, out_planes, 3, dims, str, box)) return -1;
+        if (make_map(&tmR, res_planes, 3, dims, str, box)) return -1;
+    }
+    BottArgs a;
+    memset(&a, 0, sizeof(a));
+    a.Ho = out.H; a.Wo = out.W; a.Wop = out.Wp(); a.wsegs = out.W / BM; a.Bimg = in.B;
+    const long long tiles = (long long)out.B * out.H * a.wsegs;
+    HN_CHECK(tiles < (1ll << 31) && (long long)out.B * out.H * out.Wp() < (1ll << 31), "bott_tc: too many tiles");
+    a.num_tiles = (int)tiles;
+    a.n3 = d3.Cout / 64; a.C3 = d3.Cout;
+    a.seg = tc_segment_chunks();
+    a.scale2 = aux2 + 64; a.shift2 = aux2 + 2 * 64;                        // plane units (conv_tc.cuh: tc_aux)
+    a.scale3 = aux3 + d3.Cout; a.shift3 = aux3 + 2 * d3.Cout;
+    a.out = out_planes; a.out_plane = out_plane;
+    if (a.num_tiles == 0) return 0;
+    HN_CUDA_OK(cudaFuncSetAttribute(bott_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, BtSmem::TOTAL));
+    int dev = 0, sms = 0;
+    HN_CUDA_OK(cudaGetDevice(&dev));
+    HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    bott_tc_kernel<<<a.num_tiles < sms ? a.num_tiles : sms, NTHREADS, BtSmem::TOTAL, st>>>(tmA, tmB2, tmB3, tmR, tmO, a);
+    HN_LAUNCH_OK();
+    return 0;
+}
 
 // ---------------------------------------------------------------------- stem on tensor cores (host side)
 size_t stem_tc_scratch_bytes(int B) { return (size_t)2 * B * SP_ROWS * SP_PAIRS * 16; }

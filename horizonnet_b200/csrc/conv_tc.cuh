@@ -54,6 +54,12 @@ int conv_tc(const ConvDesc& d, const Act& in, const Act& out, const float* resid
 int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_aux, const Act& in,
                    const unsigned short* in_planes, const Act& out, unsigned short* out_planes, float* out_f32,
                    const unsigned short* res_planes, cudaStream_t st);
+// conv2 (3x3 s1, 64 -> 64) + BN + ReLU fused with conv3 (1x1, 64 -> C3) + BN + identity + ReLU of a layer1 bottleneck
+// (conv_tc.cu: bott_tc_kernel); bit-identical to running conv_tc_planes twice; HN_TC_FUSE=0 disables it.
+bool bott_tc_supported(const ConvDesc& d2, const ConvDesc& d3, const Act& in, const Act& out);
+int bott_tc_planes(const ConvDesc& d2, const unsigned short* wq2, const float* aux2, const ConvDesc& d3,
+                   const unsigned short* wq3, const float* aux3, const Act& in, const unsigned short* in_planes, const Act& out,
+                   unsigned short* out_planes, const unsigned short* res_planes, cudaStream_t st);
 // 7x7 stride-2 stem on tcgen05 (conv_tc.cu: stem_tc_kernel): NCHW fp32 input -> fp32 halo-NHWC [B][256][514][64]
 // (interior columns only).  wq [2][64][224] / tc_aux [3*64+1] come from stem_tc_pack_weights (pad_scratch: 64*224 floats);
 // scratch: stem_tc_scratch_bytes(B) bytes of packed input planes.

@@ -161,6 +161,7 @@ struct hn_model {
     unsigned short* stem_wq = nullptr;               // tcgen05 stem: [2][64][224] fp16 planes (conv_tc.cu: stem_tc)
     float* stem_aux = nullptr;                       // 3*64 + 1 epilogue constants
     int stem_tc_on = 1;                              // option "stem_tc" / HN_TC_STEM=0: fp32 CUDA-core stem inside the TC path
+    int fuse_on = 1;                                 // option "fuse_bottleneck": fused conv2+conv3 kernel for layer1 (bit-identical)
     struct Block { ConvLayer c1, c2, c3, ds; bool has_ds = false; };
     std::vector<Block> blocks[4];
     ConvLayer ghc[4][4];
@@ -467,6 +468,7 @@ int hn_model_set_option(hn_model* m, const char* name, int value) {
     if (std::strcmp(name, "tensor_cores") == 0) { m->use_tc = value; return 0; }
     if (std::strcmp(name, "profile") == 0) { m->profile = value; return 0; }
     if (std::strcmp(name, "stem_tc") == 0) { m->stem_tc_on = value; return 0; }
+    if (std::strcmp(name, "fuse_bottleneck") == 0) { m->fuse_on = value; return 0; }
     return fail(std::string("hn_model_set_option: unknown option '") + name + "'");
 }
 
@@ -551,14 +553,24 @@ static int forward_encoder(hn_model* m, const float* x, int B, int in_channels, 
             Act t2 = mk(m->T2, B, Ho, Wo, blk.c2.d.Cout);
             Act y = mk(b == nb - 1 ? m->F[l] : m->X[b & 1], B, Ho, Wo, blk.c3.d.Cout);
             if (run_conv(m, blk.c1, cur, t1, nullptr, st, CLS_ENC_CONV)) return -1;
-            if (run_conv(m, blk.c2, t1, t2, nullptr, st, CLS_ENC_CONV)) return -1;
             const float* idn = cur.p;
             if (blk.has_ds) {
                 Act d = mk(m->IDN, B, Ho, Wo, blk.ds.d.Cout);
                 if (run_conv(m, blk.ds, cur, d, nullptr, st, CLS_ENC_CONV)) return -1;
                 idn = d.p;
             }
-            if (run_conv(m, blk.c3, t2, y, idn, st, CLS_ENC_CONV)) return -1;      // + identity, ReLU
+            if (m->use_tc && m->fuse_on && blk.c2.wq && blk.c3.wq && bott_tc_supported(blk.c2.d, blk.c3.d, t1, y)) {
+                // layer1: conv2 + conv3 in one kernel, the 64-channel intermediate stays in shared memory (conv_tc.cu)
+                const double flops = 2.0 * (double)B * Ho * Wo * (64.0 * 9 * 64 + (double)blk.c3.d.Cout * 64);
+                Scope sc(m, CLS_ENC_CONV, flops, st);
+                if (bott_tc_planes(blk.c2.d, blk.c2.wq, blk.c2.tc_scale, blk.c3.d, blk.c3.wq, blk.c3.tc_scale, t1,
+                                   reinterpret_cast<const unsigned short*>(t1.p), y, reinterpret_cast<unsigned short*>(y.p),
+                                   reinterpret_cast<const unsigned short*>(idn), st))
+                    return -1;
+            } else {
+                if (run_conv(m, blk.c2, t1, t2, nullptr, st, CLS_ENC_CONV)) return -1;
+                if (run_conv(m, blk.c3, t2, y, idn, st, CLS_ENC_CONV)) return -1;      // + identity, ReLU
+            }
             cur = y;
         }
         feats[l] = cur;

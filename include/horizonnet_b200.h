@@ -108,6 +108,7 @@ int hn_model_stage(hn_model* m, const char* stage, float* out_dev, long long cap
 /* Options: "tensor_cores" = 1 routes every conv / projection GEMM the tcgen05 kernel supports
  * through the split-fp16 tensor-core path (default), 0 = exact fp32 CUDA-core kernels everywhere;
  * "stem_tc" = 1 (default; env HN_TC_STEM) runs the 7x7 stem on tcgen05 when "tensor_cores" is on, 0 = fp32 CUDA-core stem;
+ * "fuse_bottleneck" = 1 (default; env HN_TC_FUSE) runs conv2 + conv3 of the layer1 bottlenecks as one kernel (bit-identical results);
  * "profile" = 1 turns on per-launch CUDA-event timing (see hn_model_profile_read). */
 int hn_model_set_option(hn_model* m, const char* name, int value);
 

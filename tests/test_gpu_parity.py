@@ -263,6 +263,27 @@ def test_forward_on_does_not_switch_the_current_device():
     assert _lib.lib().hn_build_digest().decode() == __import__('horizonnet_b200.build', fromlist=['x']).source_digest()
 
 
+def test_fused_bottleneck_kernel_is_bitwise_equal_to_the_unfused_convs():
+    """bott_tc_kernel (layer1: conv2 + BN + ReLU -> shared memory -> conv3 + BN + identity + ReLU in one kernel) performs
+    the same products in the same order with the same accumulator structure and epilogue arithmetic as conv_tc_kernel<64> +
+    gemm_tc_kernel, so layer1 and the final outputs must not change by a single bit (B = 3: odd tile counts per CTA)."""
+    sd = synthetic_state_dict(8, 'random')
+    net = _net(sd, True)
+    x = synthetic_panoramas(3, seed=71).to(DEV)
+    got = {}
+    with torch.no_grad():
+        net(x)                                  # creates the handle
+        for mode in (1, 0):
+            net.set_option('fuse_bottleneck', mode)
+            bon, cor = net(x)
+            got[mode] = (bon.clone(), cor.clone(), net.debug_stage('layer1').clone())
+        net.set_option('fuse_bottleneck', 1)
+    net.check()
+    assert torch.isfinite(got[1][2]).all()
+    assert torch.equal(got[1][2], got[0][2]), (got[1][2] - got[0][2]).abs().max().item()
+    assert torch.equal(got[1][0], got[0][0]) and torch.equal(got[1][1], got[0][1])
+
+
 def test_tensor_core_stem_vs_oracle_and_fp32_stem():
     """stem_tc_kernel (7x7 s2 conv as an implicit GEMM over packed pixel pairs) against the oracle's stem in fp64
     and against the exact fp32 CUDA-core stem_kernel it replaces on the tensor-core path."""
@@ -482,7 +503,7 @@ def test_rotate_panorama_matches_the_real_reference_golden(golden_dir):
     batch = torch.from_numpy(img).to(DEV).unsqueeze(0)
     for name in ('tilt', 'big'):
         o = rotate_panorama_batch(batch, R=g[f'{name}_R'])[0].cpu().numpy()
-        assert np.abs(o[g['rows']] - g[f'{name}_rows']).max() < 1e-12, name
+        assert np.abs(o[g["rows"]] - g[f"{name}_rows"]).max() < 1e-10, name   # R^-1 product vs the reference's per-pixel LU solve
         assert abs(o.sum() - float(g[f'{name}_sum'])) < 1e-6 and abs((o ** 2).sum() - float(g[f'{name}_sq'])) < 1e-6, name
     # identity rotation reproduces the image (the padding never contributes); odd sizes / 1 channel vs the oracle
     ident = rotatePanorama(g['small_img'], R=np.eye(3))
