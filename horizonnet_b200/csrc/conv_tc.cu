@@ -76,6 +76,12 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, ui
         : "memory");
 }
 
+// Programmatic dependent launch: the next kernel of the stream may be scheduled while this one still runs (its CTAs take
+// over an SM as soon as ours exit, set up barriers / TMEM / tensor-map prefetch there) and blocks in pdl_wait() until this
+// grid has completed and flushed: ~78 kernel boundaries per forward stop costing a launch latency + prologue each.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -176,6 +182,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+__device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack2(unsigned short a, unsigned short b) {
     return (uint32_t)a | ((uint32_t)b << 16);
 }
@@ -224,6 +244,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
     using S = Smem<BN, PAIR>;
     constexpr int NST = S::NST;
+    pdl_trigger();
     const uint32_t rank = PAIR ? cluster_rank() : 0u;                 // 0 = leader of the pair
     const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
     const int tstride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -278,6 +299,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (PAIR) cluster_sync_all(); else __syncthreads();      // barriers initialised in both CTAs before any remote signal
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                              // everything below reads / writes activations
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
@@ -728,6 +750,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmR, const __grid_constant__ CUtensorMap tmO, const TcArgs a) {
     using S = GSmem;
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
@@ -765,6 +788,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
@@ -1058,6 +1082,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 stem_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmO, const StemArgs a) {
     using S = StSmem;
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
@@ -1094,6 +1119,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     // tile -> (image b, output row yo, 128-pixel segment sg): 4 segments per row, 256 rows per image
     if (warp == 0) {
@@ -1226,10 +1252,9 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // conv3's HBM traffic of tile i.  The MMA warp issues  c2(0), c2(1), c3(0), c2(2), c3(1), ...  so that the tensor pipe
 // never waits for the conv2 epilogue.  Results are bit-identical to the unfused kernels (same products, same
 // accumulator structure, same epilogue arithmetic); HN_TC_FUSE=0 selects the unfused path.
-//   warp 0      TMA producer (input rows, conv2 / conv3 weight tiles through one ring, residual tiles)
-//   warp 1      MMA issuer          warp 2   TMEM allocator (512 columns)          warp 3   TMA store
-//   warps 4-7   conv2 epilogue (lane quarter = warp % 4, all 64 columns)
-//   warps 8-11  conv3 epilogue (lane quarter = warp % 4, all 64 columns of each of the four n-tiles)
+//   warp 0      TMA producer (input rows, conv2 / conv3 weight tiles through one ring)
+//   warp 1      MMA issuer          warp 2   TMEM allocator (512 columns), then residual-tile loader          warp 3   TMA store
+//   warps 4-11  epilogue, conv2 and conv3 (lane quarter = warp % 4, column half = (warp - 4) / 4)
 struct BottArgs {
     int Ho, Wo, Wop, wsegs, Bimg;
     int num_tiles;
@@ -1264,6 +1289,7 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmB3, const __grid_constant__ CUtensorMap tmR,
                const __grid_constant__ CUtensorMap tmO, const BottArgs a) {
     using S = BtSmem;
+    pdl_trigger();
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // [NB] weight tile landed
@@ -1274,7 +1300,7 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* tempty_bar = tfull_bar + 2;           // [2] conv2 segment drained
     uint64_t* cempty_bar = tempty_bar + 2;          // [2] conv2 cross accumulator drained
     uint64_t* t2ready_bar = cempty_bar + 2;         // [1] conv2 epilogue has written t2
-    uint64_t* t2free_bar = t2ready_bar + 1;         // [1] conv3 MMAs of the tile have read t2
+    uint64_t* t2free_bar = t2ready_bar + 1;         // [1] (unused: the epilogue order itself guarantees that t2 is free)
     uint64_t* dfull_bar = t2free_bar + 1;           // [2] conv3 accumulators ready
     uint64_t* dempty_bar = dfull_bar + 2;           // [2] conv3 accumulators drained
     uint64_t* rfull_bar = dempty_bar + 2;           // [2] residual tile landed in the epilogue buffer
@@ -1294,11 +1320,11 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int i = 0; i < S::NB; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(afull_bar + i, 1); mbar_init(aempty_bar + i, 1);
-            mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 4); mbar_init(cempty_bar + i, 4);
-            mbar_init(dfull_bar + i, 1); mbar_init(dempty_bar + i, 4);
-            mbar_init(rfull_bar + i, 1); mbar_init(oready_bar + i, 4); mbar_init(efree_bar + i, 1);
+            mbar_init(tfull_bar + i, 1); mbar_init(tempty_bar + i, 8); mbar_init(cempty_bar + i, 8);
+            mbar_init(dfull_bar + i, 1); mbar_init(dempty_bar + i, 8);
+            mbar_init(rfull_bar + i, 1); mbar_init(oready_bar + i, 8); mbar_init(efree_bar + i, 1);
         }
-        mbar_init(t2ready_bar, 4); mbar_init(t2free_bar, 1);
+        mbar_init(t2ready_bar, 8); mbar_init(t2free_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -1311,6 +1337,7 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
     // TMEM columns: conv2 main [0,64) [64,128), conv2 cross [128,192) [192,256); conv3 main [256,320) [320,384), cross [384,448) [448,512)
     const int n_local = (a.num_tiles > (int)blockIdx.x) ? (a.num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int n3 = a.n3;
@@ -1320,9 +1347,7 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             int ast = 0, bst = 0, g3 = 0;
             uint32_t aph = 0, bph = 0;
-            auto load_c3 = [&](int tile) {            // conv3 weight tiles + residual tiles of one pixel tile
-                const int rg = tile / a.wsegs;
-                const int pix0 = rg * a.Wop + 1 + (tile - rg * a.wsegs) * BM;
+            auto load_c3 = [&](int) {                 // conv3 weight tiles of one pixel tile (same for every tile: L2 hits)
                 for (int j = 0; j < n3; ++j, ++g3) {
                     mbar_wait(empty_bar + bst, bph ^ 1);
                     uint8_t* sB = smem + S::B_OFF + bst * S::B_STAGE;
@@ -1330,12 +1355,6 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     tma_load_3d(sB, &tmB3, full_bar + bst, 0, j * 64, 0);
                     tma_load_3d(sB + S::B_PLANE, &tmB3, full_bar + bst, 0, j * 64, 1);
                     if (++bst == S::NB) { bst = 0; bph ^= 1; }
-                    const int eb = g3 & 1;
-                    mbar_wait(efree_bar + eb, ((g3 >> 1) & 1) ^ 1);
-                    uint8_t* ebuf = smem + S::E_OFF + eb * S::EBUF;
-                    mbar_expect_tx(rfull_bar + eb, 2u * S::E_PLANE);
-                    tma_load_3d(ebuf, &tmR, rfull_bar + eb, j * 64, pix0, 0);
-                    tma_load_3d(ebuf + S::E_PLANE, &tmR, rfull_bar + eb, j * 64, pix0, 1);
                 }
             };
             int prev = -1;
@@ -1396,7 +1415,6 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     umma_commit(dfull_bar + db);
                     if (++bst == S::NB) { bst = 0; bph ^= 1; }
                 }
-                umma_commit(t2free_bar);
             };
             for (int it = 0; it < n_local; ++it) {
                 // ---- conv2 of local tile `it` (identical to conv_tc_kernel<64> in dxr mode)
@@ -1445,6 +1463,27 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             if (n_local > 0) conv3(n_local - 1);
         }
+    } else if (warp == 2) {
+        // =============================== residual loader ===============================
+        // its own thread, so that the identity tile of n-tile j is requested the moment its epilogue buffer is released
+        // (two n-tiles ahead of its use): the residual comes from HBM, and behind the weight ring (first version) it was
+        // requested only when the conv3 MMAs of that n-tile were about to issue -- the epilogue then waited a DRAM latency
+        // per n-tile and the fused kernel was no faster than conv2 + conv3.
+        if (lane == 0) {
+            int g3 = 0;
+            for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+                const int rg = tile / a.wsegs;
+                const int pix0 = rg * a.Wop + 1 + (tile - rg * a.wsegs) * BM;
+                for (int j = 0; j < n3; ++j, ++g3) {
+                    const int eb = g3 & 1;
+                    mbar_wait(efree_bar + eb, ((g3 >> 1) & 1) ^ 1);
+                    uint8_t* ebuf = smem + S::E_OFF + eb * S::EBUF;
+                    mbar_expect_tx(rfull_bar + eb, 2u * S::E_PLANE);
+                    tma_load_3d(ebuf, &tmR, rfull_bar + eb, j * 64, pix0, 0);
+                    tma_load_3d(ebuf + S::E_PLANE, &tmR, rfull_bar + eb, j * 64, pix0, 1);
+                }
+            }
+        }
     } else if (warp == 3) {
         // =============================== store warp ===============================
         if (lane == 0) {
@@ -1465,73 +1504,23 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
         }
-    } else if (warp >= 4 && warp < 8) {
-        // =============================== conv2 epilogue -> t2 in shared memory ===============================
+    } else if (warp >= EPI_WARP0) {
+        // =============================== epilogue warps (conv2 and conv3) ===============================
+        // All 8 warps do both jobs (lane quarter = warp % 4, 32 of the 64 columns each).  Per tile `it`:
+        //   (1) drain the conv2 segments + cross accumulator of tile it into 32 registers (BN + ReLU applied),
+        //   (2) run the four conv3 n-tile epilogues of tile it-1 (their MMAs were issued after conv2(it)),
+        //   (3) write the conv2 result as the t2 rows -- safe now: every conv3 MMA that reads t2(it-1) has completed,
+        //       this warp has just consumed their accumulators -- and release conv3(it).
+        // (First version: 4 warps for conv2 and 4 for conv3, 64 columns each; ncu showed the conv3 warps busy 70 % of
+        // the time and everything else waiting for them: 19.5 k cycles per tile.)
         const int q = warp & 3;
+        const int half = (warp - EPI_WARP0) >> 2;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const int r = q * 32 + lane;                     // pixel of the tile = row of t2
+        const int r = q * 32 + lane;                     // pixel of the tile = accumulator lane = row of t2 / epilogue buffer
         const int nseg = (9 + a.seg - 1) / a.seg;
         const uint32_t t_hi = smem_u32(smem + S::T2_OFF) + r * 128, t_lo = t_hi + S::T_PLANE;
-        int g = 0;
-        for (int it = 0; it < n_local; ++it) {
-            const int cbuf = it & 1;
-            float sum[64];
-#pragma unroll
-            for (int j = 0; j < 64; ++j) sum[j] = 0.f;
-            for (int sgi = 0; sgi < nseg; ++sgi, ++g) {
-                const int mbuf = g & 1;
-                mbar_wait(tfull_bar + mbuf, (g >> 1) & 1);
-                tc_fence_after();
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_base + (uint32_t)(mbuf * 64 + ch * 32), v);
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) sum[ch * 32 + j] += __uint_as_float(v[j]);
-                }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(tempty_bar + mbuf);
-            }
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                uint32_t v[32];
-                tmem_ld32(tmem_base + lane_base + (uint32_t)(128 + cbuf * 64 + ch * 32), v);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale2 + ch * 32 + j));
-                    const float4 sf = __ldg(reinterpret_cast<const float4*>(a.shift2 + ch * 32 + j));
-                    sum[ch * 32 + j + 0] = fmaxf(fmaf(sum[ch * 32 + j + 0] + __uint_as_float(v[j + 0]), sc.x, sf.x), 0.f);
-                    sum[ch * 32 + j + 1] = fmaxf(fmaf(sum[ch * 32 + j + 1] + __uint_as_float(v[j + 1]), sc.y, sf.y), 0.f);
-                    sum[ch * 32 + j + 2] = fmaxf(fmaf(sum[ch * 32 + j + 2] + __uint_as_float(v[j + 2]), sc.z, sf.z), 0.f);
-                    sum[ch * 32 + j + 3] = fmaxf(fmaf(sum[ch * 32 + j + 3] + __uint_as_float(v[j + 3]), sc.w, sf.w), 0.f);
-                }
-            }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(cempty_bar + cbuf);
-            // t2 may be overwritten once conv3 of the previous tile has read it
-            if (it > 0) mbar_wait(t2free_bar, (uint32_t)((it - 1) & 1));
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                uint32_t ph[4], pl[4];
-#pragma unroll
-                for (int e = 0; e < 4; ++e) split2_scaled(sum[c * 8 + 2 * e], sum[c * 8 + 2 * e + 1], ph[e], pl[e]);
-                const uint32_t off = (uint32_t)((c ^ (r & 7)) << 4);
-                st_shared_v4(t_hi + off, make_uint4(ph[0], ph[1], ph[2], ph[3]));
-                st_shared_v4(t_lo + off, make_uint4(pl[0], pl[1], pl[2], pl[3]));
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core (async proxy) reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(t2ready_bar);
-        }
-    } else if (warp >= 8) {
-        // =============================== conv3 epilogue (as gemm_tc_kernel) ===============================
-        const int q = warp & 3;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const int r = q * 32 + lane;
-        int g3 = 0;
-        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        int g = 0, g3 = 0;
+        auto conv3_epilogue = [&](int tile) {
             const int rg = tile / a.wsegs;
             const int wo0 = (tile - rg * a.wsegs) * BM;
             // circular halo columns of the output row (hn_common.cuh): wp = Wo + 1 copies wo = 0, wp = 0 copies wo = Wo - 1
@@ -1542,27 +1531,21 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int db = g3 & 1, eb = g3 & 1;
                 mbar_wait(dfull_bar + db, (g3 >> 1) & 1);
                 tc_fence_after();
-                float sum[64];
+                float sum[32];
+                {
+                    uint32_t v[32], w[32];
+                    tmem_ld32_nowait(tmem_base + lane_base + (uint32_t)(256 + db * 64 + half * 32), v);
+                    tmem_ld32_nowait(tmem_base + lane_base + (uint32_t)(384 + db * 64 + half * 32), w);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_base + (uint32_t)(256 + db * 64 + ch * 32), v);
-#pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) sum[ch * 32 + jj] = 0.f + __uint_as_float(v[jj]);
-                }
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    uint32_t v[32];
-                    tmem_ld32(tmem_base + lane_base + (uint32_t)(384 + db * 64 + ch * 32), v);
-#pragma unroll
-                    for (int jj = 0; jj < 32; ++jj) sum[ch * 32 + jj] += __uint_as_float(v[jj]);
+                    for (int jj = 0; jj < 32; ++jj) sum[jj] = (0.f + __uint_as_float(v[jj])) + __uint_as_float(w[jj]);
                 }
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(dempty_bar + db);
-                const int n0 = j * 64;
+                const int n0 = j * 64 + half * 32;
 #pragma unroll
-                for (int jj = 0; jj < 64; jj += 4) {
+                for (int jj = 0; jj < 32; jj += 4) {
                     const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale3 + n0 + jj));
                     const float4 sf = __ldg(reinterpret_cast<const float4*>(a.shift3 + n0 + jj));
                     sum[jj + 0] = fmaf(sum[jj + 0], sc.x, sf.x);
@@ -1575,8 +1558,8 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t e_lo = e_hi + S::E_PLANE;
                 unsigned short* hrow = (halo_pix >= 0) ? a.out + (size_t)halo_pix * a.C3 + n0 : nullptr;
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const uint32_t off = (uint32_t)((c ^ (r & 7)) << 4);
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t off = (uint32_t)(((half * 4 + c) ^ (r & 7)) << 4);
                     float* y = sum + c * 8;
                     const uint4 h = ld_shared_v4(e_hi + off), l = ld_shared_v4(e_lo + off);
                     const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
@@ -1603,7 +1586,57 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 __syncwarp();
                 if (lane == 0) mbar_arrive(oready_bar + eb);
             }
+        };
+        int prev = -1, it = 0;
+        for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+            const int cbuf = it & 1;
+            float y2[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) y2[j] = 0.f;
+            for (int sgi = 0; sgi < nseg; ++sgi, ++g) {
+                const int mbuf = g & 1;
+                mbar_wait(tfull_bar + mbuf, (g >> 1) & 1);
+                tc_fence_after();
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_base + (uint32_t)(mbuf * 64 + half * 32), v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) y2[j] += __uint_as_float(v[j]);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar + mbuf);
+            }
+            {
+                uint32_t v[32];
+                tmem_ld32(tmem_base + lane_base + (uint32_t)(128 + cbuf * 64 + half * 32), v);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(cempty_bar + cbuf);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale2 + half * 32 + j));
+                    const float4 sf = __ldg(reinterpret_cast<const float4*>(a.shift2 + half * 32 + j));
+                    y2[j + 0] = fmaxf(fmaf(y2[j + 0] + __uint_as_float(v[j + 0]), sc.x, sf.x), 0.f);
+                    y2[j + 1] = fmaxf(fmaf(y2[j + 1] + __uint_as_float(v[j + 1]), sc.y, sf.y), 0.f);
+                    y2[j + 2] = fmaxf(fmaf(y2[j + 2] + __uint_as_float(v[j + 2]), sc.z, sf.z), 0.f);
+                    y2[j + 3] = fmaxf(fmaf(y2[j + 3] + __uint_as_float(v[j + 3]), sc.w, sf.w), 0.f);
+                }
+            }
+            if (prev >= 0) conv3_epilogue(prev);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint32_t ph[4], pl[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) split2_scaled(y2[c * 8 + 2 * e], y2[c * 8 + 2 * e + 1], ph[e], pl[e]);
+                const uint32_t off = (uint32_t)(((half * 4 + c) ^ (r & 7)) << 4);
+                st_shared_v4(t_hi + off, make_uint4(ph[0], ph[1], ph[2], ph[3]));
+                st_shared_v4(t_lo + off, make_uint4(pl[0], pl[1], pl[2], pl[3]));
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> tensor-core (async proxy) reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t2ready_bar);
+            prev = tile;
         }
+        if (prev >= 0) conv3_epilogue(prev);
     }
 
     tc_fence_before();
@@ -1657,6 +1690,27 @@ int tc_segment_chunks() {
     return seg;
 }
 
+bool pdl_on() {
+    static const bool on = [] { const char* e = getenv("HN_TC_PDL"); return !(e && atoi(e) == 0); }();
+    return on;
+}
+
+// launch of a persistent tensor-core kernel with programmatic stream serialisation (see pdl_trigger / pdl_wait)
+template <typename K, typename... Args>
+cudaError_t launch_tc(K kernel, int grid, size_t smem_bytes, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl_on() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+
 template <int BN>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
     using S = Smem<BN, false>;
@@ -1665,7 +1719,7 @@ int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cuda
     HN_CUDA_OK(cudaGetDevice(&dev));
     HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    conv_tc_kernel<BN, false><<<grid, NTHREADS, S::TOTAL, st>>>(tmA, tmB, a);
+    HN_CUDA_OK(launch_tc(conv_tc_kernel<BN, false>, grid, S::TOTAL, st, tmA, tmB, a));
     HN_LAUNCH_OK();
     return 0;
 }
@@ -1780,7 +1834,7 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
         int dev = 0, sms = 0;
         HN_CUDA_OK(cudaGetDevice(&dev));
         HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        gemm_tc_kernel<<<a.num_tiles < sms ? a.num_tiles : sms, NTHREADS, GSmem::TOTAL, st>>>(tmA, tmB, tmR, tmO, a);
+        HN_CUDA_OK(launch_tc(gemm_tc_kernel, a.num_tiles < sms ? a.num_tiles : sms, GSmem::TOTAL, st, tmA, tmB, tmR, tmO, a));
         HN_LAUNCH_OK();
         return 0;
     }
@@ -1928,7 +1982,7 @@ int bott_tc_planes(const ConvDesc& d2, const unsigned short* wq2, const float* a
     int dev = 0, sms = 0;
     HN_CUDA_OK(cudaGetDevice(&dev));
     HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    bott_tc_kernel<<<a.num_tiles < sms ? a.num_tiles : sms, NTHREADS, BtSmem::TOTAL, st>>>(tmA, tmB2, tmB3, tmR, tmO, a);
+    HN_CUDA_OK(launch_tc(bott_tc_kernel, a.num_tiles < sms ? a.num_tiles : sms, BtSmem::TOTAL, st, tmA, tmB2, tmB3, tmR, tmO, a));
     HN_LAUNCH_OK();
     return 0;
 }
@@ -1980,7 +2034,7 @@ int stem_tc(const float* x_nchw, int B, int in_channels, const unsigned short* w
     int dev = 0, sms = 0;
     HN_CUDA_OK(cudaGetDevice(&dev));
     HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    stem_tc_kernel<<<a.num_tiles < sms ? a.num_tiles : sms, NTHREADS, StSmem::TOTAL, st>>>(tmA, tmB, tmO, a);
+    HN_CUDA_OK(launch_tc(stem_tc_kernel, a.num_tiles < sms ? a.num_tiles : sms, StSmem::TOTAL, st, tmA, tmB, tmO, a));
     HN_LAUNCH_OK();
     return 0;
 }
