@@ -1830,10 +1830,14 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
         const long long mt = (Mtot + BM - 1) / BM;
         HN_CHECK(mt * a.n_tiles < (1ll << 31), "conv_tc: too many tiles");
         a.num_tiles = (int)(mt * a.n_tiles);
-        HN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GSmem::TOTAL));
         int dev = 0, sms = 0;
         HN_CUDA_OK(cudaGetDevice(&dev));
         HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        // (Round 2 negative result: a variant that keeps the 128 x K activation tile resident across the n-tiles of an
+        // m-tile -- the tile is otherwise re-fetched from L2 per n-tile, 8-16x on conv3 of layer2/3 -- measured 10-17 %
+        // SLOWER per launch (layer3 conv3 183 -> 214 us, layer2 conv3 224 -> 247 us): the resident tile leaves room for
+        // only 2 weight stages at K = 256 and serialises the A fill at every unit start.  Removed; see profiles/README.md.)
+        HN_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GSmem::TOTAL));
         HN_CUDA_OK(launch_tc(gemm_tc_kernel, a.num_tiles < sms ? a.num_tiles : sms, GSmem::TOTAL, st, tmA, tmB, tmR, tmO, a));
         HN_LAUNCH_OK();
         return 0;
