@@ -46,6 +46,10 @@ SIGNATURES = {
                                        c_double_p, c_double_p, ctypes.c_int, vp]),
     'hn_pano_stretch_host': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             c_double_p, c_double_p, ctypes.c_int]),
+    'hn_pano_stretch_f64': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           c_double_p, c_double_p, ctypes.c_int, vp]),
+    'hn_pano_stretch_host_f64': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                c_double_p, c_double_p, ctypes.c_int]),
     'hn_augment': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, c_double_p, c_double_p, c_int_p, c_int_p,
                                   c_float_p, vp]),
     'hn_rotate_panorama': (ctypes.c_int, [vp, ctypes.c_int, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -85,56 +85,6 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// ---- 2-CTA (cta_group::2) helpers: the pair's leader (cluster rank 0) owns the operand barriers
-__device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {
-    uint32_t r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA loads whose completion is signalled on an mbarrier given as a shared::cluster address (possibly the peer CTA's)
-__device__ __forceinline__ void tma2_load_3d(void* dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
-    asm volatile(
-        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-        : "memory");
-}
-__device__ __forceinline__ void tma2_load_4d(void* dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3) {
-    asm volatile(
-        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-        : "memory");
-}
-__device__ __forceinline__ void tma2_load_5d(void* dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2, int c3,
-                                             int c4) {
-    asm volatile(
-        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-        ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(tm)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
-        : "memory");
-}
-__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
-        : "memory");
-}
-// commit of the pair's MMAs: arrives on the barrier at the same offset in BOTH CTAs
-__device__ __forceinline__ void umma2_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-                     smem_u32(bar)),
-                 "h"((unsigned short)3)
-                 : "memory");
-}
-
 // K-major, 128-byte swizzle shared-memory operand descriptor (rows of 128 B, 8-row atoms 1024 B apart)
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     uint64_t d = 0;
@@ -146,7 +96,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
-// kind::f16 instruction descriptor: D=f32, A/B formats (0 = fp16, 1 = bf16), both K-major, M=m (128, or 256 for a CTA pair), N=n
+// kind::f16 instruction descriptor: D=f32, A/B formats (0 = fp16, 1 = bf16), both K-major, M=m, N=n
 __host__ __device__ constexpr uint32_t umma_idesc(int n, uint32_t a_fmt, uint32_t b_fmt, int m = BM) {
     return (1u << 4)                    // c_format  = F32
            | (a_fmt << 7)               // a_format
@@ -224,14 +174,11 @@ struct TcArgs {
     int dbg;                  // HN_TC_DBG experiment bits: 1 skip residual reads, 2 skip output stores, 4 skip epilogue math
 };
 
-// PAIR: two CTAs of a cluster work on a 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128 A rows
-// and HALF of the B rows, so a stage is 48 KB instead of 64 KB (4 stages instead of 3) and the B operand is
-// fetched once per pair -- the large-K convs are bound by operand feed, not by the tensor pipe.
-template <int BN, bool PAIR = false>
+template <int BN>
 struct Smem {
-    static constexpr int NST = (PAIR || BN <= 64) ? 4 : STAGES;   // 48 KB stages (BN <= 64) leave room for a 4th
+    static constexpr int NST = (BN <= 64) ? 4 : STAGES;   // 48 KB stages (BN <= 64) leave room for a 4th
     static constexpr int A_PLANE = BM * BKC * 2;          // 16 KB
-    static constexpr int B_PLANE = (PAIR ? BN / 2 : BN) * BKC * 2;
+    static constexpr int B_PLANE = BN * BKC * 2;
     static constexpr int STAGE = 2 * A_PLANE + 2 * B_PLANE;
     static constexpr int EPI_OFF = NST * STAGE;                       // 8 warp-private epilogue staging buffers
     static constexpr int BAR_OFF = EPI_OFF + 8 * 32 * STAGE_PITCH;
@@ -239,15 +186,14 @@ struct Smem {
     static constexpr int TMEM_COLS = 4 * BN;        // 2 hi*hi segment accumulators + 2 cross accumulators (128..512)
 };
 
-template <int BN, bool PAIR>
+template <int BN>
 __global__ void __launch_bounds__(NTHREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const TcArgs a) {
-    using S = Smem<BN, PAIR>;
+    using S = Smem<BN>;
     constexpr int NST = S::NST;
     pdl_trigger();
-    const uint32_t rank = PAIR ? cluster_rank() : 0u;                 // 0 = leader of the pair
-    const int tile0 = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-    const int tstride = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int tile0 = (int)blockIdx.x;
+    const int tstride = (int)gridDim.x;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
@@ -274,36 +220,28 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < NST; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(afull_bar + i, 1); mbar_init(aempty_bar + i, 1); }
-        // accumulator hand-back: 8 epilogue warps per CTA arrive (for a pair: on the leader's barriers, 16 arrivals)
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < 2; ++i) {               // accumulator hand-back: the 8 epilogue warps arrive
             mbar_init(tfull_bar + i, 1);
-            mbar_init(tempty_bar + i, PAIR ? 16 : 8);
-            mbar_init(cempty_bar + i, PAIR ? 16 : 8);
+            mbar_init(tempty_bar + i, 8);
+            mbar_init(cempty_bar + i, 8);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
-        if (PAIR) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                         "r"((uint32_t)S::TMEM_COLS)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
-        } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                         "r"((uint32_t)S::TMEM_COLS)
-                         : "memory");
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-        }
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
-    if (PAIR) cluster_sync_all(); else __syncthreads();      // barriers initialised in both CTAs before any remote signal
+    __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();                                              // everything below reads / writes activations
 
     if (warp == 0) {
         // =============================== TMA producer ===============================
-        if (lane == 0 && !PAIR && a.dxr) {
+        if (lane == 0 && a.dxr) {
             // 3x3 conv, one output row of 128 pixels per tile: per (dy, channel chunk) ONE box of 130 input pixels,
             // then the three weight tiles of that (dy, chunk)
             int ast = 0, bst = 0;
@@ -338,15 +276,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = tile0; tile < a.num_tiles; tile += tstride) {
-                const int mtp = tile / a.n_tiles, nt = tile - mtp * a.n_tiles;
-                const int mt = PAIR ? mtp * 2 + (int)rank : mtp;
+                const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
                 int valid_rows = 1, row0 = 0, wo0 = 0;
                 if (a.mode == 1) {
                     const int rg = mt / a.wsegs;
                     wo0 = (mt - rg * a.wsegs) * a.tw;
                     row0 = rg * a.rows_per_tile;
-                    // a pair always loads full tiles (rows past the end are out-of-bounds boxes: zero fill, full byte count)
-                    valid_rows = PAIR ? a.rows_per_tile : min(a.rows_per_tile, a.M - row0);
+                    valid_rows = min(a.rows_per_tile, a.M - row0);
                 }
                 // a row box always delivers the full tile (rows past the end are out-of-bounds zero fill, full byte count)
                 const uint32_t a_bytes = (a.mode == 0) ? 2u * S::A_PLANE
@@ -357,65 +293,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     uint8_t* sB = sA + 2 * S::A_PLANE;
                     const int tap = kc / a.kc_per_tap;
                     const int c0 = (kc - tap * a.kc_per_tap) * BKC;
-                    if (!PAIR) {
-                        mbar_expect_tx(full_bar + stage, a_bytes + 2u * S::B_PLANE);
-                        if (a.mode == 0) {
-                            tma_load_3d(sA, &tmA, full_bar + stage, c0, mt * BM, 0);
-                            tma_load_3d(sA + S::A_PLANE, &tmA, full_bar + stage, c0, mt * BM, 1);
-                        } else {
-                            const int dy = tap / a.kw, dx = tap - dy * a.kw;
-                            // rowbox: the tile's output rows map to consecutive input rows of one image: one box per plane
-                            // (small per-row boxes cost tensor-pipe time: 31 % on the W=32 layers vs 55-60 % on W>=128)
-                            const int nbox = a.rowbox ? 1 : valid_rows;
-                            for (int rr = 0; rr < nbox; ++rr) {
-                                const int R = row0 + rr;
-                                const int b = R / a.Ho, ho = R - b * a.Ho;
-                                const int hin = ho * a.sh + dy - a.ph;
-                                uint8_t* dst = sA + rr * a.tw * (BKC * 2);
-                                if (a.parity) {
-                                    const int p = dx + a.woff;
-                                    tma_load_5d(dst, &tmA, full_bar + stage, c0, p & 1, wo0 + (p >> 1), hin, b);
-                                    tma_load_5d(dst + S::A_PLANE, &tmA, full_bar + stage, c0, p & 1, wo0 + (p >> 1), hin,
-                                                a.Bimg + b);
-                                } else {
-                                    tma_load_4d(dst, &tmA, full_bar + stage, c0, wo0 + dx + a.woff, hin, b);
-                                    tma_load_4d(dst + S::A_PLANE, &tmA, full_bar + stage, c0, wo0 + dx + a.woff, hin,
-                                                a.Bimg + b);
-                                }
-                            }
-                        }
-                        tma_load_3d(sB, &tmB, full_bar + stage, kc * BKC, nt * BN, 0);
-                        tma_load_3d(sB + S::B_PLANE, &tmB, full_bar + stage, kc * BKC, nt * BN, 1);
+                    mbar_expect_tx(full_bar + stage, a_bytes + 2u * S::B_PLANE);
+                    if (a.mode == 0) {
+                        tma_load_3d(sA, &tmA, full_bar + stage, c0, mt * BM, 0);
+                        tma_load_3d(sA + S::A_PLANE, &tmA, full_bar + stage, c0, mt * BM, 1);
                     } else {
-                        // all bytes of both CTAs are counted on the LEADER's barrier (it issues the MMAs for the pair)
-                        const uint32_t fb = map_to_cta(smem_u32(full_bar + stage), 0);
-                        if (rank == 0) mbar_expect_tx(full_bar + stage, 2u * (2u * S::A_PLANE + 2u * S::B_PLANE));
-                        if (a.mode == 0) {
-                            tma2_load_3d(sA, &tmA, fb, c0, mt * BM, 0);
-                            tma2_load_3d(sA + S::A_PLANE, &tmA, fb, c0, mt * BM, 1);
-                        } else {
-                            const int dy = tap / a.kw, dx = tap - dy * a.kw;
-                            for (int rr = 0; rr < valid_rows; ++rr) {
-                                const int R = row0 + rr;
-                                const int b = R / a.Ho, ho = R - b * a.Ho;
-                                const int hin = ho * a.sh + dy - a.ph;
-                                uint8_t* dst = sA + rr * a.tw * (BKC * 2);
-                                // rows past the end: b >= Bimg; keep the lo-plane coordinate out of bounds as well
-                                const int bl = (b < a.Bimg) ? a.Bimg + b : 2 * a.Bimg + b;
-                                if (a.parity) {
-                                    const int p = dx + a.woff;
-                                    tma2_load_5d(dst, &tmA, fb, c0, p & 1, wo0 + (p >> 1), hin, b < a.Bimg ? b : 2 * a.Bimg + b);
-                                    tma2_load_5d(dst + S::A_PLANE, &tmA, fb, c0, p & 1, wo0 + (p >> 1), hin, bl);
-                                } else {
-                                    tma2_load_4d(dst, &tmA, fb, c0, wo0 + dx + a.woff, hin, b < a.Bimg ? b : 2 * a.Bimg + b);
-                                    tma2_load_4d(dst + S::A_PLANE, &tmA, fb, c0, wo0 + dx + a.woff, hin, bl);
-                                }
+                        const int dy = tap / a.kw, dx = tap - dy * a.kw;
+                        // rowbox: the tile's output rows map to consecutive input rows of one image: one box per plane
+                        // (small per-row boxes cost tensor-pipe time: 31 % on the W=32 layers vs 55-60 % on W>=128)
+                        const int nbox = a.rowbox ? 1 : valid_rows;
+                        for (int rr = 0; rr < nbox; ++rr) {
+                            const int R = row0 + rr;
+                            const int b = R / a.Ho, ho = R - b * a.Ho;
+                            const int hin = ho * a.sh + dy - a.ph;
+                            uint8_t* dst = sA + rr * a.tw * (BKC * 2);
+                            if (a.parity) {
+                                const int p = dx + a.woff;
+                                tma_load_5d(dst, &tmA, full_bar + stage, c0, p & 1, wo0 + (p >> 1), hin, b);
+                                tma_load_5d(dst + S::A_PLANE, &tmA, full_bar + stage, c0, p & 1, wo0 + (p >> 1), hin,
+                                            a.Bimg + b);
+                            } else {
+                                tma_load_4d(dst, &tmA, full_bar + stage, c0, wo0 + dx + a.woff, hin, b);
+                                tma_load_4d(dst + S::A_PLANE, &tmA, full_bar + stage, c0, wo0 + dx + a.woff, hin,
+                                            a.Bimg + b);
                             }
                         }
-                        const int nrow = nt * BN + (int)rank * (BN / 2);       // this CTA stages its half of the B rows
-                        tma2_load_3d(sB, &tmB, fb, kc * BKC, nrow, 0);
-                        tma2_load_3d(sB + S::B_PLANE, &tmB, fb, kc * BKC, nrow, 1);
                     }
+                    tma_load_3d(sB, &tmB, full_bar + stage, kc * BKC, nt * BN, 0);
+                    tma_load_3d(sB + S::B_PLANE, &tmB, full_bar + stage, kc * BKC, nt * BN, 1);
                     if (++stage == NST) { stage = 0; phase ^= 1; }
                 }
             }
@@ -427,7 +332,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // end.  So (1) the small cross products (hi*lo, lo*hi; 2^-11 of the result) get their own
         // accumulator, and (2) the hi*hi accumulator is restarted every `seg` K-chunks: the epilogue
         // warps drain each segment and add it to a register-resident fp32 sum with round-to-nearest.
-        if (lane == 0 && !PAIR && a.dxr) {
+        if (lane == 0 && a.dxr) {
             constexpr uint32_t idesc = umma_idesc(BN, 0, 0, BM);
             int ast = 0, bst = 0;
             uint32_t aph = 0, bph = 0;
@@ -479,8 +384,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (++ast == 2) { ast = 0; aph ^= 1; }
                 }
             }
-        } else if (lane == 0 && rank == 0) {                       // for a pair only the leader issues MMAs
-            constexpr uint32_t idesc = umma_idesc(BN, 0, 0, PAIR ? 2 * BM : BM);       // fp16 x fp16 -> fp32
+        } else if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(BN, 0, 0, BM);       // fp16 x fp16 -> fp32
             int stage = 0;
             uint32_t phase = 0;
             int it = 0, g = 0;
@@ -507,21 +412,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < BKC / 16; ++k) {
                         const uint64_t ko = (uint64_t)((k * 16 * 2) >> 4);     // advance 32 B inside the swizzle row
-                        if (PAIR) {
-                            umma2_f16(d_main, a_hi + ko, b_hi + ko, idesc, (seg_pos | k) != 0);
-                            umma2_f16(d_cross, a_hi + ko, b_lo + ko, idesc, (kc | k) != 0);
-                            umma2_f16(d_cross, a_lo + ko, b_hi + ko, idesc, 1);
-                        } else {
-                            umma_f16(d_main, a_hi + ko, b_hi + ko, idesc, (seg_pos | k) != 0);
-                            umma_f16(d_cross, a_hi + ko, b_lo + ko, idesc, (kc | k) != 0);
-                            umma_f16(d_cross, a_lo + ko, b_hi + ko, idesc, 1);
-                        }
+                        umma_f16(d_main, a_hi + ko, b_hi + ko, idesc, (seg_pos | k) != 0);
+                        umma_f16(d_cross, a_hi + ko, b_lo + ko, idesc, (kc | k) != 0);
+                        umma_f16(d_cross, a_lo + ko, b_hi + ko, idesc, 1);
                     }
-                    // frees the smem stage (in both CTAs of a pair) when the MMAs retire
-                    if (PAIR) umma2_commit(empty_bar + stage); else umma_commit(empty_bar + stage);
+                    umma_commit(empty_bar + stage);               // frees the smem stage when the MMAs retire
                     if (++seg_pos == a.seg || kc == a.num_kc - 1) {
-                        // segment (and, at the end, the tile) complete
-                        if (PAIR) umma2_commit(tfull_bar + mbuf); else umma_commit(tfull_bar + mbuf);
+                        umma_commit(tfull_bar + mbuf);            // segment (and, at the end, the tile) complete
                         seg_pos = 0;
                         ++g;
                     }
@@ -541,13 +438,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         uint8_t* stage = smem + S::EPI_OFF + (warp - EPI_WARP0) * 32 * STAGE_PITCH;
         const int nseg = (a.num_kc + a.seg - 1) / a.seg;
-        // accumulators are handed back on the leader's barriers (remote arrive for the peer CTA)
-        const uint32_t tempty_l[2] = {map_to_cta(smem_u32(tempty_bar), 0), map_to_cta(smem_u32(tempty_bar + 1), 0)};
-        const uint32_t cempty_l[2] = {map_to_cta(smem_u32(cempty_bar), 0), map_to_cta(smem_u32(cempty_bar + 1), 0)};
         int it = 0, g = 0;
         for (int tile = tile0; tile < a.num_tiles; tile += tstride, ++it) {
-            const int mtp = tile / a.n_tiles, nt = tile - mtp * a.n_tiles;
-            const int mt = PAIR ? mtp * 2 + (int)rank : mtp;
+            const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
             const int cbuf = it & 1;
             const int r = q * 32 + lane;                 // accumulator row = pixel of the tile
             // ---- where does this row live in the output?
@@ -589,7 +482,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) { if (PAIR) mbar_arrive_cluster(tempty_l[mbuf]); else mbar_arrive(tempty_bar + mbuf); }
+                if (lane == 0) mbar_arrive(tempty_bar + mbuf);
             }
             // ---- the last segment's commit also covers the cross products of the whole tile.
             // Global traffic of the epilogue is routed through a warp-private staging buffer so that
@@ -699,19 +592,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // cross accumulator drained: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) { if (PAIR) mbar_arrive_cluster(cempty_l[cbuf]); else mbar_arrive(cempty_bar + cbuf); }
+            if (lane == 0) mbar_arrive(cempty_bar + cbuf);
         }
     }
 
     tc_fence_before();
-    if (PAIR) cluster_sync_all(); else __syncthreads();      // nobody leaves while the peer may still signal / read
+    __syncthreads();
     if (warp == 2) {
-        if (PAIR)
-            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
-                         : "memory");
-        else
-            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
-                         : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)S::TMEM_COLS)
+                     : "memory");
     }
 }
 
@@ -735,7 +624,9 @@ struct GSmem {
     static constexpr int EBUF = 2 * E_PLANE;              // hi + lo
     static constexpr int EPI_OFF = STAGES * STAGE;        // 144 KB
     static constexpr int BAR_OFF = EPI_OFF + 2 * EBUF;    // 208 KB
-    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+    static constexpr int CST_OFF = BAR_OFF + 256;         // epilogue constants scale[Cout] shift[Cout], Cout <= 1024
+    static constexpr int MAX_COUT = 1024;
+    static constexpr int TOTAL = CST_OFF + 2 * MAX_COUT * 4 + 1024;
     static constexpr int TMEM_COLS = 4 * GBN;
 };
 
@@ -784,6 +675,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // epilogue constants -> shared memory (the per-tile __ldg of scale / shift miss L1 after every fence.proxy.async: ncu showed
+    // them as the top stall of the conv3 epilogue; weights-side data, safe to read before pdl_wait)
+    float* cst = reinterpret_cast<float*>(smem + S::CST_OFF);
+    for (int i = threadIdx.x; i < 2 * a.Cout; i += NTHREADS) cst[i] = (i < a.Cout) ? a.scale[i] : a.shift[i - a.Cout];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -904,8 +799,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int n0 = nt * GBN + half * 32;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-                const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + n0 + j));
-                const float4 sf = __ldg(reinterpret_cast<const float4*>(a.shift + n0 + j));
+                const float4 sc = *reinterpret_cast<const float4*>(cst + n0 + j);
+                const float4 sf = *reinterpret_cast<const float4*>(cst + a.Cout + n0 + j);
                 sum[j + 0] = fmaf(sum[j + 0], sc.x, sf.x);
                 sum[j + 1] = fmaf(sum[j + 1], sc.y, sf.y);
                 sum[j + 2] = fmaf(sum[j + 2], sc.z, sf.z);
@@ -915,13 +810,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(rfull_bar + eb, (it >> 1) & 1);
             const uint32_t e_hi = smem_u32(smem + S::EPI_OFF + eb * S::EBUF) + r * 128;
             const uint32_t e_lo = e_hi + S::E_PLANE;
+            uint4 rh[4], rl[4];                          // all residual loads in flight before the first use
+            if (has_res) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t off = (uint32_t)(((half * 4 + c) ^ (r & 7)) << 4);
+                    rh[c] = ld_shared_v4(e_hi + off);
+                    rl[c] = ld_shared_v4(e_lo + off);
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 const uint32_t off = (uint32_t)(((half * 4 + c) ^ (r & 7)) << 4);
                 float* y = sum + c * 8;
                 if (has_res) {
-                    const uint4 h = ld_shared_v4(e_hi + off), l = ld_shared_v4(e_lo + off);
-                    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+                    const uint32_t hw[4] = {rh[c].x, rh[c].y, rh[c].z, rh[c].w}, lw[4] = {rl[c].x, rl[c].y, rl[c].z, rl[c].w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float2 fh = unpack_half2(hw[e]), fl = unpack_half2(lw[e]);
@@ -1279,7 +1182,8 @@ struct BtSmem {
     static constexpr int E_PLANE = BM * 64 * 2;           // 16 KB
     static constexpr int EBUF = 2 * E_PLANE;
     static constexpr int BAR_OFF = E_OFF + 2 * EBUF;      // 212 KB
-    static constexpr int TOTAL = BAR_OFF + 512 + 1024;
+    static constexpr int CST_OFF = BAR_OFF + 512;         // epilogue constants: scale2[64] shift2[64] scale3[C3] shift3[C3] (C3 <= 512)
+    static constexpr int TOTAL = CST_OFF + (128 + 2 * 512) * 4 + 1024;
     static constexpr int TMEM_COLS = 512;                 // c2: 2 main + 2 cross, c3: 2 main + 2 cross accumulators of 64 columns
 };
 static_assert(BtSmem::T2_OFF % 1024 == 0 && BtSmem::E_OFF % 1024 == 0 && BtSmem::B_OFF % 1024 == 0, "swizzle atoms need 1024-byte alignment");
@@ -1333,6 +1237,11 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    // epilogue constants -> shared memory (ncu: the per-tile __ldg of scale / shift cost the conv3 epilogue 20 % of its time --
+    // they miss L1 after every fence.proxy.async; weights-side data, safe to read before pdl_wait)
+    float* cst = reinterpret_cast<float*>(smem + S::CST_OFF);
+    for (int i = threadIdx.x; i < 128 + 2 * a.C3; i += NTHREADS)
+        cst[i] = (i < 64) ? a.scale2[i] : (i < 128) ? a.shift2[i - 64] : (i < 128 + a.C3) ? a.scale3[i - 128] : a.shift3[i - 128 - a.C3];
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -1546,8 +1455,8 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int n0 = j * 64 + half * 32;
 #pragma unroll
                 for (int jj = 0; jj < 32; jj += 4) {
-                    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale3 + n0 + jj));
-                    const float4 sf = __ldg(reinterpret_cast<const float4*>(a.shift3 + n0 + jj));
+                    const float4 sc = *reinterpret_cast<const float4*>(cst + 128 + n0 + jj);
+                    const float4 sf = *reinterpret_cast<const float4*>(cst + 128 + a.C3 + n0 + jj);
                     sum[jj + 0] = fmaf(sum[jj + 0], sc.x, sf.x);
                     sum[jj + 1] = fmaf(sum[jj + 1], sc.y, sf.y);
                     sum[jj + 2] = fmaf(sum[jj + 2], sc.z, sf.z);
@@ -1557,12 +1466,18 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t e_hi = smem_u32(smem + S::E_OFF + eb * S::EBUF) + r * 128;
                 const uint32_t e_lo = e_hi + S::E_PLANE;
                 unsigned short* hrow = (halo_pix >= 0) ? a.out + (size_t)halo_pix * a.C3 + n0 : nullptr;
+                uint4 rh[4], rl[4];                      // all eight 16-byte residual loads in flight before the first use
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint32_t off = (uint32_t)(((half * 4 + c) ^ (r & 7)) << 4);
+                    rh[c] = ld_shared_v4(e_hi + off);
+                    rl[c] = ld_shared_v4(e_lo + off);
+                }
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const uint32_t off = (uint32_t)(((half * 4 + c) ^ (r & 7)) << 4);
                     float* y = sum + c * 8;
-                    const uint4 h = ld_shared_v4(e_hi + off), l = ld_shared_v4(e_lo + off);
-                    const uint32_t hw[4] = {h.x, h.y, h.z, h.w}, lw[4] = {l.x, l.y, l.z, l.w};
+                    const uint32_t hw[4] = {rh[c].x, rh[c].y, rh[c].z, rh[c].w}, lw[4] = {rl[c].x, rl[c].y, rl[c].z, rl[c].w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         const float2 fh = unpack_half2(hw[e]), fl = unpack_half2(lw[e]);
@@ -1613,8 +1528,8 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) mbar_arrive(cempty_bar + cbuf);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale2 + half * 32 + j));
-                    const float4 sf = __ldg(reinterpret_cast<const float4*>(a.shift2 + half * 32 + j));
+                    const float4 sc = *reinterpret_cast<const float4*>(cst + half * 32 + j);
+                    const float4 sf = *reinterpret_cast<const float4*>(cst + 64 + half * 32 + j);
                     y2[j + 0] = fmaxf(fmaf(y2[j + 0] + __uint_as_float(v[j + 0]), sc.x, sf.x), 0.f);
                     y2[j + 1] = fmaxf(fmaf(y2[j + 1] + __uint_as_float(v[j + 1]), sc.y, sf.y), 0.f);
                     y2[j + 2] = fmaxf(fmaf(y2[j + 2] + __uint_as_float(v[j + 2]), sc.z, sf.z), 0.f);
@@ -1713,35 +1628,13 @@ cudaError_t launch_tc(K kernel, int grid, size_t smem_bytes, cudaStream_t st, Ar
 
 template <int BN>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
-    using S = Smem<BN, false>;
-    HN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
+    using S = Smem<BN>;
+    HN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
     int dev = 0, sms = 0;
     HN_CUDA_OK(cudaGetDevice(&dev));
     HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const int grid = a.num_tiles < sms ? a.num_tiles : sms;
-    HN_CUDA_OK(launch_tc(conv_tc_kernel<BN, false>, grid, S::TOTAL, st, tmA, tmB, a));
-    HN_LAUNCH_OK();
-    return 0;
-}
-
-// CTA-pair launch: a.num_tiles counts PAIR tiles (256 rows x 128 channels); clusters of 2 CTAs
-int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
-    using S = Smem<128, true>;
-    HN_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL));
-    int dev = 0, sms = 0;
-    HN_CUDA_OK(cudaGetDevice(&dev));
-    HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    const int pairs = a.num_tiles < sms / 2 ? a.num_tiles : sms / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(NTHREADS);
-    cfg.dynamicSmemBytes = S::TOTAL;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
-    HN_CUDA_OK(cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, true>, tmA, tmB, a));
+    HN_CUDA_OK(launch_tc(conv_tc_kernel<BN>, grid, S::TOTAL, st, tmA, tmB, a));
     HN_LAUNCH_OK();
     return 0;
 }
@@ -1801,7 +1694,7 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
     long long m_tiles;
     // asynchronous-epilogue GEMM kernel: plane output, K <= 512, Cout a multiple of 64
     static const bool gemm_kernel_on = [] { const char* e = getenv("HN_TC_GEMM"); return !(e && atoi(e) == 0); }();
-    const bool use_gemm_kernel = gemm && gemm_kernel_on && !out_f32 && d.Cin <= 256 && d.Cout % GBN == 0;
+    const bool use_gemm_kernel = gemm && gemm_kernel_on && !out_f32 && d.Cin <= 256 && d.Cout % GBN == 0 && d.Cout <= GSmem::MAX_COUT;
     if (use_gemm_kernel) {
         const long long Mtot = (long long)in.B * in.H * in.Wp();
         a.mode = 0;
@@ -1876,12 +1769,7 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
         const int hs = (a.rowbox && d.sh == 2) ? 2 : 1;
         const cuuint64_t C2 = (cuuint64_t)d.Cin * 2, Wp = in.Wp();
         // dx reuse (HN_TC_DXR=0 disables)
-        static const int dxr_mode = [] {
-            const char* p = getenv("HN_TC_PAIR");
-            if (p && atoi(p) == 1) return 0;                       // the CTA-pair experiment keeps per-tap boxes
-            const char* e = getenv("HN_TC_DXR");
-            return e ? atoi(e) : 1;
-        }();
+        static const int dxr_mode = [] { const char* e = getenv("HN_TC_DXR"); return e ? atoi(e) : 1; }();
         a.dxr = (dxr_mode != 0 && !a.parity && d.kw == 3 && a.rows_per_tile == 1 && a.tw == BM &&
                  (long long)a.wsegs * BM + a.woff + 2 <= (long long)Wp) ? 1 : 0;
         if (!a.parity) {
@@ -1900,21 +1788,9 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
     HN_CHECK(m_tiles * a.n_tiles < (1ll << 31), "conv_tc: too many tiles");
     a.num_tiles = (int)(m_tiles * a.n_tiles);
     if (a.num_tiles == 0) return 0;
-    // CTA pairs (cta_group::2, M = 256 per pair).  Correct (unit tests run it with HN_TC_PAIR=1) but measured 5-25 %
-    // SLOWER than single-CTA tiles on every layer of this net: the large-K convs are bound by shared-memory
-    // bandwidth (three products re-read the same 128x64 tiles: 96 KB of MMA operand reads + 64 KB of TMA fill
-    // per 768-cycle chunk = 213 B/clk against 128 B/clk => ~60 % tensor pipe, which is what ncu shows), and in a
-    // pair each SM still serves its B half to both tensor cores, so only the L2 fill is halved.  Off by default.
-    static const bool pair_on = [] { const char* e = getenv("HN_TC_PAIR"); return e && atoi(e) == 1; }();
-    if (pair_on && BN == 128 && a.num_kc >= 8 && m_tiles >= 2) {
-        cuuint64_t dims[3] = {(cuuint64_t)K, (cuuint64_t)d.Cout, 2};
-        cuuint64_t str[2] = {(cuuint64_t)K * 2, (cuuint64_t)K * d.Cout * 2};
-        cuuint32_t box[3] = {BKC, 64, 1};                          // each CTA of the pair stages 64 of the 128 B rows
-        if (make_map(&tmB, wq, 3, dims, str, box)) return -1;
-        a.num_tiles = (int)(((m_tiles + 1) / 2) * a.n_tiles);
-        HN_CHECK(!a.rowbox, "conv_tc: the CTA-pair experiment needs HN_TC_ROWBOX=0");
-        return launch_pair(tmA, tmB, a, st);
-    }
+    // (CTA pairs -- cta_group::2, M = 256 per pair, B operand fetched once per pair -- were implemented, verified and measured
+    // 5-25 % SLOWER than single-CTA tiles on every layer of this net in round 1 (each SM still serves its B half to both tensor
+    // cores; only the L2 fill is halved); the variant was deleted in round 2)
     switch (BN) {
         case 128: return launch<128>(tmA, tmB, a, st);
         case 64: return launch<64>(tmA, tmB, a, st);

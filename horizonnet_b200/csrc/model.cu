@@ -38,6 +38,8 @@ int tta_merge(const float* bon, const float* cor, int V, const int* modes_dev, c
               float* y_cor, cudaStream_t st);
 int pano_stretch_device(const float* img, float* out, int n, int H, int W, int C, const double* kx_dev,
                         const double* ky_dev, double* scratch, int order, cudaStream_t st);
+int pano_stretch_device_f64(const double* img, double* out, int n, int H, int W, int C, const double* kx_dev,
+                            const double* ky_dev, double* scratch, int order, cudaStream_t st);
 int augment_device(const unsigned char* img, float* out, int n, int H, int W, const double* kx_dev, const double* ky_dev,
                    const int* params_dev, double* scratch, cudaStream_t st);
 int rotate_panorama_device(const void* img, int in_f64, double* out, int n, int H, int W, int C, const double* rinv,
@@ -871,44 +873,65 @@ int hn_model_stage(hn_model* m, const char* stage, float* out, long long capacit
 void hn_model_destroy(hn_model* m) { delete m; }
 
 // ---- pano_stretch ------------------------------------------------------------------------------
-int hn_pano_stretch(const float* img, float* out, int n, int h, int w, int c, const double* kx, const double* ky,
-                    int order, void* stream) {
-    HN_CHECK(n >= 0 && h >= 1 && w >= 1, "hn_pano_stretch: bad geometry");
+static int pano_stretch_any(const void* img, void* out, int f64, int n, int h, int w, int c, const double* kx, const double* ky,
+                            int order, void* stream, const char* who) {
+    if (!(n >= 0 && h >= 1 && w >= 1)) return fail(std::string(who) + ": bad geometry");
     if (n == 0) return 0;
-    HN_CHECK(img && out && kx && ky, "hn_pano_stretch: NULL argument");
+    if (!(img && out && kx && ky)) return fail(std::string(who) + ": NULL argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-        return fail("hn_pano_stretch: no CUDA device -- libhorizonnet_b200 has no CPU path");
-    for (int i = 0; i < n; ++i) HN_CHECK(kx[i] > 0 && ky[i] > 0, "hn_pano_stretch: kx, ky must be positive");
+        return fail(std::string(who) + ": no CUDA device -- libhorizonnet_b200 has no CPU path");
+    for (int i = 0; i < n; ++i)
+        if (!(kx[i] > 0 && ky[i] > 0)) return fail(std::string(who) + ": kx, ky must be positive");
     cudaStream_t st = (cudaStream_t)stream;
     double* scratch = nullptr;
     const size_t nd = (size_t)2 * n + (size_t)4 * n * w + h;
     HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&scratch), nd * sizeof(double), st));
     HN_CUDA_OK(cudaMemcpyAsync(scratch, kx, n * sizeof(double), cudaMemcpyHostToDevice, st));
     HN_CUDA_OK(cudaMemcpyAsync(scratch + n, ky, n * sizeof(double), cudaMemcpyHostToDevice, st));
-    int rc = pano_stretch_device(img, out, n, h, w, c, scratch, scratch + n, scratch + 2 * (size_t)n, order, st);
+    int rc = f64 ? pano_stretch_device_f64(static_cast<const double*>(img), static_cast<double*>(out), n, h, w, c, scratch,
+                                           scratch + n, scratch + 2 * (size_t)n, order, st)
+                 : pano_stretch_device(static_cast<const float*>(img), static_cast<float*>(out), n, h, w, c, scratch,
+                                       scratch + n, scratch + 2 * (size_t)n, order, st);
     cudaFreeAsync(scratch, st);
     return rc;
 }
 
-int hn_pano_stretch_host(const float* img, float* out, int n, int h, int w, int c, const double* kx,
-                         const double* ky, int order) {
+static int pano_stretch_any_host(const void* img, void* out, int f64, int n, int h, int w, int c, const double* kx,
+                                 const double* ky, int order, const char* who) {
     if (n == 0) return 0;
-    HN_CHECK(img && out && kx && ky, "hn_pano_stretch_host: NULL argument");
+    if (!(img && out && kx && ky)) return fail(std::string(who) + ": NULL argument");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
-        return fail("hn_pano_stretch_host: no CUDA device -- libhorizonnet_b200 has no CPU path");
-    const size_t bytes = (size_t)n * h * w * c * sizeof(float);
-    float *d_in = nullptr, *d_out = nullptr;
-    HN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(&d_in), bytes));
-    if (cudaMalloc(reinterpret_cast<void**>(&d_out), bytes) != cudaSuccess) { cudaFree(d_in); return fail("hn_pano_stretch_host: out of memory"); }
+        return fail(std::string(who) + ": no CUDA device -- libhorizonnet_b200 has no CPU path");
+    const size_t bytes = (size_t)n * h * w * c * (f64 ? sizeof(double) : sizeof(float));
+    void *d_in = nullptr, *d_out = nullptr;
+    HN_CUDA_OK(cudaMalloc(&d_in, bytes));
+    if (cudaMalloc(&d_out, bytes) != cudaSuccess) { cudaFree(d_in); return fail(std::string(who) + ": out of memory"); }
     int rc = 0;
-    if (cudaMemcpy(d_in, img, bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail("hn_pano_stretch_host: H2D failed");
-    if (!rc) rc = hn_pano_stretch(d_in, d_out, n, h, w, c, kx, ky, order, nullptr);
-    if (!rc && cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail("hn_pano_stretch_host: D2H failed");
+    if (cudaMemcpy(d_in, img, bytes, cudaMemcpyHostToDevice) != cudaSuccess) rc = fail(std::string(who) + ": H2D failed");
+    if (!rc) rc = pano_stretch_any(d_in, d_out, f64, n, h, w, c, kx, ky, order, nullptr, who);
+    if (!rc && cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) rc = fail(std::string(who) + ": D2H failed");
     cudaFree(d_in);
     cudaFree(d_out);
     return rc;
+}
+
+int hn_pano_stretch(const float* img, float* out, int n, int h, int w, int c, const double* kx, const double* ky,
+                    int order, void* stream) {
+    return pano_stretch_any(img, out, 0, n, h, w, c, kx, ky, order, stream, "hn_pano_stretch");
+}
+int hn_pano_stretch_host(const float* img, float* out, int n, int h, int w, int c, const double* kx,
+                         const double* ky, int order) {
+    return pano_stretch_any_host(img, out, 0, n, h, w, c, kx, ky, order, "hn_pano_stretch_host");
+}
+int hn_pano_stretch_f64(const double* img, double* out, int n, int h, int w, int c, const double* kx, const double* ky,
+                        int order, void* stream) {
+    return pano_stretch_any(img, out, 1, n, h, w, c, kx, ky, order, stream, "hn_pano_stretch_f64");
+}
+int hn_pano_stretch_host_f64(const double* img, double* out, int n, int h, int w, int c, const double* kx,
+                             const double* ky, int order) {
+    return pano_stretch_any_host(img, out, 1, n, h, w, c, kx, ky, order, "hn_pano_stretch_host_f64");
 }
 
 // ---- training augmentation, image path (reference dataset.py:53, 69-105, 124) ----------------------

@@ -108,8 +108,8 @@ __device__ __forceinline__ int nearest_row(double cy, int H, int W) {
 // u(W-1-x) = -u(x) and v(H-1-y) = -v(y), so g is even in the column and v0 is odd in the row: one fp64
 // atan serves four pixels.  ncu showed the kernel latency-bound (long-scoreboard stalls on the gathers, 30 %
 // DRAM), so all taps of the four pixels (4 x 4 x C loads) are issued back to back before any blending.
-template <int C>
-__global__ void __launch_bounds__(128) stretch_kernel(const float* __restrict__ img, float* __restrict__ out,
+template <int C, typename T>
+__global__ void __launch_bounds__(128) stretch_kernel(const T* __restrict__ img, T* __restrict__ out,
                                                       const ColEntry* __restrict__ cols,
                                                       const double* __restrict__ tanv, int H, int W, int order) {
     const int x = blockIdx.x * 128 + threadIdx.x;
@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(128) stretch_kernel(const float* __restrict__ 
     const int xm = W - 1 - x;
     if (x > xm) return;
     const size_t plane = (size_t)H * W * C;
-    const float* src = img + (size_t)n * plane;
-    float* dst = out + (size_t)n * plane;
+    const T* src = img + (size_t)n * plane;
+    T* dst = out + (size_t)n * plane;
     const ColEntry* ce = cols + (size_t)n * W;
     const ColEntry e[2] = {ce[x], ce[xm]};
     const double v0 = atan(tanv[y] * e[0].g);                                    // panostretch.py:93
@@ -137,15 +137,15 @@ __global__ void __launch_bounds__(128) stretch_kernel(const float* __restrict__ 
                 for (int c = 0; c < C; ++c) dst[orow[vt] + ocol[sd] + c] = __ldg(src + rn[vt] + e[sd].xn * C + c);
         return;
     }
-    float tap[2][2][4][C];                       // [side][vert][tap][channel]
+    T tap[2][2][4][C];                           // [side][vert][tap][channel]
 #pragma unroll
     for (int sd = 0; sd < 2; ++sd)
 #pragma unroll
         for (int vt = 0; vt < 2; ++vt) {
-            const float* p00 = src + rt[vt].r0 + e[sd].x0 * C;
-            const float* p01 = src + rt[vt].r0 + e[sd].x1 * C;
-            const float* p10 = src + rt[vt].r1 + e[sd].x0 * C;
-            const float* p11 = src + rt[vt].r1 + e[sd].x1 * C;
+            const T* p00 = src + rt[vt].r0 + e[sd].x0 * C;
+            const T* p01 = src + rt[vt].r0 + e[sd].x1 * C;
+            const T* p10 = src + rt[vt].r1 + e[sd].x0 * C;
+            const T* p11 = src + rt[vt].r1 + e[sd].x1 * C;
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 tap[sd][vt][0][c] = __ldg(p00 + c);
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(128) stretch_kernel(const float* __restrict__ 
                 acc = fma(w01, (double)tap[sd][vt][1][c], acc);
                 acc = fma(w10, (double)tap[sd][vt][2][c], acc);
                 acc = fma(w11, (double)tap[sd][vt][3][c], acc);
-                dst[orow[vt] + ocol[sd] + c] = (float)acc;
+                dst[orow[vt] + ocol[sd] + c] = (T)acc;       // map_coordinates output dtype = input dtype
             }
         }
     }
@@ -275,8 +275,9 @@ __global__ void __launch_bounds__(128) augment_kernel(const unsigned char* __res
 
 // img/out: n images [H][W][C] fp32 on the device; kx/ky: n doubles on the device;
 // scratch: (4*n*W + H) doubles on the device (n*W ColEntry records of 32 bytes, then H doubles).
-int pano_stretch_device(const float* img, float* out, int n, int H, int W, int C, const double* kx_dev,
-                        const double* ky_dev, double* scratch, int order, cudaStream_t st) {
+template <typename T>
+static int pano_stretch_device_t(const T* img, T* out, int n, int H, int W, int C, const double* kx_dev,
+                                 const double* ky_dev, double* scratch, int order, cudaStream_t st) {
     HN_CHECK(order == 0 || order == 1, "pano_stretch: only order 0/1 are on the hot path (panostretch.py:86)");
     HN_CHECK(C >= 1 && C <= 4, "pano_stretch: 1..4 channels supported");
     HN_CHECK(n >= 0 && H >= 1 && W >= 1, "pano_stretch: bad geometry");
@@ -291,13 +292,23 @@ int pano_stretch_device(const float* img, float* out, int n, int H, int W, int C
     dim3 g(((W + 1) / 2 + 127) / 128, (H + 1) / 2, n);
     HN_CHECK(n <= 65535, "pano_stretch: at most 65535 images per call");
     switch (C) {
-        case 1: stretch_kernel<1><<<g, 128, 0, st>>>(img, out, cols, tanv, H, W, order); break;
-        case 2: stretch_kernel<2><<<g, 128, 0, st>>>(img, out, cols, tanv, H, W, order); break;
-        case 3: stretch_kernel<3><<<g, 128, 0, st>>>(img, out, cols, tanv, H, W, order); break;
-        default: stretch_kernel<4><<<g, 128, 0, st>>>(img, out, cols, tanv, H, W, order); break;
+        case 1: stretch_kernel<1, T><<<g, 128, 0, st>>>(img, out, cols, tanv, H, W, order); break;
+        case 2: stretch_kernel<2, T><<<g, 128, 0, st>>>(img, out, cols, tanv, H, W, order); break;
+        case 3: stretch_kernel<3, T><<<g, 128, 0, st>>>(img, out, cols, tanv, H, W, order); break;
+        default: stretch_kernel<4, T><<<g, 128, 0, st>>>(img, out, cols, tanv, H, W, order); break;
     }
     HN_LAUNCH_OK();
     return 0;
+}
+
+int pano_stretch_device(const float* img, float* out, int n, int H, int W, int C, const double* kx_dev,
+                        const double* ky_dev, double* scratch, int order, cudaStream_t st) {
+    return pano_stretch_device_t<float>(img, out, n, H, W, C, kx_dev, ky_dev, scratch, order, st);
+}
+// float64 images (the reference's CLI feeds float64 0-255, misc/panostretch.py:171): taps and result stay double
+int pano_stretch_device_f64(const double* img, double* out, int n, int H, int W, int C, const double* kx_dev,
+                            const double* ky_dev, double* scratch, int order, cudaStream_t st) {
+    return pano_stretch_device_t<double>(img, out, n, H, W, C, kx_dev, ky_dev, scratch, order, st);
 }
 
 // img: n uint8 images [H][W][3]; out: n float32 images [3][H][W]; kx/ky: n doubles on the device (entries of images without

@@ -136,6 +136,13 @@ int hn_pano_stretch(const float* img_dev, float* out_dev, int n, int h, int w, i
 int hn_pano_stretch_host(const float* img_host, float* out_host, int n, int h, int w, int c,
                          const double* kx_host, const double* ky_host, int order);
 
+/* float64 images (the reference's own CLI feeds float64 0-255, misc/panostretch.py:171): taps, blend and result in double,
+ * like scipy returns for a float64 input. */
+int hn_pano_stretch_f64(const double* img_dev, double* out_dev, int n, int h, int w, int c,
+                        const double* kx_host, const double* ky_host, int order, void* stream);
+int hn_pano_stretch_host_f64(const double* img_host, double* out_host, int n, int h, int w, int c,
+                             const double* kx_host, const double* ky_host, int order);
+
 /* ---- dataset.PanoCorBonDataset.__getitem__, image path (reference dataset.py:53, 69-105, 124) ------
  *
  * One fused gather pass per image:  uint8 HWC / 255 -> pano_stretch(kx, ky) -> flip -> roll(dx) -> ** gamma -> CHW:
