@@ -492,7 +492,7 @@ def run_ours(args):
         'kernel': 'conv implicit-GEMM family (%s)' % ('conv_igemm_f32, fp32 CUDA cores' if args.fp32 else 'conv_tc_kernel / gemm_tc_kernel, tcgen05 split-fp16 x3 products'),
         'bound': 'tensor', 'achieved': round(achieved, 3), 'peak': peaks['tf'], 'unit': 'TFLOP/s',
         'frac': round(achieved / peaks['tf'], 5), 'peak_source': peaks['src'] + ' bf16 dense, sustained',
-        'traffic': traffic, 'traffic_source': 'dram__bytes_read+write per launch (avg of the 70 conv launches), ncu --set full, see profiles/' if traffic else None,
+        'traffic': traffic, 'traffic_source': 'dram__bytes_read+write per launch, averaged over the conv-family launches of one bs32 forward (ncu per-launch capture, latest profiles/r*_conv_tc_traffic.json)' if traffic else None,
         'launches_per_step': conv_n / args.steps,
         'avg_launch_ms': round(conv_ms / max(conv_n, 1), 5),
         'algorithmic_gflop_per_step': round(conv_flops / args.steps / 1e9, 2),

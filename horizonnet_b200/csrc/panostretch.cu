@@ -9,8 +9,12 @@
 // tables of W entries per (kx, ky) pair and the main kernel spends one fp64 atan per FOUR pixels
 // (rows y and H-1-y have tan v of opposite sign, so v0 is odd: refy(H-1-y) = H-1-refy(y); columns x
 // and W-1-x have u of opposite sign, so g is even).
-// Coordinates and the bilinear accumulation are fp64 like scipy (result cast to fp32); scipy's
-// legacy 'wrap' folds coordinates with period n-1.  HBM-bound: 2*H*W*C*4 bytes per panorama.
+// Coordinates and the bilinear accumulation are fp64 like scipy (result cast to the image dtype); scipy's
+// legacy 'wrap' folds coordinates with period n-1.  HBM-bound: 2*H*W*C*4 bytes per panorama; measured: bound by the L1
+// data pipe (89.7 % of its wavefront peak: 4-byte gathers and stores at a 12-byte pixel stride), 0.43-0.50 of HBM peak.
+// Round-2 negative result: a variant that staged each tile's source patch in shared memory (16-byte cp.async, LDS
+// gathers; bit-identical, verified over the 49-pair grid) ran 0.38 ms vs 0.28 ms per 64 images -- the patch fill cannot
+// overlap the gathers inside a block and every smem pass costs the same L1 wavefronts it saves; removed.
 #include <cstdlib>
 #include "hn_common.cuh"
 
@@ -289,8 +293,8 @@ static int pano_stretch_device_t(const T* img, T* out, int n, int H, int W, int 
     const int tot = (n * W > H) ? n * W : H;
     stretch_tables_kernel<<<(tot + 255) / 256, 256, 0, st>>>(kx_dev, ky_dev, cols, tanv, n, H, W);
     HN_LAUNCH_OK();
-    dim3 g(((W + 1) / 2 + 127) / 128, (H + 1) / 2, n);
     HN_CHECK(n <= 65535, "pano_stretch: at most 65535 images per call");
+    dim3 g(((W + 1) / 2 + 127) / 128, (H + 1) / 2, n);
     switch (C) {
         case 1: stretch_kernel<1, T><<<g, 128, 0, st>>>(img, out, cols, tanv, H, W, order); break;
         case 2: stretch_kernel<2, T><<<g, 128, 0, st>>>(img, out, cols, tanv, H, W, order); break;
