@@ -188,6 +188,9 @@ class HorizonNet(nn.Module):
         with self._lock:
             h = self._handles.get(key)
             if h is not None and h['max_batch'] < batch:
+                if h.get('pending'):
+                    raise RuntimeError('collect_host() the submitted batches before running a larger batch: the device '
+                                       'workspace has to be re-created for it')
                 lib.hn_model_destroy(h['ptr'])
                 h = None
             if h is None:
