@@ -82,6 +82,20 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, ui
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// L2 prefetch of a tensor-map box (no shared memory involved).  The HBM-bound kernels hold at most two 32 KB identity tiles per SM
+// in flight (their landing buffers double as output staging), i.e. 64 KB / ~3 us = Little's-law bound near 50 % DRAM; prefetching
+// the boxes a few tiles ahead moves the DRAM latency off the buffer-recycling chain.
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                 "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -172,6 +186,7 @@ struct TcArgs {
                               //    dx taps read it through row-shifted UMMA descriptors (L2->SM traffic per tap: 64 -> 43 KB)
     int rowbox;               // 1: the rows_per_tile output rows of a tile come from consecutive input rows of one image -> one TMA box
     int dbg;                  // HN_TC_DBG experiment bits: 1 skip residual reads, 2 skip output stores, 4 skip epilogue math
+    int pf;                   // gemm_tc_kernel: L2 prefetch distance (in tiles) of the residual / activation boxes, 0 = off
 };
 
 template <int BN>
@@ -692,6 +707,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
                 const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+                if (a.pf > 0) {                  // residual and activation boxes of the tile a.pf rounds ahead -> L2
+                    const int ta = tile + a.pf * (int)gridDim.x;
+                    if (ta < a.num_tiles) {
+                        const int mta = ta / a.n_tiles, nta = ta - mta * a.n_tiles;
+                        if (has_res) {
+                            tma_prefetch_3d(&tmR, nta * GBN, mta * BM, 0);
+                            tma_prefetch_3d(&tmR, nta * GBN, mta * BM, 1);
+                        }
+                        for (int kc = 0; kc < a.num_kc; ++kc) {
+                            tma_prefetch_3d(&tmA, kc * BKC, mta * BM, 0);
+                            tma_prefetch_3d(&tmA, kc * BKC, mta * BM, 1);
+                        }
+                    }
+                }
                 // operands first: the MMAs of this tile overlap the epilogue of the previous one
                 for (int kc = 0; kc < a.num_kc; ++kc) {
                     mbar_wait(empty_bar + stage, phase ^ 1);
@@ -1164,6 +1193,7 @@ struct BottArgs {
     int n3;                              // conv3 n-tiles of 64 channels (Cout3 / 64)
     int C3;                              // conv3 output channels
     int seg;
+    int pf_dist;                         // L2 prefetch distance of the identity tiles in n-tiles (0 = off; HN_TC_PF)
     const float* scale2; const float* shift2;     // conv2: accumulator -> plane units, shift in plane units
     const float* scale3; const float* shift3;     // conv3
     unsigned short* out; size_t out_plane;        // output planes (halo-column stores)
@@ -1271,6 +1301,15 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int rg = tile / a.wsegs;
                 const int wo0 = (tile - rg * a.wsegs) * BM;
                 const int b = rg / a.Ho, ho = rg - b * a.Ho;
+                if (a.pf_dist > 0 && tile + (int)gridDim.x < a.num_tiles) {      // next tile's input rows -> L2
+                    const int tn = tile + (int)gridDim.x;
+                    const int rgn = tn / a.wsegs, won = (tn - rgn * a.wsegs) * BM;
+                    const int bn = rgn / a.Ho, hon = rgn - bn * a.Ho;
+                    for (int dy = 0; dy < 3; ++dy) {
+                        tma_prefetch_4d(&tmA, 0, won, hon + dy - 1, bn);
+                        tma_prefetch_4d(&tmA, 0, won, hon + dy - 1, a.Bimg + bn);
+                    }
+                }
                 for (int dy = 0; dy < 3; ++dy) {
                     const int hin = ho + dy - 1;
                     mbar_wait(aempty_bar + ast, aph ^ 1);
@@ -1384,6 +1423,16 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int rg = tile / a.wsegs;
                 const int pix0 = rg * a.Wop + 1 + (tile - rg * a.wsegs) * BM;
                 for (int j = 0; j < n3; ++j, ++g3) {
+                    if (a.pf_dist > 0) {            // identity tile of the n-tile pf_dist steps ahead -> L2
+                        const int ja = j + a.pf_dist;
+                        const int ta = tile + (ja / n3) * (int)gridDim.x;
+                        if (ta < a.num_tiles) {
+                            const int rga = ta / a.wsegs;
+                            const int pa = rga * a.Wop + 1 + (ta - rga * a.wsegs) * BM;
+                            tma_prefetch_3d(&tmR, (ja % n3) * 64, pa, 0);
+                            tma_prefetch_3d(&tmR, (ja % n3) * 64, pa, 1);
+                        }
+                    }
                     const int eb = g3 & 1;
                     mbar_wait(efree_bar + eb, ((g3 >> 1) & 1) ^ 1);
                     uint8_t* ebuf = smem + S::E_OFF + eb * S::EBUF;
@@ -1626,6 +1675,16 @@ cudaError_t launch_tc(K kernel, int grid, size_t smem_bytes, cudaStream_t st, Ar
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
+int tc_prefetch_distance() {
+    // identity / activation tiles are prefetched into L2 this many n-tiles ahead by the HBM-bound kernels; HN_TC_PF=0 disables
+    static int d = [] {
+        const char* e = getenv("HN_TC_PF");
+        int v = e ? atoi(e) : 6;
+        return v < 0 ? 0 : (v > 64 ? 64 : v);
+    }();
+    return d;
+}
+
 template <int BN>
 int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, cudaStream_t st) {
     using S = Smem<BN>;
@@ -1700,6 +1759,7 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
         a.mode = 0;
         a.M = (int)Mtot;
         a.n_tiles = d.Cout / GBN;
+        a.pf = tc_prefetch_distance() > 0 ? 2 : 0;
         CUtensorMap tmR, tmO;
         {
             cuuint64_t dims[3] = {(cuuint64_t)d.Cin, (cuuint64_t)Mtot, 2};
@@ -1854,6 +1914,7 @@ int bott_tc_planes(const ConvDesc& d2, const unsigned short* wq2, const float* a
     a.num_tiles = (int)tiles;
     a.n3 = d3.Cout / 64; a.C3 = d3.Cout;
     a.seg = tc_segment_chunks();
+    a.pf_dist = tc_prefetch_distance();
     a.scale2 = aux2 + 64; a.shift2 = aux2 + 2 * 64;                        // plane units (conv_tc.cuh: tc_aux)
     a.scale3 = aux3 + d3.Cout; a.shift3 = aux3 + 2 * d3.Cout;
     a.out = out_planes; a.out_plane = out_plane;

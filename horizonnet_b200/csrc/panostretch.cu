@@ -269,7 +269,9 @@ __global__ void __launch_bounds__(128) augment_kernel(const unsigned char* __res
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             float v = val[vt][c];
-            if (pr.gamma > 0.f) v = powf(v, pr.gamma);                             // dataset.py:105 (float32 ** float32)
+            // dataset.py:105 (float32 ** float32) for v in [0, 1], p > 0: exp2f(p * log2f(v)) with the full-precision (1 ulp)
+            // functions is within 1e-7 of the correctly rounded power here and a third of powf's instructions
+            if (pr.gamma > 0.f) v = (v > 0.f) ? exp2f(pr.gamma * log2f(v)) : 0.f;
             dst[(size_t)c * plane + (size_t)yy * W + xo] = v;                      // dataset.py:124 HWC -> CHW
         }
     }
