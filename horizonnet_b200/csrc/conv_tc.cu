@@ -82,20 +82,12 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* tm, ui
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// L2 prefetch of a tensor-map box (no shared memory involved).  The HBM-bound kernels hold at most two 32 KB identity tiles per SM
-// in flight (their landing buffers double as output staging), i.e. 64 KB / ~3 us = Little's-law bound near 50 % DRAM; prefetching
-// the boxes a few tiles ahead moves the DRAM latency off the buffer-recycling chain.
+// L2 prefetch of a tensor-map box (no shared memory involved): used by gemm_tc_kernel for its K = 64 layers.
 __device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap* tm, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
                  "r"(c0), "r"(c1), "r"(c2)
                  : "memory");
 }
-__device__ __forceinline__ void tma_prefetch_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3) {
-    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(reinterpret_cast<uint64_t>(tm)),
-                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-                 : "memory");
-}
-
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
@@ -1193,7 +1185,6 @@ struct BottArgs {
     int n3;                              // conv3 n-tiles of 64 channels (Cout3 / 64)
     int C3;                              // conv3 output channels
     int seg;
-    int pf_dist;                         // L2 prefetch distance of the identity tiles in n-tiles (0 = off; HN_TC_PF)
     const float* scale2; const float* shift2;     // conv2: accumulator -> plane units, shift in plane units
     const float* scale3; const float* shift3;     // conv3
     unsigned short* out; size_t out_plane;        // output planes (halo-column stores)
@@ -1301,15 +1292,6 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int rg = tile / a.wsegs;
                 const int wo0 = (tile - rg * a.wsegs) * BM;
                 const int b = rg / a.Ho, ho = rg - b * a.Ho;
-                if (a.pf_dist > 0 && tile + (int)gridDim.x < a.num_tiles) {      // next tile's input rows -> L2
-                    const int tn = tile + (int)gridDim.x;
-                    const int rgn = tn / a.wsegs, won = (tn - rgn * a.wsegs) * BM;
-                    const int bn = rgn / a.Ho, hon = rgn - bn * a.Ho;
-                    for (int dy = 0; dy < 3; ++dy) {
-                        tma_prefetch_4d(&tmA, 0, won, hon + dy - 1, bn);
-                        tma_prefetch_4d(&tmA, 0, won, hon + dy - 1, a.Bimg + bn);
-                    }
-                }
                 for (int dy = 0; dy < 3; ++dy) {
                     const int hin = ho + dy - 1;
                     mbar_wait(aempty_bar + ast, aph ^ 1);
@@ -1423,16 +1405,6 @@ bott_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int rg = tile / a.wsegs;
                 const int pix0 = rg * a.Wop + 1 + (tile - rg * a.wsegs) * BM;
                 for (int j = 0; j < n3; ++j, ++g3) {
-                    if (a.pf_dist > 0) {            // identity tile of the n-tile pf_dist steps ahead -> L2
-                        const int ja = j + a.pf_dist;
-                        const int ta = tile + (ja / n3) * (int)gridDim.x;
-                        if (ta < a.num_tiles) {
-                            const int rga = ta / a.wsegs;
-                            const int pa = rga * a.Wop + 1 + (ta - rga * a.wsegs) * BM;
-                            tma_prefetch_3d(&tmR, (ja % n3) * 64, pa, 0);
-                            tma_prefetch_3d(&tmR, (ja % n3) * 64, pa, 1);
-                        }
-                    }
                     const int eb = g3 & 1;
                     mbar_wait(efree_bar + eb, ((g3 >> 1) & 1) ^ 1);
                     uint8_t* ebuf = smem + S::E_OFF + eb * S::EBUF;
@@ -1759,7 +1731,10 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
         a.mode = 0;
         a.M = (int)Mtot;
         a.n_tiles = d.Cout / GBN;
-        a.pf = tc_prefetch_distance() > 0 ? 2 : 0;
+        // L2 prefetch two tile rounds ahead, K = 64 only: measured -9..-11 % on layer1's conv1 / downsample (HBM-bound, one
+        // 32 KB activation box per tile); +38 % on the K = 256 conv1 (8 boxes per tile compete with the demand loads) and
+        // +2..4 % on conv3 of layer2/3 and on bott_tc_kernel, where it is therefore not used (profiles/r02_experiments.md)
+        a.pf = (tc_prefetch_distance() > 0 && a.num_kc == 1) ? 2 : 0;
         CUtensorMap tmR, tmO;
         {
             cuuint64_t dims[3] = {(cuuint64_t)d.Cin, (cuuint64_t)Mtot, 2};
@@ -1914,7 +1889,6 @@ int bott_tc_planes(const ConvDesc& d2, const unsigned short* wq2, const float* a
     a.num_tiles = (int)tiles;
     a.n3 = d3.Cout / 64; a.C3 = d3.Cout;
     a.seg = tc_segment_chunks();
-    a.pf_dist = tc_prefetch_distance();
     a.scale2 = aux2 + 64; a.shift2 = aux2 + 2 * 64;                        // plane units (conv_tc.cuh: tc_aux)
     a.scale3 = aux3 + d3.Cout; a.shift3 = aux3 + 2 * d3.Cout;
     a.out = out_planes; a.out_plane = out_plane;
