@@ -10,9 +10,11 @@
 // written by the producing kernel's epilogue, so every operand tile is MMA-ready when TMA drops
 // it into shared memory (no in-kernel conversion pass).
 //
-// Kernels in this file (all persistent, warp-specialised, one CTA per SM, 384 threads):
+// Kernels in this file (all persistent, warp-specialised, one CTA per SM, 384 threads, launched with programmatic
+// stream serialisation: griddepcontrol.launch_dependents at entry, griddepcontrol.wait after the prologue):
 //   conv_tc_kernel<BN>  3x3 / strided / large-K 1x1 convs and the LSTM input projections
 //   gemm_tc_kernel      1x1 stride-1 convs with K <= 256 (TMA-prefetched residual, in-place epilogue, TMA store)
+//   bott_tc_kernel      layer1: conv2 (3x3, 64->64) + conv3 (1x1, 64->256, + identity) fused, intermediate in shared memory
 //   stem_tc_kernel      the 7x7 stride-2 stem over packed pixel pairs (no-swizzle UMMA operand with overlapping rows)
 //
 // conv_tc_kernel:

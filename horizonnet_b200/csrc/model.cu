@@ -458,6 +458,11 @@ int hn_model_set_tensor(hn_model* m, const char* key, const float* data, long lo
         return fail(std::string("hn_model_set_tensor: size mismatch for '") + key + "': got " + std::to_string(numel) +
                     ", expected " + std::to_string(s.numel));
     HN_ON_DEVICE(m->device);
+    if (m->rnn_inflight) {        // forwards may still be running on the internal (non-blocking) streams: do not race them
+        HN_CUDA_OK(cudaStreamSynchronize(m->enc_stream));
+        HN_CUDA_OK(cudaStreamSynchronize(m->rnn_stream));
+        m->rnn_inflight = false;
+    }
     HN_CUDA_OK(cudaMemcpy(s.dev, data, (size_t)numel * sizeof(float),
                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
     s.set = true;
