@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(128) stretch_kernel(const T* __restrict__ img,
 // core, dominated by pano_stretch).  Here output pixel (y, xo) is traced back through roll and flip to column xs of
 // the stretched image, sampled bilinearly from the uint8 source (fp64 coordinates and blend, scipy legacy 'wrap'; the
 // taps are read through a 256-entry table of double(float32(v) / 255f), so there is no per-tap conversion), raised to
-// the power p in fp32 and written to the three channel planes.  Rows y and H-1-y share the column entry and the atan.
+// the power p in fp32 and written to the three channel planes.  As in stretch_kernel one atan serves the four mirror pixels.
 // Algorithmic bytes per panorama: H*W*3 (uint8 in) + H*W*3*4 (float32 out).
 struct AugParams {
     int flip;        // dataset.py:88-91
@@ -207,72 +207,90 @@ __global__ void __launch_bounds__(128) augment_kernel(const unsigned char* __res
     __shared__ double lut[256];
     for (int i = threadIdx.x; i < 256; i += blockDim.x) lut[i] = (double)__fdiv_rn((float)i, 255.f);   // dataset.py:53
     __syncthreads();
-    const int xo = blockIdx.x * 128 + threadIdx.x;
+    // thread = column pair (xs, W-1-xs) of the STRETCHED image x row pair (y, H-1-y): one atan serves four pixels, as in
+    // stretch_kernel; each stretched column is then carried to its output column through flip and roll
+    const int xs0 = blockIdx.x * 128 + threadIdx.x;
     const int y = blockIdx.y;
     const int n = blockIdx.z;
-    if (xo >= W) return;
+    const int xs1 = W - 1 - xs0;
+    if (xs0 > xs1) return;
     const AugParams pr = params[n];
-    // un-roll (np.roll(img, dx, axis=1): out[x] = in[(x - dx) mod W]), then un-flip (np.flip: in[j] = st[W-1-j])
-    int xs = xo - pr.dx;
-    if (xs < 0) xs += W;
-    if (pr.flip) xs = W - 1 - xs;
     const size_t plane = (size_t)H * W;
     const unsigned char* src = img + (size_t)n * plane * 3;
     float* dst = out + (size_t)n * plane * 3;
     const int ym = H - 1 - y;
-    const int nvert = (ym == y) ? 1 : 2;
-    float val[2][3];
+    const int nside = (xs1 == xs0) ? 1 : 2, nvert = (ym == y) ? 1 : 2;
+    const int xsd[2] = {xs0, xs1};
+    int xo[2];                                   // np.flip: st[j] -> flipped[W-1-j]; np.roll(.., dx): in[j] -> out[(j + dx) mod W]
+#pragma unroll
+    for (int sd = 0; sd < 2; ++sd) {
+        int j = pr.flip ? W - 1 - xsd[sd] : xsd[sd];
+        j += pr.dx;
+        xo[sd] = j >= W ? j - W : j;
+    }
+    float val[2][2][3];                          // [side][vert][channel]
     if (!pr.stretch) {
 #pragma unroll
-        for (int vt = 0; vt < 2; ++vt) {
-            const unsigned char* p = src + ((size_t)(vt ? ym : y) * W + xs) * 3;
+        for (int sd = 0; sd < 2; ++sd)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) val[vt][c] = (float)lut[p[c]];
-        }
+            for (int vt = 0; vt < 2; ++vt) {
+                const unsigned char* p = src + ((size_t)(vt ? ym : y) * W + xsd[sd]) * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) val[sd][vt][c] = (float)lut[p[c]];
+            }
     } else {
-        const ColEntry e = cols[(size_t)n * W + xs];
-        const double v0 = atan(tanv[y] * e.g);                                    // panostretch.py:93
+        const ColEntry* ce = cols + (size_t)n * W;
+        const ColEntry e[2] = {ce[xs0], ce[xs1]};
+        const double v0 = atan(tanv[y] * e[0].g);                                 // panostretch.py:93
         const double ry = (v0 / PI_D + 0.5) * (double)H - 0.5;                     // :96
         const RowTaps rt[2] = {resolve_row<3>(ry, H, W), resolve_row<3>((double)(H - 1) - ry, H, W)};
-        unsigned char tap[2][4][3];
+        unsigned char tap[2][2][4][3];
 #pragma unroll
-        for (int vt = 0; vt < 2; ++vt) {
-            const unsigned char* p00 = src + rt[vt].r0 + e.x0 * 3;
-            const unsigned char* p01 = src + rt[vt].r0 + e.x1 * 3;
-            const unsigned char* p10 = src + rt[vt].r1 + e.x0 * 3;
-            const unsigned char* p11 = src + rt[vt].r1 + e.x1 * 3;
+        for (int sd = 0; sd < 2; ++sd)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                tap[vt][0][c] = __ldg(p00 + c); tap[vt][1][c] = __ldg(p01 + c);
-                tap[vt][2][c] = __ldg(p10 + c); tap[vt][3][c] = __ldg(p11 + c);
+            for (int vt = 0; vt < 2; ++vt) {
+                const unsigned char* p00 = src + rt[vt].r0 + e[sd].x0 * 3;
+                const unsigned char* p01 = src + rt[vt].r0 + e[sd].x1 * 3;
+                const unsigned char* p10 = src + rt[vt].r1 + e[sd].x0 * 3;
+                const unsigned char* p11 = src + rt[vt].r1 + e[sd].x1 * 3;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    tap[sd][vt][0][c] = __ldg(p00 + c); tap[sd][vt][1][c] = __ldg(p01 + c);
+                    tap[sd][vt][2][c] = __ldg(p10 + c); tap[sd][vt][3][c] = __ldg(p11 + c);
+                }
             }
-        }
 #pragma unroll
-        for (int vt = 0; vt < 2; ++vt) {
-            const double ty = rt[vt].ty, tx = e.tx;
-            const double uy = 1.0 - ty, ux = 1.0 - tx;
-            const double w00 = uy * ux, w01 = uy * tx, w10 = ty * ux, w11 = ty * tx;
+        for (int sd = 0; sd < 2; ++sd)
 #pragma unroll
-            for (int c = 0; c < 3; ++c) {
-                double acc = w00 * lut[tap[vt][0][c]];
-                acc = fma(w01, lut[tap[vt][1][c]], acc);
-                acc = fma(w10, lut[tap[vt][2][c]], acc);
-                acc = fma(w11, lut[tap[vt][3][c]], acc);
-                val[vt][c] = (float)acc;                                          // map_coordinates output dtype = float32
+            for (int vt = 0; vt < 2; ++vt) {
+                const double ty = rt[vt].ty, tx = e[sd].tx;
+                const double uy = 1.0 - ty, ux = 1.0 - tx;
+                const double w00 = uy * ux, w01 = uy * tx, w10 = ty * ux, w11 = ty * tx;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    double acc = w00 * lut[tap[sd][vt][0][c]];
+                    acc = fma(w01, lut[tap[sd][vt][1][c]], acc);
+                    acc = fma(w10, lut[tap[sd][vt][2][c]], acc);
+                    acc = fma(w11, lut[tap[sd][vt][3][c]], acc);
+                    val[sd][vt][c] = (float)acc;                                  // map_coordinates output dtype = float32
+                }
             }
-        }
     }
 #pragma unroll
-    for (int vt = 0; vt < 2; ++vt) {
-        if (vt >= nvert) break;
-        const int yy = vt ? ym : y;
+    for (int sd = 0; sd < 2; ++sd) {
+        if (sd >= nside) break;
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            float v = val[vt][c];
-            // dataset.py:105 (float32 ** float32) for v in [0, 1], p > 0: exp2f(p * log2f(v)) with the full-precision (1 ulp)
-            // functions is within 1e-7 of the correctly rounded power here and a third of powf's instructions
-            if (pr.gamma > 0.f) v = (v > 0.f) ? exp2f(pr.gamma * log2f(v)) : 0.f;
-            dst[(size_t)c * plane + (size_t)yy * W + xo] = v;                      // dataset.py:124 HWC -> CHW
+        for (int vt = 0; vt < 2; ++vt) {
+            if (vt >= nvert) break;
+            const int yy = vt ? ym : y;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                float v = val[sd][vt][c];
+                // dataset.py:105 (float32 ** float32) for v in [0, 1], p > 0: exp2f(p * log2f(v)) with the full-precision (1 ulp)
+                // functions is within 1e-7 of the correctly rounded power here and a third of powf's instructions
+                if (pr.gamma > 0.f) v = (v > 0.f) ? exp2f(pr.gamma * log2f(v)) : 0.f;
+                dst[(size_t)c * plane + (size_t)yy * W + xo[sd]] = v;              // dataset.py:124 HWC -> CHW
+            }
         }
     }
 }
@@ -331,7 +349,7 @@ int augment_device(const unsigned char* img, float* out, int n, int H, int W, co
     const int tot = (n * W > H) ? n * W : H;
     stretch_tables_kernel<<<(tot + 255) / 256, 256, 0, st>>>(kx_dev, ky_dev, cols, tanv, n, H, W);
     HN_LAUNCH_OK();
-    dim3 g((W + 127) / 128, (H + 1) / 2, n);
+    dim3 g(((W + 1) / 2 + 127) / 128, (H + 1) / 2, n);
     augment_kernel<<<g, 128, 0, st>>>(img, out, cols, tanv, reinterpret_cast<const AugParams*>(params_dev), H, W);
     HN_LAUNCH_OK();
     return 0;
