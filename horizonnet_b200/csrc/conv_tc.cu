@@ -1649,14 +1649,10 @@ cudaError_t launch_tc(K kernel, int grid, size_t smem_bytes, cudaStream_t st, Ar
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
-int tc_prefetch_distance() {
-    // identity / activation tiles are prefetched into L2 this many n-tiles ahead by the HBM-bound kernels; HN_TC_PF=0 disables
-    static int d = [] {
-        const char* e = getenv("HN_TC_PF");
-        int v = e ? atoi(e) : 6;
-        return v < 0 ? 0 : (v > 64 ? 64 : v);
-    }();
-    return d;
+bool tc_prefetch_on() {
+    // gemm_tc_kernel prefetches the activation / residual boxes of its K = 64 layers into L2 two tile rounds ahead; HN_TC_PF=0 disables
+    static const bool on = [] { const char* e = getenv("HN_TC_PF"); return !(e && atoi(e) == 0); }();
+    return on;
 }
 
 template <int BN>
@@ -1736,7 +1732,7 @@ int conv_tc_planes(const ConvDesc& d, const unsigned short* wq, const float* tc_
         // L2 prefetch two tile rounds ahead, K = 64 only: measured -9..-11 % on layer1's conv1 / downsample (HBM-bound, one
         // 32 KB activation box per tile); +38 % on the K = 256 conv1 (8 boxes per tile compete with the demand loads) and
         // +2..4 % on conv3 of layer2/3 and on bott_tc_kernel, where it is therefore not used (profiles/r02_experiments.md)
-        a.pf = (tc_prefetch_distance() > 0 && a.num_kc == 1) ? 2 : 0;
+        a.pf = (tc_prefetch_on() && a.num_kc == 1) ? 2 : 0;
         CUtensorMap tmR, tmO;
         {
             cuuint64_t dims[3] = {(cuuint64_t)d.Cin, (cuuint64_t)Mtot, 2};

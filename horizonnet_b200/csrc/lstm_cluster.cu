@@ -24,6 +24,13 @@
 //             column group) units: a cluster then takes TWO column groups and interleaves them step by step, so the
 //             exchange of one group travels while the other group computes.
 //   grid    = 2 directions x ceil(ceil(B/8) / groups-per-cluster) clusters.
+//
+// Round 2: the tcgen05 version of this kernel was built and validated (D[128 x 16] = W[128 x 512] h[512 x 16] per step as 96
+// MMAs M128 N16 K16: W_hi K-major in shared memory, W_lo as an A operand in tensor memory, h as a no-swizzle B operand assembled
+// from the peers' 2 KB blocks; 1.6e-7 max error, same as this kernel) and measured 7.2 us per step for 16 columns against 3.96 us
+// here: the 64 MMAs that read their A operand from shared memory take ~130 cycles each whatever N is (the 32 with A in tensor memory
+// are free), 8.3 k cycles per step, and a single group of 16 columns cannot hide its exchange (1.7 k wait + 1.6 k copy issue) behind
+// another group's compute the way the two interleaved 8-column groups do here.  Not shipped; numbers in profiles/r02_experiments.md.
 #include <cuda_fp16.h>
 #include <cstdlib>
 #include "hn_common.cuh"
