@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
                                                    const float* __restrict__ w,      // [147][64], k=(dy*7+dx)*3+c
                                                    const float* __restrict__ scale,
                                                    const float* __restrict__ shift,
-                                                   float* __restrict__ out, int Hin, int Win) {
+                                                   float* __restrict__ out, int Hin, int Win, float flo) {
     extern __shared__ __align__(16) float smem[];
     float* ws = smem;                              // 147*64
     float* patch = smem + 147 * 64;                // [3][ST_PH][ST_PP]
@@ -319,10 +319,10 @@ __global__ void __launch_bounds__(256) stem_kernel(const float* __restrict__ x, 
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             float4 v;
-            v.x = fmaxf(fmaf(acc[p][q * 4 + 0], sc[q].x, sf[q].x), 0.f);
-            v.y = fmaxf(fmaf(acc[p][q * 4 + 1], sc[q].y, sf[q].y), 0.f);
-            v.z = fmaxf(fmaf(acc[p][q * 4 + 2], sc[q].z, sf[q].z), 0.f);
-            v.w = fmaxf(fmaf(acc[p][q * 4 + 3], sc[q].w, sf[q].w), 0.f);
+            v.x = fmaxf(fmaf(acc[p][q * 4 + 0], sc[q].x, sf[q].x), flo);
+            v.y = fmaxf(fmaf(acc[p][q * 4 + 1], sc[q].y, sf[q].y), flo);
+            v.z = fmaxf(fmaf(acc[p][q * 4 + 2], sc[q].z, sf[q].z), flo);
+            v.w = fmaxf(fmaf(acc[p][q * 4 + 3], sc[q].w, sf[q].w), flo);
             reinterpret_cast<float4*>(o)[q] = v;
             if (oh) reinterpret_cast<float4*>(oh)[q] = v;
         }
@@ -392,13 +392,14 @@ __global__ void __launch_bounds__(256) maxpool_kernel(const float* __restrict__ 
 }  // namespace
 
 int stem_f32(const float* x_nchw, int B, int in_channels, const float* w_packed, const float* scale,
-             const float* shift, const Act& out, cudaStream_t st) {
+             const float* shift, const Act& out, cudaStream_t st, bool relu) {
     HN_CHECK(in_channels >= 3, "stem: input needs >= 3 channels (reference model.py:252 uses x[:, :3])");
     HN_CHECK(out.B == B && out.H == 256 && out.W == 512 && out.C == 64 && out.halo == 1, "stem: bad output tensor");
     const size_t smem = (147 * 64 + 3 * ST_PH * ST_PP) * sizeof(float);
     HN_CUDA_OK(cudaFuncSetAttribute(stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     dim3 g(512 / ST_TW, 256 / ST_TH, B);
-    stem_kernel<<<g, 256, smem, st>>>(x_nchw, in_channels, w_packed, scale, shift, out.p, 512, 1024);
+    // relu = false (train-mode statistics pass): floor at -inf, i.e. the raw conv * scale + shift
+    stem_kernel<<<g, 256, smem, st>>>(x_nchw, in_channels, w_packed, scale, shift, out.p, 512, 1024, relu ? 0.f : -INFINITY);
     HN_LAUNCH_OK();
     return 0;
 }

@@ -940,6 +940,7 @@ struct StemArgs {
     int B, num_tiles;
     const float* scale;       // accumulator -> true units for an input scaled by 2^-4 (tc_aux[0..64))
     const float* shift;       // folded BN shift
+    float floor;              // 0: ReLU (model.py:75); -inf: none
 };
 
 // K-major operand without swizzle: 8-row x 16-byte core matrices, `lbo` bytes between the two core matrices of a
@@ -1123,7 +1124,7 @@ stem_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (lane == 0) mbar_arrive(tempty_bar + acc);
             float y[32];
 #pragma unroll
-            for (int j = 0; j < 32; ++j) y[j] = fmaxf(fmaf(__uint_as_float(v[j]), sc[j], sf[j]), 0.f);
+            for (int j = 0; j < 32; ++j) y[j] = fmaxf(fmaf(__uint_as_float(v[j]), sc[j], sf[j]), a.floor);
             mbar_wait(efree_bar + eb, ((it >> 1) & 1) ^ 1);
             const uint32_t e = smem_u32(smem + S::EPI_OFF + eb * S::EBUF + half * S::E_HALF) + r * 128;
 #pragma unroll
@@ -1911,7 +1912,7 @@ int stem_tc_pack_weights(const float* w_oihw, float* pad_scratch, unsigned short
 }
 
 int stem_tc(const float* x_nchw, int B, int in_channels, const unsigned short* wq, const float* tc_aux,
-            const float* shift, unsigned short* scratch, const Act& out, cudaStream_t st) {
+            const float* shift, unsigned short* scratch, const Act& out, cudaStream_t st, bool relu) {
     HN_CHECK(in_channels >= 3, "stem: input needs >= 3 channels (reference model.py:252 uses x[:, :3])");
     HN_CHECK(out.B == B && out.H == 256 && out.W == 512 && out.C == 64 && out.halo == 1, "stem: bad output tensor");
     HN_CHECK(B >= 1 && B <= 2048, "stem: bad batch");
@@ -1943,6 +1944,7 @@ int stem_tc(const float* x_nchw, int B, int in_channels, const unsigned short* w
     a.num_tiles = B * 1024;
     a.scale = tc_aux;
     a.shift = shift;
+    a.floor = relu ? 0.f : -INFINITY;       // no ReLU: the raw output the train-mode batch statistics are taken from
     HN_CUDA_OK(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StSmem::TOTAL));
     int dev = 0, sms = 0;
     HN_CUDA_OK(cudaGetDevice(&dev));
@@ -2059,6 +2061,12 @@ int merge_planes(const unsigned short* in, float* out, size_t n, cudaStream_t st
 int pack_weight_tc(const float* w_oihw, unsigned short* wq, const float* scale, const float* shift, float* tc_aux,
                    float* scratch, int Cout, int Cin, int kh, int kw, cudaStream_t st) {
     return pack_weight_impl<true>(w_oihw, wq, scale, shift, tc_aux, scratch, Cout, Cin, kh, kw, st);
+}
+
+int tc_aux_update(const float* scale, const float* shift, const float* absmax, float* tc_aux, int Cout, cudaStream_t st) {
+    tc_scale_kernel<<<(Cout + 255) / 256, 256, 0, st>>>(scale, shift, absmax, tc_aux, Cout);
+    HN_LAUNCH_OK();
+    return 0;
 }
 
 // Unit-test convenience: fp32 halo-NHWC in and out, planes built on the fly.

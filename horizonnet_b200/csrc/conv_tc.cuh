@@ -67,11 +67,14 @@ size_t stem_tc_scratch_bytes(int B);
 int stem_tc_pack_weights(const float* w_oihw, float* pad_scratch, unsigned short* wq, const float* scale,
                          const float* shift, float* tc_aux, cudaStream_t st);
 int stem_tc(const float* x_nchw, int B, int in_channels, const unsigned short* wq, const float* tc_aux,
-            const float* shift, unsigned short* scratch, const Act& out, cudaStream_t st);
+            const float* shift, unsigned short* scratch, const Act& out, cudaStream_t st, bool relu = true);
 int split_planes(const float* in, unsigned short* out, size_t n, cudaStream_t st);
 int merge_planes(const unsigned short* in, float* out, size_t n, cudaStream_t st);
 // OIHW fp32 weights -> wq planes + tc_aux[3*Cout] (scale/shift may be null = ones/zeros); scratch: 1 float.
 int pack_weight_tc(const float* w_oihw, unsigned short* wq, const float* scale, const float* shift, float* tc_aux,
                    float* scratch, int Cout, int Cin, int kh, int kw, cudaStream_t st);
+// New epilogue constants for already packed weights (train mode: batch-statistics scale/shift); absmax = the scratch
+// float pack_weight_tc left behind (weight plane scale).
+int tc_aux_update(const float* scale, const float* shift, const float* absmax, float* tc_aux, int Cout, cudaStream_t st);
 
 }  // namespace hn

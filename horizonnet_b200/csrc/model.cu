@@ -142,6 +142,16 @@ struct ConvLayer {
     float* shift = nullptr;
     unsigned short* wq = nullptr;     // [2][Cout][K] hi/lo weight planes for the tcgen05 kernel
     float* tc_scale = nullptr;        // 3*Cout (+1 scratch) epilogue constants of the tcgen05 path (conv_tc.cuh: tc_aux)
+    int bn_index = -1;                // position in hn_model::bn_names (train mode: which BatchNorm2d module this is)
+};
+
+// Train-mode forward (hn_model_forward_train): per-BatchNorm2d switches handed in by the caller
+struct TrainCtx {
+    const unsigned char* bn_train;    // [n_bn] 1: batch statistics + running update, 0: module is in eval mode
+    const double* bn_factor;          // [n_bn] exponential_average_factor (momentum, or 1/num_batches_tracked); < 0: none
+    unsigned long long seed;
+    double rnn_p, head_p;             // dropout probabilities (0: off)
+    const float* mask[2];             // caller-supplied multiplicative masks instead of the Philox ones (parity tests)
 };
 
 }  // namespace
@@ -171,6 +181,11 @@ struct hn_model {
     float* head_w = nullptr;
     float* head_b = nullptr;
     const float* whh[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};
+    std::vector<std::string> bn_names;               // state_dict prefixes of the 69 BatchNorm2d modules, graph order
+    // train-mode scratch (one layer at a time, stream ordered): batch sums, scale/shift, tcgen05 epilogue constants
+    bool bn_stale = false;     // running statistics moved (train forward) since the eval-mode constants were folded
+    double* trn_sums = nullptr;
+    float *trn_scale = nullptr, *trn_shift = nullptr, *trn_aux = nullptr;
 
     // workspace (sized for max_batch)
     float *S0 = nullptr, *S1 = nullptr, *X[2] = {nullptr, nullptr}, *IDN = nullptr, *T1 = nullptr, *T2 = nullptr;
@@ -264,6 +279,8 @@ ConvLayer make_conv(hn_model* m, const std::string& wkey, const std::string& bn,
     m->add_slot(wkey, (long long)cout * cin * k * k);
     if (!biaskey.empty()) m->add_slot(biaskey, cout);
     m->add_bn(bn, cout);
+    c.bn_index = (int)m->bn_names.size();
+    m->bn_names.push_back(bn);
     return c;
 }
 
@@ -368,6 +385,54 @@ int run_conv(hn_model* m, const ConvLayer& c, const Act& in, const Act& out, con
                           reinterpret_cast<const unsigned short*>(res), st);
 }
 
+// Eval-mode epilogue constants again from the (moved) running statistics; the packed weights are untouched.
+int refold_bn(hn_model* m, cudaStream_t st) {
+    std::vector<ConvLayer*> all{&m->stem};
+    for (int l = 0; l < 4; ++l)
+        for (auto& b : m->blocks[l]) {
+            all.push_back(&b.c1); all.push_back(&b.c2); all.push_back(&b.c3);
+            if (b.has_ds) all.push_back(&b.ds);
+        }
+    for (int s = 0; s < 4; ++s)
+        for (int j = 0; j < 4; ++j) all.push_back(&m->ghc[s][j]);
+    for (ConvLayer* c : all) {
+        const int C = c->d.Cout;
+        fold_bn_kernel<<<(C + 255) / 256, 256, 0, st>>>(
+            m->T(c->bnprefix + ".weight"), m->T(c->bnprefix + ".bias"), m->T(c->bnprefix + ".running_mean"),
+            m->T(c->bnprefix + ".running_var"), c->biaskey.empty() ? nullptr : m->T(c->biaskey), c->scale, c->shift, C);
+        HN_LAUNCH_OK();
+        if (c->tc_scale && tc_aux_update(c->scale, c->shift, c->tc_scale + 3 * C, c->tc_scale, C, st)) return -1;
+    }
+    if (tc_aux_update(m->stem.scale, m->stem.shift, m->stem_aux + 3 * 64, m->stem_aux, 64, st)) return -1;
+    m->bn_stale = false;
+    return 0;
+}
+
+// conv + BatchNorm2d (+ identity, ReLU).  Eval (tr == nullptr, or a BN module the caller keeps in eval mode --
+// train.py:251-256 --freeze_earlier_blocks): one launch with the running statistics folded into the epilogue.
+// Train: the same convolution kernel twice -- raw output (+ conv bias) -> batch mean / biased variance and the
+// running-statistics update (train_fwd.cu) -> the real pass with the batch statistics folded into the epilogue.
+int conv_bn(hn_model* m, const ConvLayer& c, const Act& in, const Act& out, const float* res, cudaStream_t st, int cls,
+            const TrainCtx* tr) {
+    if (!tr || !tr->bn_train[c.bn_index]) return run_conv(m, c, in, out, res, st, cls);
+    const int C = c.d.Cout;
+    const float* bias = c.biaskey.empty() ? nullptr : m->T(c.biaskey);
+    ConvLayer t = c;
+    t.d.relu = 0; t.d.scale = m->trn_scale; t.d.shift = m->trn_shift; t.tc_scale = m->trn_aux;
+    if (bn_identity_constants(bias, m->trn_scale, m->trn_shift, C, st)) return -1;
+    if (m->use_tc && tc_aux_update(m->trn_scale, m->trn_shift, c.tc_scale + 3 * C, m->trn_aux, C, st)) return -1;
+    if (run_conv(m, t, in, out, nullptr, st, cls)) return -1;
+    if (bn_batch_stats(out, m->use_tc != 0, m->trn_sums, st)) return -1;
+    if (bn_train_finalize(m->trn_sums, (long long)out.B * out.H * out.W, m->T(c.bnprefix + ".weight"),
+                          m->T(c.bnprefix + ".bias"), bias, const_cast<float*>(m->T(c.bnprefix + ".running_mean")),
+                          const_cast<float*>(m->T(c.bnprefix + ".running_var")), tr->bn_factor[c.bn_index],
+                          m->trn_scale, m->trn_shift, C, st))
+        return -1;
+    if (m->use_tc && tc_aux_update(m->trn_scale, m->trn_shift, c.tc_scale + 3 * C, m->trn_aux, C, st)) return -1;
+    t.d.relu = c.d.relu;
+    return run_conv(m, t, in, out, res, st, cls);
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -415,6 +480,9 @@ int hn_model_create(int device, int max_batch, hn_model** out) {
     if (m->alloc(reinterpret_cast<void**>(&m->counters), lstm_scratch_bytes())) return -1;
     if (m->alloc_t(&m->error_flag, 1)) return -1;
     if (m->alloc_t(&m->tta_ints, 128)) return -1;
+    if (m->alloc_t(&m->trn_sums, 2 * 4096) || m->alloc_t(&m->trn_scale, 4096) || m->alloc_t(&m->trn_shift, 4096) ||
+        m->alloc_t(&m->trn_aux, 3 * 4096 + 1))
+        return -1;
     HN_CUDA_OK(cudaMemset(m->error_flag, 0, sizeof(int)));
     m->x_slot[0] = m->x_in;
     m->bon_slot[0] = m->bon_out; m->cor_slot[0] = m->cor_out;
@@ -523,6 +591,7 @@ int hn_model_finalize(hn_model* m) {
     HN_CUDA_OK(cudaMemcpyAsync(m->head_w, m->T("linear.weight"), 12 * 1024 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     HN_CUDA_OK(cudaMemcpyAsync(m->head_b, m->T("linear.bias"), 12 * sizeof(float), cudaMemcpyDeviceToDevice, st));
     HN_CUDA_OK(cudaStreamSynchronize(st));
+    m->bn_stale = false;
     m->finalized = true;
     return 0;
 }
@@ -530,16 +599,40 @@ int hn_model_finalize(hn_model* m) {
 // ---- the three parts of HorizonNet.forward (model.py:254-281); static helpers (no extern "C" linkage needed)
 // (1) normalise + stem + max-pool + layer1..4 + the 16 height-reduction convs: leaves gout[] in GO[0..3]
 static int forward_encoder(hn_model* m, const float* x, int B, int in_channels, Act gout[4], cudaStream_t st,
-                           cudaEvent_t x_consumed) {
+                           cudaEvent_t x_consumed, const TrainCtx* tr = nullptr) {
+    if (m->bn_stale) {
+        bool need = !tr;                     // eval forward, or a train forward with frozen (eval-mode) BN modules
+        for (size_t i = 0; tr && i < m->bn_names.size(); ++i) need = need || !tr->bn_train[i];
+        if (need && refold_bn(m, st)) return -1;
+    }
     // model.py:248-252 + :73-76: normalise, stem conv/BN/ReLU, max-pool
     Act s0 = mk(m->S0, B, 256, 512, 64);
     {
         Scope sc(m, CLS_STEM, 2.0 * B * 256 * 512 * 64 * 147, st);
-        if (m->use_tc && m->stem_tc_on) {
-            // packed input planes live in X[0] (free until layer1): B * 8.6 MB of its B * 33.8 MB
-            if (stem_tc(x, B, in_channels, m->stem_wq, m->stem_aux, m->stem.shift,
-                        reinterpret_cast<unsigned short*>(m->X[0]), s0, st)) return -1;
-        } else if (stem_f32(x, B, in_channels, m->stem.w, m->stem.scale, m->stem.shift, s0, st)) return -1;
+        const bool tc = m->use_tc && m->stem_tc_on;
+        const bool batch_stats = tr && tr->bn_train[m->stem.bn_index];
+        const float *scale = m->stem.scale, *shift = m->stem.shift, *aux = m->stem_aux;
+        for (int pass = batch_stats ? 0 : 1; pass < 2; ++pass) {
+            if (batch_stats) {          // pass 0: raw stem output -> batch statistics; pass 1: the real thing
+                if (pass == 0 && bn_identity_constants(nullptr, m->trn_scale, m->trn_shift, 64, st)) return -1;
+                if (pass == 1) {
+                    if (bn_batch_stats(s0, false, m->trn_sums, st)) return -1;
+                    if (bn_train_finalize(m->trn_sums, (long long)B * 256 * 512, m->T(m->stem.bnprefix + ".weight"),
+                                          m->T(m->stem.bnprefix + ".bias"), nullptr,
+                                          const_cast<float*>(m->T(m->stem.bnprefix + ".running_mean")),
+                                          const_cast<float*>(m->T(m->stem.bnprefix + ".running_var")),
+                                          tr->bn_factor[m->stem.bn_index], m->trn_scale, m->trn_shift, 64, st))
+                        return -1;
+                }
+                if (tc && tc_aux_update(m->trn_scale, m->trn_shift, m->stem_aux + 3 * 64, m->trn_aux, 64, st)) return -1;
+                scale = m->trn_scale; shift = m->trn_shift; aux = m->trn_aux;
+            }
+            if (tc) {
+                // packed input planes live in X[0] (free until layer1): B * 8.6 MB of its B * 33.8 MB
+                if (stem_tc(x, B, in_channels, m->stem_wq, aux, shift, reinterpret_cast<unsigned short*>(m->X[0]), s0, st,
+                            pass == 1)) return -1;
+            } else if (stem_f32(x, B, in_channels, m->stem.w, scale, shift, s0, st, pass == 1)) return -1;
+        }
     }
     if (x_consumed) HN_CUDA_OK(cudaEventRecord(x_consumed, st));       // the input batch is not read after the stem
     Act cur = mk(m->S1, B, 128, 256, 64);
@@ -559,14 +652,14 @@ static int forward_encoder(hn_model* m, const float* x, int B, int in_channels, 
             Act t1 = mk(m->T1, B, cur.H, cur.W, blk.c1.d.Cout);
             Act t2 = mk(m->T2, B, Ho, Wo, blk.c2.d.Cout);
             Act y = mk(b == nb - 1 ? m->F[l] : m->X[b & 1], B, Ho, Wo, blk.c3.d.Cout);
-            if (run_conv(m, blk.c1, cur, t1, nullptr, st, CLS_ENC_CONV)) return -1;
+            if (conv_bn(m, blk.c1, cur, t1, nullptr, st, CLS_ENC_CONV, tr)) return -1;
             const float* idn = cur.p;
             if (blk.has_ds) {
                 Act d = mk(m->IDN, B, Ho, Wo, blk.ds.d.Cout);
-                if (run_conv(m, blk.ds, cur, d, nullptr, st, CLS_ENC_CONV)) return -1;
+                if (conv_bn(m, blk.ds, cur, d, nullptr, st, CLS_ENC_CONV, tr)) return -1;
                 idn = d.p;
             }
-            if (m->use_tc && m->fuse_on && blk.c2.wq && blk.c3.wq && bott_tc_supported(blk.c2.d, blk.c3.d, t1, y)) {
+            if (!tr && m->use_tc && m->fuse_on && blk.c2.wq && blk.c3.wq && bott_tc_supported(blk.c2.d, blk.c3.d, t1, y)) {
                 // layer1: conv2 + conv3 in one kernel, the 64-channel intermediate stays in shared memory (conv_tc.cu)
                 const double flops = 2.0 * (double)B * Ho * Wo * (64.0 * 9 * 64 + (double)blk.c3.d.Cout * 64);
                 Scope sc(m, CLS_ENC_CONV, flops, st);
@@ -575,8 +668,8 @@ static int forward_encoder(hn_model* m, const float* x, int B, int in_channels, 
                                    reinterpret_cast<const unsigned short*>(idn), st))
                     return -1;
             } else {
-                if (run_conv(m, blk.c2, t1, t2, nullptr, st, CLS_ENC_CONV)) return -1;
-                if (run_conv(m, blk.c3, t2, y, idn, st, CLS_ENC_CONV)) return -1;      // + identity, ReLU
+                if (conv_bn(m, blk.c2, t1, t2, nullptr, st, CLS_ENC_CONV, tr)) return -1;
+                if (conv_bn(m, blk.c3, t2, y, idn, st, CLS_ENC_CONV, tr)) return -1;   // + identity, ReLU
             }
             cur = y;
         }
@@ -589,7 +682,7 @@ static int forward_encoder(hn_model* m, const float* x, int B, int in_channels, 
         for (int j = 0; j < 4; ++j) {
             const ConvLayer& c = m->ghc[s][j];
             Act o = mk(j == 3 ? m->GO[s] : m->G[j & 1], B, g.H / 2, g.W, c.d.Cout);
-            if (run_conv(m, c, g, o, nullptr, st, CLS_GHC_CONV)) return -1;
+            if (conv_bn(m, c, g, o, nullptr, st, CLS_GHC_CONV, tr)) return -1;
             g = o;
         }
         gout[s] = g;
@@ -604,12 +697,19 @@ static int forward_sequence(hn_model* m, const Act gout[4], cudaStream_t st) {
 }
 
 // (3) model.py:264-281: 2-layer bidirectional LSTM (eval: dropout = identity), linear head, reshape, split
-static int forward_rnn(hn_model* m, int B, float* bon, float* cor, cudaStream_t st) {
+static int forward_rnn(hn_model* m, int B, float* bon, float* cor, cudaStream_t st, const TrainCtx* tr = nullptr) {
     const float* lin = m->SEQ;
     float* louts[2] = {m->R1, m->R2};
     for (int layer = 0; layer < 2; ++layer) {
         Act a = mk(const_cast<float*>(lin), 1, 1, 256 * B, 1024, 0);
         Act xp = mk(m->XP, 1, 1, 256 * B, 4096, 0);
+        if (tr && layer == 1 && tr->rnn_p > 0.0) {
+            // train mode: nn.LSTM(dropout=p) zeroes layer-1 outputs on their way into layer 2 (model.py:226)
+            Scope sc(m, CLS_TAIL, 0.0, st);
+            if (tr->mask[0] ? multiply_inplace(m->R1, tr->mask[0], (size_t)256 * B * 1024, st)
+                            : dropout_inplace(m->R1, (size_t)256 * B * 1024, tr->rnn_p, tr->seed, 0, false, st))
+                return -1;
+        }
         if (m->use_tc && layer == 1) {
             // layer-2 projection operand: the fp32 recurrence output as fp16 hi/lo planes
             Scope sc(m, CLS_TAIL, 0.0, st);
@@ -624,6 +724,12 @@ static int forward_rnn(hn_model* m, int B, float* bon, float* cor, cudaStream_t 
                 return -1;
         }
         lin = louts[layer];
+    }
+    if (tr && tr->head_p > 0.0) {         // train mode: self.drop_out before the linear head (model.py:265)
+        Scope sc(m, CLS_TAIL, 0.0, st);
+        if (tr->mask[1] ? multiply_inplace(m->R2, tr->mask[1], (size_t)256 * B * 1024, st)
+                        : dropout_inplace(m->R2, (size_t)256 * B * 1024, tr->head_p, tr->seed, 1, false, st))
+            return -1;
     }
     {
         Scope sc(m, CLS_HEAD, 2.0 * 256 * B * 12 * 1024, st);
@@ -679,6 +785,59 @@ int hn_model_forward(hn_model* m, const float* x, int B, int in_channels, float*
     HN_CUDA_OK(cudaEventRecord(m->ev_plain_done, st));
     m->plain_recorded = true;
     return 0;
+}
+
+int hn_model_num_bn(const hn_model* m) { return m ? (int)m->bn_names.size() : 0; }
+
+const char* hn_model_bn_name(const hn_model* m, int i) {
+    return (m && i >= 0 && i < (int)m->bn_names.size()) ? m->bn_names[i].c_str() : nullptr;
+}
+
+int hn_model_forward_train(hn_model* m, const float* x, int B, int in_channels, float* bon, float* cor,
+                           const unsigned char* bn_train, const double* bn_factor, int n_bn, unsigned long long seed,
+                           double rnn_dropout, double head_dropout, const float* rnn_mask, const float* head_mask,
+                           void* stream) {
+    if (forward_args_ok(m, x, B, bon, cor, "hn_model_forward_train")) return -1;
+    HN_CHECK(bn_train && bn_factor && n_bn == (int)m->bn_names.size(),
+             "hn_model_forward_train: bn_train / bn_factor need hn_model_num_bn() entries");
+    HN_CHECK(rnn_dropout >= 0.0 && rnn_dropout < 1.0 && head_dropout >= 0.0 && head_dropout < 1.0,
+             "hn_model_forward_train: dropout probabilities must be in [0, 1)");
+    HN_ON_DEVICE(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (m->rnn_inflight) {
+        HN_CUDA_OK(cudaStreamWaitEvent(st, m->ev_rnn_last, 0));
+        m->rnn_inflight = false;
+    }
+    m->last_batch = B;
+    const TrainCtx tr{bn_train, bn_factor, seed, rnn_dropout, head_dropout, {rnn_mask, head_mask}};
+    Act gout[4];
+    if (forward_encoder(m, x, B, in_channels, gout, st, nullptr, &tr)) return -1;
+    if (forward_sequence(m, gout, st)) return -1;
+    if (forward_rnn(m, B, bon, cor, st, &tr)) return -1;
+    for (int i = 0; i < n_bn; ++i) m->bn_stale = m->bn_stale || (bn_train[i] && bn_factor[i] >= 0.0);
+    HN_CUDA_OK(cudaEventRecord(m->ev_plain_done, st));
+    m->plain_recorded = true;
+    return 0;
+}
+
+int hn_model_get_tensor(hn_model* m, const char* key, float* out, long long numel, int on_device, void* stream) {
+    HN_CHECK(m && key && out, "hn_model_get_tensor: NULL argument");
+    auto it = m->index.find(key);
+    if (it == m->index.end()) return fail(std::string("hn_model_get_tensor: unknown key '") + key + "'");
+    const TensorSlot& s = m->slots[it->second];
+    HN_CHECK(!s.ignored && s.set && s.dev, "hn_model_get_tensor: tensor was never set");
+    HN_CHECK(numel == s.numel, "hn_model_get_tensor: element count differs from the tensor's");
+    HN_ON_DEVICE(m->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    HN_CUDA_OK(cudaMemcpyAsync(out, s.dev, (size_t)numel * sizeof(float),
+                               on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+    if (!on_device) HN_CUDA_OK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+int hn_dropout_mask(unsigned long long seed, int which, double p, float* out, long long n, void* stream) {
+    HN_CHECK(out && n >= 0, "hn_dropout_mask: bad argument");
+    return dropout_inplace(out, (size_t)n, p, seed, which, true, (cudaStream_t)stream);
 }
 
 int hn_model_forward_async(hn_model* m, const float* x, int B, int in_channels, float* bon, float* cor, void* stream) {

@@ -8,7 +8,9 @@ Boundary kept from the reference:
     ``NotImplementedError`` for any other H x W (model.py:255-256);
   * ``.backbone``, ``.use_rnn``, ``.feature_extractor.list_blocks()``, ``.x_mean``, ``.x_std``.
 Only the path BASELINE.json names is built: ``backbone='resnet50'``, ``use_rnn=True``, inference
-(eval) forward.  The modules below are parameter containers with the reference's names; none of
+(eval) forward -- plus the train-mode FORWARD (batch-statistics BatchNorm with running-stat updates,
+LSTM / head dropout; train.py:52), the first step of the "next" row f1: its outputs carry no autograd
+graph, so ``loss.backward()`` (train.py:278) still has nothing to differentiate.  The modules below are parameter containers with the reference's names; none of
 their torch ``forward`` methods is ever called -- all arithmetic runs in the CUDA library, and there
 is no CPU fallback: a CPU tensor or a missing library raises.
 """
@@ -135,6 +137,8 @@ class HorizonNet(nn.Module):
         object.__setattr__(self, '_lock', threading.Lock())
         object.__setattr__(self, '_tensor_cores', 1)
         object.__setattr__(self, '_refresh_epoch', 0)
+        object.__setattr__(self, 'last_dropout_seed', None)
+        object.__setattr__(self, 'dropout_masks_override', None)    # test hook: (inter-layer, head) masks instead of Philox
         self._slots = None
 
     # ---- weights -> device library --------------------------------------------------------------
@@ -216,19 +220,102 @@ class HorizonNet(nn.Module):
         raise RuntimeError('input normalisation is fused into the stem kernel; call forward()')
 
     def forward(self, x):
+        if self._train_mode_active():
+            return self._forward_train(x)
         x, B, C, h, bon, cor, stream = self._forward_prologue(x)
         _lib.check(_lib.lib().hn_model_forward(h['ptr'], x.data_ptr(), B, C, bon.data_ptr(), cor.data_ptr(), stream),
                    'hn_model_forward')
         return bon, cor
 
-    def _forward_prologue(self, x):
+    # ---- train-mode forward (train.py:52 under net.train()) ---------------------------------------
+    def _train_mode_active(self):
+        """True if any module that behaves differently in training mode is in training mode: a BatchNorm2d (batch
+        statistics), the LSTM (inter-layer dropout) or the head dropout.  torch keeps the flag per module, and
+        train.py:251-256 (--freeze_earlier_blocks) really does mix them."""
+        if (self.bi_rnn.training and self.bi_rnn.dropout > 0) or (self.drop_out.training and self.drop_out.p > 0):
+            return True
+        return any(m.training for m in self.modules() if isinstance(m, nn.BatchNorm2d))
+
+    def _bn_modules(self, h):
+        if 'bn' not in h:
+            lib = _lib.lib()
+            names = [lib.hn_model_bn_name(h['ptr'], i).decode() for i in range(lib.hn_model_num_bn(h['ptr']))]
+            h['bn'] = [(n, self.get_submodule(n)) for n in names]
+        return h['bn']
+
+    def _forward_train(self, x):
+        """Batch-statistics BN (+ running-stat update written back into the module buffers, num_batches_tracked
+        incremented), LSTM inter-layer dropout and head dropout.  The dropout seed is drawn from torch's default
+        generator (reproducible under torch.manual_seed) and kept in ``last_dropout_seed``; the masks are this
+        library's Philox stream, not torch's.  No autograd graph is built (backward: row f1, not implemented)."""
+        x, B, C, h, bon, cor, stream = self._forward_prologue(x, train=True)
+        lib = _lib.lib()
+        bns = self._bn_modules(h)
+        flags = (ctypes.c_ubyte * len(bns))(*[1 if m.training else 0 for _, m in bns])
+        factors = (ctypes.c_double * len(bns))()
+        for i, (_, m) in enumerate(bns):
+            if not (m.training and m.track_running_stats):
+                factors[i] = -1.0
+            elif m.momentum is None:
+                factors[i] = 1.0 / float(int(m.num_batches_tracked) + 1)        # cumulative moving average
+            else:
+                factors[i] = float(m.momentum)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        object.__setattr__(self, 'last_dropout_seed', seed)
+        rnn_p = float(self.bi_rnn.dropout) if self.bi_rnn.training else 0.0
+        head_p = float(self.drop_out.p) if self.drop_out.training else 0.0
+        masks = [None, None]
+        if getattr(self, 'dropout_masks_override', None) is not None:        # parity-test hook: torch-drawn masks
+            masks = [t.to(device=x.device, dtype=torch.float32).contiguous() for t in self.dropout_masks_override]
+            assert all(t.shape == (256, B, 2 * RNN_HIDDEN) for t in masks)
+        _lib.check(lib.hn_model_forward_train(h['ptr'], x.data_ptr(), B, C, bon.data_ptr(), cor.data_ptr(), flags, factors,
+                                              len(bns), seed, rnn_p, head_p,
+                                              masks[0].data_ptr() if masks[0] is not None else None,
+                                              masks[1].data_ptr() if masks[1] is not None else None, stream),
+                   'hn_model_forward_train')
+        with torch.no_grad():
+            for i, (name, m) in enumerate(bns):
+                if factors[i] < 0:
+                    continue
+                for leaf in ('running_mean', 'running_var'):
+                    buf = getattr(m, leaf)
+                    direct = buf.is_cuda and buf.device == x.device and buf.dtype == torch.float32 and buf.is_contiguous()
+                    dst = buf if direct else torch.empty(buf.numel(), device=x.device, dtype=torch.float32)
+                    _lib.check(lib.hn_model_get_tensor(h['ptr'], f'{name}.{leaf}'.encode(), dst.data_ptr(), buf.numel(), 1,
+                                                       stream), 'hn_model_get_tensor')
+                    if not direct:
+                        buf.copy_(dst.view_as(buf))
+                m.num_batches_tracked += 1
+        h['sig'] = self._weight_signature()       # the device copies already hold what the buffers now hold
+        for other in self._handles.values():
+            if other is not h:
+                other['sig'] = None
+        return bon, cor
+
+    def dropout_masks(self, seed, batch, device):
+        """The two multiplicative masks ([256, batch, 1024], values 0 or 1/(1-p)) a train forward with this seed applies:
+        (between the LSTM layers, before the linear head).  Test hook."""
+        out = []
+        dev = torch.device(device)
+        for which, p in ((0, float(self.bi_rnn.dropout)), (1, float(self.drop_out.p))):
+            t = torch.empty(256, batch, 2 * RNN_HIDDEN, device=dev, dtype=torch.float32)
+            with torch.cuda.device(dev):
+                _lib.check(_lib.lib().hn_dropout_mask(seed, which, p, t.data_ptr(), t.numel(),
+                                                      torch.cuda.current_stream(dev).cuda_stream), 'hn_dropout_mask')
+            out.append(t)
+        return out
+
+    def _refuse_train_mode(self):
+        if self._train_mode_active():
+            # the pipelined / host entry points run the eval graph only; in train mode that would diverge silently
+            raise NotImplementedError('this entry point runs the inference graph: call .eval() first, or use forward() '
+                                      'for the train-mode forward (backward is the "next" row f1)')
+
+    def _forward_prologue(self, x, train=False):
         if x.shape[2] != PANO_H or x.shape[3] != PANO_W:
             raise NotImplementedError()                                   # model.py:255-256
-        if self.training:
-            # train mode means batch-statistics BN and dropout in the reference (train.py:52); running the eval graph
-            # instead would diverge silently, with or without grad
-            raise NotImplementedError('horizonnet_b200 implements the inference forward only: call .eval() '
-                                      '(train-mode BN / dropout / backward are the "next" row f1)')
+        if not train:
+            self._refuse_train_mode()
         if not x.is_cuda:
             raise RuntimeError('horizonnet_b200.HorizonNet has no CPU path: move the input to a B200 (cuda) device')
         if x.shape[1] < 3:
@@ -269,6 +356,7 @@ class HorizonNet(nn.Module):
             raise RuntimeError('forward_host expects a contiguous fp32 host array')
         if xt.shape[2] != PANO_H or xt.shape[3] != PANO_W:
             raise NotImplementedError()
+        self._refuse_train_mode()
         B, C = xt.shape[0], xt.shape[1]
         dev = torch.device('cuda', device)
         h = self._handle(dev, B)
@@ -285,6 +373,7 @@ class HorizonNet(nn.Module):
             raise RuntimeError('submit_host expects a contiguous fp32 host array')
         if xt.shape[2] != PANO_H or xt.shape[3] != PANO_W:
             raise NotImplementedError()
+        self._refuse_train_mode()
         h = self._handle(torch.device('cuda', device), xt.shape[0])
         _lib.check(_lib.lib().hn_model_submit_host(h['ptr'], xt.data_ptr(), xt.shape[0], xt.shape[1]), 'hn_model_submit_host')
         h.setdefault('pending', []).append((xt, xt.shape[0]))        # keep the host buffer alive until collected

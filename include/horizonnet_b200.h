@@ -73,6 +73,32 @@ int hn_model_forward_async(hn_model* m, const float* x_nchw_dev, int batch, int 
 /* Makes `stream` wait for every forward enqueued so far by hn_model_forward_async. */
 int hn_model_flush(hn_model* m, void* stream);
 
+/* TRAIN-mode forward: what `net(x)` computes under `net.train()` (reference train.py:52 inside feed_forward,
+ * model.py:254-281 with every nn.BatchNorm2d in training mode and both dropouts active) -- the first step of the
+ * "next" row f1; the backward pass is NOT built.
+ *   - BatchNorm2d i (i < hn_model_num_bn(m), state_dict prefix hn_model_bn_name(m, i)): bn_train[i] = 1 normalises
+ *     with the batch mean / biased variance of the raw conv output and moves running_mean / running_var (the device
+ *     copies inside the model, read them back with hn_model_get_tensor) by bn_factor[i] (= the module's momentum, or
+ *     1/num_batches_tracked for momentum=None; < 0: track_running_stats off) using the unbiased variance;
+ *     bn_train[i] = 0 keeps that module in eval mode (train.py:251-256, --freeze_earlier_blocks).
+ *   - rnn_dropout: nn.LSTM(dropout=0.5) between the recurrent layers (model.py:226); head_dropout: self.drop_out
+ *     (model.py:228, :265); 0 disables.  Masks are Philox4x32-10 functions of (seed, which, element index):
+ *     hn_dropout_mask writes the factors (0 or 1/(1-p)) the forward multiplies with, which = 0 inter-layer
+ *     [256][batch][1024], 1 head [256][batch][1024].  torch's own generator stream is not reproduced; for parity
+ *     against a torch run, rnn_mask_dev / head_mask_dev (same shapes, or NULL) replace the Philox masks.
+ * Each convolution runs twice (statistics pass + real pass); eval-mode entry points called afterwards fold the moved
+ * running statistics again on their own. */
+int hn_model_num_bn(const hn_model* m);
+const char* hn_model_bn_name(const hn_model* m, int i);
+int hn_model_forward_train(hn_model* m, const float* x_nchw_dev, int batch, int in_channels, float* bon_dev,
+                           float* cor_dev, const unsigned char* bn_train, const double* bn_factor, int n_bn,
+                           unsigned long long seed, double rnn_dropout, double head_dropout,
+                           const float* rnn_mask_dev, const float* head_mask_dev, void* stream);
+int hn_dropout_mask(unsigned long long seed, int which, double p, float* out_dev, long long n, void* stream);
+/* Current device copy of a state_dict tensor (e.g. "...bn1.running_mean" after train forwards) -> out
+ * (device pointer if on_device, else host; the host form synchronises). */
+int hn_model_get_tensor(hn_model* m, const char* key, float* out, long long numel, int on_device, void* stream);
+
 /* Same call with HOST buffers: H2D of x, forward, D2H of bon/cor, synchronous.  This is what
  * inference.py:78-79 (`net(x.to(device))` + `.cpu()`) amounts to. */
 int hn_model_forward_host(hn_model* m, const float* x_nchw_host, int batch, int in_channels,

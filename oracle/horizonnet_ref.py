@@ -33,42 +33,68 @@ def _circ_conv(x, w, b, stride, pad_h, pad_w):
     return F.conv2d(x, w, b, stride=stride, padding=(pad_h, 0))
 
 
-def _bn(x, sd, p):
+class TrainMode:
+    """What ``net.train()`` changes in the forward (train.py:52 runs it under net.train()):
+      * every nn.BatchNorm2d not listed in ``frozen`` (state_dict prefixes; train.py:251-256 keeps the frozen blocks in
+        eval mode) normalises with batch statistics and moves its running statistics by ``momentum`` (torch default 0.1;
+        train.py:210-213 --bn_momentum) -- the moved values are collected in ``running``;
+      * nn.LSTM(dropout=p) drops layer-1 outputs on their way into layer 2 (model.py:226) and self.drop_out drops the
+        LSTM output before the linear head (model.py:228, :265).  ``masks`` = (inter-layer, head) multiplicative masks
+        [256, B, 1024] (0 or 1/(1-p)); None draws them with F.dropout from torch's generator in that same order, which is
+        the order the reference consumes it in, so torch.manual_seed reproduces the reference's own masks on CPU.
+    """
+
+    def __init__(self, masks=None, momentum=0.1, frozen=(), p=0.5):
+        self.masks, self.momentum, self.frozen, self.p = masks, momentum, set(frozen), p
+        self.running = {}
+
+    def dropout(self, x, which):
+        if self.p <= 0:
+            return x
+        return x * self.masks[which].to(x.dtype) if self.masks is not None else F.dropout(x, self.p, True)
+
+
+def _bn(x, sd, p, tm=None):
+    if tm is not None and p not in tm.frozen:
+        rm, rv = sd[p + '.running_mean'].clone(), sd[p + '.running_var'].clone()
+        y = F.batch_norm(x, rm, rv, sd[p + '.weight'], sd[p + '.bias'], True, tm.momentum, BN_EPS)
+        tm.running[p + '.running_mean'], tm.running[p + '.running_var'] = rm, rv
+        return y
     return F.batch_norm(x, sd[p + '.running_mean'], sd[p + '.running_var'],
                         sd[p + '.weight'], sd[p + '.bias'], False, 0.0, BN_EPS)
 
 
-def _bottleneck(x, sd, p, stride, has_ds):
+def _bottleneck(x, sd, p, stride, has_ds, tm=None):
     # torchvision resnet.py Bottleneck.forward (v1.5: the stride sits on the 3x3 conv2)
-    out = F.relu(_bn(F.conv2d(x, sd[p + 'conv1.weight']), sd, p + 'bn1'))
-    out = F.relu(_bn(_circ_conv(out, sd[p + 'conv2.1.weight'], None, stride, 1, 1), sd, p + 'bn2'))
-    out = _bn(F.conv2d(out, sd[p + 'conv3.weight']), sd, p + 'bn3')
+    out = F.relu(_bn(F.conv2d(x, sd[p + 'conv1.weight']), sd, p + 'bn1', tm))
+    out = F.relu(_bn(_circ_conv(out, sd[p + 'conv2.1.weight'], None, stride, 1, 1), sd, p + 'bn2', tm))
+    out = _bn(F.conv2d(out, sd[p + 'conv3.weight']), sd, p + 'bn3', tm)
     if has_ds:
-        x = _bn(F.conv2d(x, sd[p + 'downsample.0.weight'], stride=stride), sd, p + 'downsample.1')
+        x = _bn(F.conv2d(x, sd[p + 'downsample.0.weight'], stride=stride), sd, p + 'downsample.1', tm)
     return F.relu(out + x)
 
 
-def encoder(x, sd):
+def encoder(x, sd, tm=None):
     """model.py:71-82 (Resnet.forward): stem + layer1..4, returns the 4 feature maps."""
     e = 'feature_extractor.encoder.'
     x = _circ_conv(x, sd[e + 'conv1.1.weight'], None, 2, 3, 3)        # model.py:73 (7x7 s2, wrapped)
-    x = F.relu(_bn(x, sd, e + 'bn1'))                                  # model.py:74-75
+    x = F.relu(_bn(x, sd, e + 'bn1', tm))                              # model.py:74-75
     x = F.max_pool2d(x, 3, 2, 1)                                       # model.py:76 (NOT wrapped)
     feats = []
     for li, nblk in zip((1, 2, 3, 4), (3, 4, 6, 3)):
         for b in range(nblk):
             stride = 2 if (b == 0 and li > 1) else 1
-            x = _bottleneck(x, sd, f'{e}layer{li}.{b}.', stride, b == 0)
+            x = _bottleneck(x, sd, f'{e}layer{li}.{b}.', stride, b == 0, tm)
         feats.append(x)                                                # model.py:78-81
     return feats
 
 
-def global_height_conv(x, sd, s, out_w):
+def global_height_conv(x, sd, s, out_w, tm=None):
     """model.py:148-156 (GlobalHeightConv.forward) for scale index s."""
     for j in range(4):
         p = f'reduce_height_module.ghc_lst.{s}.layer.{j}.layers.'
         x = _circ_conv(x, sd[p + '0.1.weight'], sd[p + '0.1.bias'], (2, 1), 1, 1)   # model.py:129
-        x = F.relu(_bn(x, sd, p + '1'))                                              # model.py:130-131
+        x = F.relu(_bn(x, sd, p + '1', tm))                                          # model.py:130-131
     factor = out_w // x.shape[3]                                                     # model.py:152
     x = torch.cat([x[..., -1:], x, x[..., :1]], 3)                                   # model.py:153
     x = F.interpolate(x, size=(x.shape[2], out_w + 2 * factor), mode='bilinear',
@@ -94,23 +120,27 @@ def lstm_layer_dir(x, w_ih, w_hh, b_ih, b_hh, reverse):
     return out
 
 
-def bi_lstm(x, sd):
+def bi_lstm(x, sd, tm=None):
     for layer in range(2):
+        if layer == 1 and tm is not None:
+            x = tm.dropout(x, 0)          # nn.LSTM(dropout=0.5), train mode only (model.py:226)
         outs = []
         for suffix, rev in (('', False), ('_reverse', True)):
             outs.append(lstm_layer_dir(
                 x, sd[f'bi_rnn.weight_ih_l{layer}{suffix}'], sd[f'bi_rnn.weight_hh_l{layer}{suffix}'],
                 sd[f'bi_rnn.bias_ih_l{layer}{suffix}'], sd[f'bi_rnn.bias_hh_l{layer}{suffix}'], rev))
-        x = torch.cat(outs, dim=2)        # eval mode: inter-layer dropout(0.5) is the identity
+        x = torch.cat(outs, dim=2)
     return x
 
 
-def forward(sd, x, dtype=torch.float32, return_stages=False):
+def forward(sd, x, dtype=torch.float32, return_stages=False, train=None):
     """model.py:254-281.  sd: the 448-key state_dict; x: [B, C>=3, 512, 1024] in [0,1].
 
     Returns (bon [B,2,1024], cor [B,1,1024]) like the reference; with return_stages also a dict of
-    intermediate tensors (NCHW) used by the per-stage parity tests.
+    intermediate tensors (NCHW) used by the per-stage parity tests.  train: a TrainMode (train-mode forward; the
+    moved running statistics end up in train.running), None = eval.
     """
+    tm = train
     if x.shape[2] != 512 or x.shape[3] != 1024:
         raise NotImplementedError()                                    # model.py:255-256
     sd = {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in sd.items()}
@@ -118,14 +148,15 @@ def forward(sd, x, dtype=torch.float32, return_stages=False):
     mean = x.new_tensor(X_MEAN).view(1, 3, 1, 1)
     std = x.new_tensor(X_STD).view(1, 3, 1, 1)
     x = (x[:, :3] - mean) / std                                        # model.py:248-252
-    feats = encoder(x, sd)
+    feats = encoder(x, sd, tm)
     bs = x.shape[0]
     out_w = 1024 // 4                                                  # model.py:260
-    red = [global_height_conv(f, sd, s, out_w).reshape(bs, -1, out_w) for s, f in enumerate(feats)]
+    red = [global_height_conv(f, sd, s, out_w, tm).reshape(bs, -1, out_w) for s, f in enumerate(feats)]
     feature = torch.cat(red, dim=1)                                    # model.py:175-178 -> [B,1024,256]
     seq = feature.permute(2, 0, 1)                                     # model.py:263
-    rnn_out = bi_lstm(seq, sd)                                         # model.py:264 (dropout = id in eval)
-    out = rnn_out @ sd['linear.weight'].t() + sd['linear.bias']        # model.py:266
+    rnn_out = bi_lstm(seq, sd, tm)                                     # model.py:264 (dropout = id in eval)
+    head_in = rnn_out if tm is None else tm.dropout(rnn_out, 1)        # model.py:265 self.drop_out
+    out = head_in @ sd['linear.weight'].t() + sd['linear.bias']        # model.py:266
     out = out.view(out.shape[0], out.shape[1], 3, 4).permute(1, 2, 0, 3)
     out = out.contiguous().view(out.shape[0], 3, -1)                   # model.py:267-269
     cor, bon = out[:, :1], out[:, 1:]                                  # model.py:278-279

@@ -3,7 +3,8 @@
 Run in the build container only (the GPU box has no /root/reference):
     python tests/golden/make_golden.py
 Outputs (committed): tests/golden/forward_identity.npz, forward_randombn.npz,
-panostretch_small.npz, panostretch_rows.npz, tta_randombn.npz, augment.npz (row f3), rotate.npz (row f4).  The two shims are the ones SURVEY.md section 8c
+panostretch_small.npz, panostretch_rows.npz, tta_randombn.npz, augment.npz (row f3), rotate.npz (row f4),
+train_all.npz / train_frozen1.npz (row f1, train-mode forward).  The two shims are the ones SURVEY.md section 8c
 describes: torchvision.resnet50 is forced to weights=None (no network), nothing else is patched.
 Weights/inputs come from horizonnet_b200.weights (numpy RandomState => reproducible on any box).
 """
@@ -228,10 +229,74 @@ def golden_rotate():
     print('rotate golden written')
 
 
+TRAIN_SEED = 1234
+
+
+def replay_dropout_masks(seed, batch, p=0.5):
+    """The two masks the reference's train-mode forward consumes after torch.manual_seed(seed): at::dropout draws
+    `empty_like(x).bernoulli_(1 - p).div_(1 - p)` -- first inside nn.LSTM on the layer-1 output [256, B, 1024]
+    (model.py:226), then in self.drop_out on the LSTM output (model.py:265).  Nothing else on the path draws."""
+    torch.manual_seed(seed)
+    return [torch.empty(256, batch, 1024).bernoulli_(1 - p).div_(1 - p) for _ in range(2)]
+
+
+def golden_train(name, freeze_earlier_blocks, bn_momentum=None, batch=2, wseed=1):
+    """'next' row f1, forward only: the REAL reference under net.train() exactly as train.py drives it
+    (:249 net.train(); :251-256 frozen blocks back to eval; :210-213 --bn_momentum), one forward (:52, without
+    autocast: fp32 is the parity target).  Stores outputs, every BatchNorm2d's moved running statistics and the dropout
+    masks (recovered by replaying torch's generator; the mint asserts that the oracle fed with those masks reproduces
+    the reference to 2e-5 -- wrong masks would differ by O(1) -- which proves the replay)."""
+    from oracle import horizonnet_ref as oracle
+    net = ref_model.HorizonNet('resnet50', True)
+    sd = synthetic_state_dict(wseed, 'random')
+    net.load_state_dict(sd, strict=True)
+    if bn_momentum:
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.momentum = bn_momentum                                # train.py:210-213
+    net.train()                                                         # train.py:249
+    frozen = []
+    if freeze_earlier_blocks != -1:
+        blocks = net.feature_extractor.list_blocks()
+        for i in range(freeze_earlier_blocks + 1):
+            for m in blocks[i]:
+                m.eval()                                                # train.py:251-256
+        frozen = [n for n, m in net.named_modules() if isinstance(m, torch.nn.BatchNorm2d) and not m.training]
+    x = synthetic_panoramas(batch, seed=200 + wseed)
+    torch.manual_seed(TRAIN_SEED)
+    with torch.no_grad():
+        bon, cor = net(x)
+    after = net.state_dict()
+    masks = replay_dropout_masks(TRAIN_SEED, batch)
+    tm = oracle.TrainMode(masks=masks, momentum=bn_momentum or 0.1, frozen=frozen)
+    with torch.no_grad():
+        o_bon, o_cor = oracle.forward(sd, x, train=tm)
+    err = max(float((o_bon - bon).abs().max()), float((o_cor - cor).abs().max()))
+    assert err < 2e-5, f'mask replay / oracle restatement differs from the reference: {err}'   # wrong masks: O(1)
+    bn_keys = [k for k in sd if k.endswith('running_mean') or k.endswith('running_var')]
+    for k in bn_keys:
+        moved = not torch.equal(after[k], sd[k])
+        assert moved == (k.rsplit('.', 1)[0] not in frozen), k
+        if moved:
+            assert torch.allclose(tm.running[k], after[k], rtol=1e-5, atol=1e-6), k
+    nbt = [int(after[k]) for k in after if k.endswith('num_batches_tracked')]
+    out = dict(bon=bon.numpy(), cor=cor.numpy(), wseed=wseed, x_seed=200 + wseed, batch=batch, train_seed=TRAIN_SEED,
+               momentum=np.float64(bn_momentum or 0.1), frozen=np.array(frozen, dtype='U'),
+               masks_bits=np.packbits(np.stack([(m > 0).numpy() for m in masks]).reshape(-1)),
+               running=np.concatenate([after[k].numpy().reshape(-1) for k in bn_keys]).astype(np.float32),
+               num_batches_tracked=np.array(nbt))
+    np.savez_compressed(os.path.join(HERE, f'train_{name}.npz'), **out)
+    print('train golden', name, 'oracle-vs-reference', err, 'frozen BN modules:', len(frozen), 'bon', float(bon.abs().max()), 'cor', float(cor.abs().max()))
+
+
 if __name__ == '__main__':
     if len(sys.argv) > 1 and sys.argv[1] == 'next':        # only the fixtures of the "next" rows f3 / f4
         golden_augment()
         golden_rotate()
+        sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == 'train':       # only the train-mode forward fixtures (row f1, forward)
+        golden_train('all', -1)
+        golden_train('frozen1', 1, bn_momentum=0.01)
         sys.exit(0)
     golden_augment()
     golden_rotate()
@@ -239,3 +304,5 @@ if __name__ == '__main__':
     golden_panostretch()
     golden_forward('identity', seed=0, bn='identity', batch=2)
     golden_forward('randombn', seed=1, bn='random', batch=1)
+    golden_train('all', -1)
+    golden_train('frozen1', 1, bn_momentum=0.01)

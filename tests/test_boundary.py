@@ -72,14 +72,26 @@ def test_checkpoint_round_trip_through_the_real_reference_utils(tmp_path):
         assert torch.equal(v, sd[k]), k
 
 
-def test_train_mode_forward_is_refused_not_silently_run_in_eval_mode():
-    """net.train() under torch.no_grad() must not run the eval graph (the reference would use batch
-    statistics and dropout there, train.py:52)."""
+def test_train_mode_never_runs_the_eval_graph():
+    """net.train() (with or without torch.no_grad()) must not run the eval graph -- the reference uses
+    batch statistics and dropout there (train.py:52).  forward() routes to the train-mode kernels (GPU only, so a CPU
+    tensor is refused like in eval mode); the throughput / host entry points run the inference graph only and refuse."""
     net = HorizonNet('resnet50', True).train()
-    with torch.no_grad(), pytest.raises(NotImplementedError):
+    assert net._train_mode_active()
+    with torch.no_grad(), pytest.raises(RuntimeError, match='no CPU path'):
         net(torch.zeros(1, 3, 512, 1024))
-    with pytest.raises(NotImplementedError):
-        net(torch.zeros(1, 3, 512, 1024))
+    for call in (net.forward_pipelined, net.forward_host, net.submit_host):
+        with pytest.raises(NotImplementedError):
+            call(torch.zeros(1, 3, 512, 1024))
+    # torch keeps the flag per module (train.py:251-256 mixes them): one BatchNorm2d in training mode is enough
+    net.eval()
+    assert not net._train_mode_active()
+    net.feature_extractor.encoder.layer3[0].bn2.train()
+    assert net._train_mode_active()
+    net.eval().drop_out.train()
+    assert net._train_mode_active()
+    net.eval().bi_rnn.train()
+    assert net._train_mode_active()
 
 
 def test_module_surface_used_by_reference_callers():

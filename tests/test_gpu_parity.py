@@ -514,3 +514,95 @@ def test_rotate_panorama_matches_the_real_reference_golden(golden_dir):
     assert np.abs(rotatePanorama(img1, R=q) - panorotate_ref.rotate_panorama(img1, R=q)).max() < 1e-12
     with pytest.raises(RuntimeError):
         rotatePanorama(np.zeros((8, 15, 3)), R=np.eye(3))         # odd width: the reference's padding rule is undefined
+
+
+# ------------------------------------------------------------------------------- train-mode forward (row f1, forward only)
+def _train_net(sd, tensor_cores, frozen=(), momentum=None):
+    net = HorizonNet('resnet50', True)
+    net.load_state_dict(sd, strict=True)
+    net.use_tensor_cores(tensor_cores)
+    net = net.to(DEV).train()                                           # train.py:249
+    if frozen:                                                          # train.py:251-256 (--freeze_earlier_blocks 1)
+        blocks = net.feature_extractor.list_blocks()
+        for i in range(2):
+            for m in blocks[i]:
+                m.eval()
+        assert sorted(n for n, m in net.named_modules() if isinstance(m, torch.nn.BatchNorm2d) and not m.training) == \
+            sorted(frozen)
+    if momentum is not None:
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.momentum = momentum                                   # train.py:210-213
+    return net
+
+
+@pytest.mark.parametrize('tensor_cores', [False, True])
+@pytest.mark.parametrize('name', ['all', 'frozen1'])
+def test_train_forward_matches_the_real_reference_golden(golden_dir, name, tensor_cores):
+    """net.train(); net(x) (train.py:52) against the REAL reference's train-mode forward: batch-statistics BatchNorm,
+    running-statistics update, both dropouts (the reference's own masks, injected), frozen blocks and --bn_momentum."""
+    from train_fixture import train_golden
+    g, sd, x, masks, running, frozen = train_golden(golden_dir, name)
+    net = _train_net(sd, tensor_cores, frozen, float(g['momentum']) if name == 'frozen1' else None)
+    net.dropout_masks_override = masks
+    bon, cor = net(x.to(DEV))
+    net.check()
+    assert np.abs(bon.cpu().numpy() - g['bon']).max() < 1e-4
+    assert np.abs(cor.cpu().numpy() - g['cor']).max() < 1e-4
+    assert not bon.requires_grad                 # forward only: there is no autograd graph behind these outputs
+    after = net.state_dict()
+    for k, v in running.items():
+        if k.rsplit('.', 1)[0] in frozen:
+            assert torch.equal(after[k].cpu(), sd[k]), k
+        else:
+            assert torch.allclose(after[k].cpu(), v, rtol=1e-4, atol=1e-5), k
+    nbt = [int(after[k]) for k in after if k.endswith('num_batches_tracked')]
+    assert nbt == list(g['num_batches_tracked'])
+    # back to eval: the moved running statistics are the ones folded into the inference graph now
+    net.eval()
+    after_cpu = {k: v.cpu() for k, v in after.items()}
+    with torch.no_grad():
+        ebon, ecor = net(x[:1].to(DEV))
+        rbon, rcor = horizonnet_ref.forward(after_cpu, x[:1])
+    assert (ebon.cpu() - rbon).abs().max().item() < 1e-4 and (ecor.cpu() - rcor).abs().max().item() < 1e-4
+    with torch.no_grad():
+        obon, _ = horizonnet_ref.forward(sd, x[:1])
+    assert (rbon - obon).abs().max().item() > 1e-3 or name == 'frozen1'     # ... and they did move the result
+
+
+def test_train_forward_with_device_dropout_masks_matches_oracle_and_is_seeded():
+    """The library's own Philox masks: a pure function of the seed (drawn from torch's generator, so torch.manual_seed
+    makes a run reproducible), Bernoulli(0.5) scaled by 2, independent between the two dropouts; the oracle fed with
+    exactly those masks agrees with the device forward."""
+    sd = synthetic_state_dict(5, 'random')
+    x = synthetic_panoramas(2, seed=31)
+    net = _train_net(sd, True)
+    torch.manual_seed(77)
+    bon, cor = net(x.to(DEV))
+    seed = net.last_dropout_seed
+    m0, m1 = net.dropout_masks(seed, 2, DEV)
+    for m in (m0, m1):
+        assert set(torch.unique(m).tolist()) == {0.0, 2.0}
+        assert abs(float((m > 0).float().mean()) - 0.5) < 0.005
+    assert 0.45 < float(((m0 > 0) == (m1 > 0)).float().mean()) < 0.55
+    tm = horizonnet_ref.TrainMode(masks=[m0.cpu(), m1.cpu()])
+    with torch.no_grad():
+        rbon, rcor = horizonnet_ref.forward(sd, x, train=tm)
+    assert (bon.cpu() - rbon).abs().max().item() < 1e-4 and (cor.cpu() - rcor).abs().max().item() < 1e-4
+    # same torch seed, fresh weights -> same masks -> bit-identical outputs; another seed -> other masks
+    net2 = _train_net(sd, True)
+    torch.manual_seed(77)
+    bon2, cor2 = net2(x.to(DEV))
+    assert net2.last_dropout_seed == seed and torch.equal(bon2, bon) and torch.equal(cor2, cor)
+    bon3, _ = net2(x.to(DEV))
+    assert net2.last_dropout_seed != seed and not torch.equal(bon3, bon)
+    # dropout off (p = 0 modules in eval) but BatchNorm in train mode: still the train path, no masks
+    net2.bi_rnn.eval(); net2.drop_out.eval()
+    assert net2._train_mode_active()
+    net3 = _train_net(sd, True)
+    net3.bi_rnn.eval(); net3.drop_out.eval()
+    b3, c3 = net3(x.to(DEV))
+    tm = horizonnet_ref.TrainMode(p=0.0)
+    with torch.no_grad():
+        rb, rc = horizonnet_ref.forward(sd, x, train=tm)
+    assert (b3.cpu() - rb).abs().max().item() < 1e-4 and (c3.cpu() - rc).abs().max().item() < 1e-4

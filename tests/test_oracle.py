@@ -11,6 +11,7 @@ import torch
 from horizonnet_b200._spec import state_dict_spec
 from horizonnet_b200.weights import synthetic_state_dict, synthetic_panoramas
 from oracle import horizonnet_ref, panostretch_ref
+from train_fixture import train_golden as _train_golden
 
 KGRID = (0.5, 0.75, 1.0, 1.25, 1.5, 1.75, 2.0)
 
@@ -141,3 +142,36 @@ def test_rotate_oracle_matches_the_real_rotatePanorama(golden_dir):
         o = panorotate_ref.rotate_panorama(img, R=g[f'{name}_R'])
         assert np.abs(o[g['rows']] - g[f'{name}_rows']).max() < 1e-12, name
         assert abs(o.sum() - float(g[f'{name}_sum'])) < 1e-6, name
+
+
+# ------------------------------------------------------------------------------- train-mode forward (row f1, forward only)
+@pytest.mark.parametrize('name', ['all', 'frozen1'])
+def test_train_mode_oracle_matches_the_real_reference(golden_dir, name):
+    """The oracle's TrainMode (batch-statistics BN + running update, both dropouts; frozen blocks like
+    train.py:251-256, --bn_momentum like :210-213) against the REAL reference run under net.train(), with the masks
+    the reference consumed."""
+    g, sd, x, masks, running, frozen = _train_golden(golden_dir, name)
+    tm = horizonnet_ref.TrainMode(masks=masks, momentum=float(g['momentum']), frozen=frozen)
+    with torch.no_grad():
+        bon, cor = horizonnet_ref.forward(sd, x, train=tm)
+    assert np.abs(bon.numpy() - g['bon']).max() < 2e-5
+    assert np.abs(cor.numpy() - g['cor']).max() < 2e-5
+    assert len(frozen) == (0 if name == 'all' else 11)          # bn1 + layer1's 10 BatchNorm2d (blocks 0 and 1)
+    for k, v in running.items():
+        if k.rsplit('.', 1)[0] in frozen:
+            assert torch.equal(v, sd[k]), k                      # the reference left frozen statistics alone
+        else:
+            assert torch.allclose(tm.running[k], v, rtol=1e-5, atol=1e-6), k
+    assert set(tm.running) == {k for k in running if k.rsplit('.', 1)[0] not in frozen}
+    assert g['num_batches_tracked'].sum() == 69 - len(frozen)
+
+
+def test_train_mode_oracle_draws_the_reference_masks_from_torchs_generator(golden_dir):
+    """masks=None: F.dropout in the reference's order reproduces, under the same torch.manual_seed, what the reference
+    drew inside nn.LSTM and self.drop_out (CPU generator)."""
+    g, sd, x, masks, _, _ = _train_golden(golden_dir, 'all')
+    torch.manual_seed(int(g['train_seed']))
+    with torch.no_grad():
+        bon, cor = horizonnet_ref.forward(sd, x, train=horizonnet_ref.TrainMode())
+    assert np.abs(bon.numpy() - g['bon']).max() < 2e-5 and np.abs(cor.numpy() - g['cor']).max() < 2e-5
+    assert 0.49 < float((masks[0] > 0).float().mean()) < 0.51
