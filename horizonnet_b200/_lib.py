@@ -37,6 +37,16 @@ SIGNATURES = {
     'hn_model_bn_name': (ctypes.c_char_p, [vp, ctypes.c_int]),
     'hn_model_forward_train': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int,
                                               ctypes.c_ulonglong, ctypes.c_double, ctypes.c_double, vp, vp, vp]),
+    'hn_train_forward': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int,
+                                        ctypes.c_ulonglong, ctypes.c_double, ctypes.c_double, vp, vp, vp]),
+    'hn_train_backward': (ctypes.c_int, [vp, vp, vp, vp]),
+    'hn_model_get_grad': (ctypes.c_int, [vp, ctypes.c_char_p, vp, ctypes.c_longlong, vp]),
+    'hn_conv2d_backward': (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp]
+                           + [ctypes.c_int] * 7 + [vp, vp, vp]),
+    'hn_bn_forward_backward': (ctypes.c_int, [vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp,
+                                              ctypes.c_double, ctypes.c_int, ctypes.c_int, vp, vp, vp, vp, vp, vp, vp, vp, vp,
+                                              vp]),
+    'hn_lstm_layer_backward': (ctypes.c_int, [vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp, vp, vp]),
     'hn_dropout_mask': (ctypes.c_int, [ctypes.c_ulonglong, ctypes.c_int, ctypes.c_double, vp, ctypes.c_longlong, vp]),
     'hn_model_get_tensor': (ctypes.c_int, [vp, ctypes.c_char_p, vp, ctypes.c_longlong, ctypes.c_int, vp]),
     'hn_model_forward_host': (ctypes.c_int, [vp, vp, ctypes.c_int, ctypes.c_int, vp, vp]),

@@ -9,8 +9,9 @@ Boundary kept from the reference:
   * ``.backbone``, ``.use_rnn``, ``.feature_extractor.list_blocks()``, ``.x_mean``, ``.x_std``.
 Only the path BASELINE.json names is built: ``backbone='resnet50'``, ``use_rnn=True``, inference
 (eval) forward -- plus the train-mode FORWARD (batch-statistics BatchNorm with running-stat updates,
-LSTM / head dropout; train.py:52), the first step of the "next" row f1: its outputs carry no autograd
-graph, so ``loss.backward()`` (train.py:278) still has nothing to differentiate.  The modules below are parameter containers with the reference's names; none of
+LSTM / head dropout; train.py:52) and its backward (train.py:278 ``loss.backward()``): with autograd on,
+``forward`` in train mode returns outputs whose grad_fn runs the library's backward pass and fills
+``.grad`` of every parameter -- row f1 as a first correct fp32 path (not tensor-core, no DDP).  The modules below are parameter containers with the reference's names; none of
 their torch ``forward`` methods is ever called -- all arithmetic runs in the CUDA library, and there
 is no CPU fallback: a CPU tensor or a missing library raises.
 """
@@ -108,6 +109,26 @@ class _HeightStage(nn.Module):
         self.cs = cs
         self.out_scale = out_scale
         self.ghc_lst = nn.ModuleList([_HeightConv(c, c // out_scale) for c in cs])
+
+
+class _TrainStep(torch.autograd.Function):
+    """forward = hn_train_forward (train-mode forward with a tape), backward = hn_train_backward.  The parameters are
+    inputs only so that autograd routes their gradients; the arithmetic reads the device copies the handle holds."""
+
+    @staticmethod
+    def forward(ctx, net, x, *params):
+        bon, cor = net._train_forward_impl(x, tape=True)
+        ctx.net, ctx.device = net, x.device
+        ctx.wanted = [p.requires_grad for p in params]
+        return bon, cor
+
+    @staticmethod
+    def backward(ctx, dbon, dcor):
+        B = dbon.shape[0] if dbon is not None else dcor.shape[0]
+        dbon = torch.zeros(B, 2, PANO_W, device=ctx.device) if dbon is None else dbon.to(torch.float32).contiguous()
+        dcor = torch.zeros(B, 1, PANO_W, device=ctx.device) if dcor is None else dcor.to(torch.float32).contiguous()
+        grads = ctx.net._train_backward_impl(ctx.device, dbon, dcor, ctx.wanted)
+        return (None, None) + tuple(grads)
 
 
 class HorizonNet(nn.Module):
@@ -247,7 +268,18 @@ class HorizonNet(nn.Module):
         """Batch-statistics BN (+ running-stat update written back into the module buffers, num_batches_tracked
         incremented), LSTM inter-layer dropout and head dropout.  The dropout seed is drawn from torch's default
         generator (reproducible under torch.manual_seed) and kept in ``last_dropout_seed``; the masks are this
-        library's Philox stream, not torch's.  No autograd graph is built (backward: row f1, not implemented)."""
+        library's Philox stream, not torch's.
+
+        With autograd on and a parameter that requires grad this is the TRAINING STEP's forward (hn_train_forward:
+        exact-fp32 kernels + a tape) and the outputs carry a grad_fn whose backward is hn_train_backward: the
+        reference's ``loss.backward()`` (train.py:278) then fills ``.grad`` of every parameter.  Otherwise (no_grad /
+        all frozen) the tensor-core forward without tape runs (hn_model_forward_train)."""
+        params = [(k, p) for k, p in self.named_parameters()]
+        if torch.is_grad_enabled() and any(p.requires_grad for _, p in params):
+            return _TrainStep.apply(self, x, *[p for _, p in params])
+        return self._train_forward_impl(x, tape=False)
+
+    def _train_forward_impl(self, x, tape):
         x, B, C, h, bon, cor, stream = self._forward_prologue(x, train=True)
         lib = _lib.lib()
         bns = self._bn_modules(h)
@@ -268,11 +300,12 @@ class HorizonNet(nn.Module):
         if getattr(self, 'dropout_masks_override', None) is not None:        # parity-test hook: torch-drawn masks
             masks = [t.to(device=x.device, dtype=torch.float32).contiguous() for t in self.dropout_masks_override]
             assert all(t.shape == (256, B, 2 * RNN_HIDDEN) for t in masks)
-        _lib.check(lib.hn_model_forward_train(h['ptr'], x.data_ptr(), B, C, bon.data_ptr(), cor.data_ptr(), flags, factors,
-                                              len(bns), seed, rnn_p, head_p,
-                                              masks[0].data_ptr() if masks[0] is not None else None,
-                                              masks[1].data_ptr() if masks[1] is not None else None, stream),
-                   'hn_model_forward_train')
+        fn = lib.hn_train_forward if tape else lib.hn_model_forward_train
+        _lib.check(fn(h['ptr'], x.data_ptr(), B, C, bon.data_ptr(), cor.data_ptr(), flags, factors, len(bns), seed, rnn_p,
+                      head_p, masks[0].data_ptr() if masks[0] is not None else None,
+                      masks[1].data_ptr() if masks[1] is not None else None, stream),
+                   'hn_train_forward' if tape else 'hn_model_forward_train')
+        h['tape_keepalive'] = (x, masks) if tape else None     # the backward reads the masks again
         with torch.no_grad():
             for i, (name, m) in enumerate(bns):
                 if factors[i] < 0:
@@ -291,6 +324,25 @@ class HorizonNet(nn.Module):
             if other is not h:
                 other['sig'] = None
         return bon, cor
+
+    def _train_backward_impl(self, device, dbon, dcor, wanted):
+        """d(loss)/d(bon), d(loss)/d(cor) -> one gradient per named parameter (None where not wanted)."""
+        lib = _lib.lib()
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        h = self._handles[key]
+        stream = torch.cuda.current_stream(device).cuda_stream
+        with torch.cuda.device(device):
+            _lib.check(lib.hn_train_backward(h['ptr'], dbon.data_ptr(), dcor.data_ptr(), stream), 'hn_train_backward')
+            grads = []
+            for (name, p), want in zip(self.named_parameters(), wanted):
+                if not want:
+                    grads.append(None)
+                    continue
+                g = torch.empty(p.shape, device=device, dtype=torch.float32)
+                _lib.check(lib.hn_model_get_grad(h['ptr'], name.encode(), g.data_ptr(), g.numel(), stream), 'hn_model_get_grad')
+                grads.append(g.to(device=p.device, dtype=p.dtype))
+        h['tape_keepalive'] = None
+        return grads
 
     def dropout_masks(self, seed, batch, device):
         """The two multiplicative masks ([256, batch, 1024], values 0 or 1/(1-p)) a train forward with this seed applies:

@@ -99,6 +99,20 @@ int hn_dropout_mask(unsigned long long seed, int which, double p, float* out_dev
  * (device pointer if on_device, else host; the host form synchronises). */
 int hn_model_get_tensor(hn_model* m, const char* key, float* out, long long numel, int on_device, void* stream);
 
+/* Training step (row f1; reference train.py:44-58 feed_forward + :272-281 backward).  hn_train_forward = the train-mode
+ * forward above (same arguments) but on exact-fp32 kernels and with a tape: every conv output and activation is kept.
+ * hn_train_backward takes d(loss)/d(bon) [batch][2][1024] and d(loss)/d(cor) [batch][1][1024] (device) -- the losses
+ * themselves (train.py:53-56: L1 + BCE-with-logits) and the optimizer (train.py:216-223) stay with the caller -- and
+ * leaves d(loss)/d(parameter) for every state_dict parameter in the reference's layout (nn.Conv2d OIHW, nn.LSTM
+ * [4H][in], ...), read back with hn_model_get_grad (device pointer).  One backward per forward.  First correct path:
+ * fp32 CUDA-core kernels; no tensor-core dgrad/wgrad, loss scaling or gradient all-reduce yet. */
+int hn_train_forward(hn_model* m, const float* x_nchw_dev, int batch, int in_channels, float* bon_dev, float* cor_dev,
+                     const unsigned char* bn_train, const double* bn_factor, int n_bn, unsigned long long seed,
+                     double rnn_dropout, double head_dropout, const float* rnn_mask_dev, const float* head_mask_dev,
+                     void* stream);
+int hn_train_backward(hn_model* m, const float* dbon_dev, const float* dcor_dev, void* stream);
+int hn_model_get_grad(hn_model* m, const char* key, float* out_dev, long long numel, void* stream);
+
 /* Same call with HOST buffers: H2D of x, forward, D2H of bon/cor, synchronous.  This is what
  * inference.py:78-79 (`net(x.to(device))` + `.cpu()`) amounts to. */
 int hn_model_forward_host(hn_model* m, const float* x_nchw_host, int batch, int in_channels,
@@ -200,6 +214,17 @@ int hn_conv2d(const float* in_dev, int B, int H, int W, int Cin, int in_halo,
               const float* w_packed_dev, const float* scale_dev, const float* shift_dev,
               const float* residual_dev, int Cout, int kh, int kw, int sh, int sw, int ph, int pw,
               int relu, float* out_dev, int out_halo, int impl, void* stream);
+/* Backward building blocks of the training step, for unit tests against torch.autograd (train_step.cu):
+ * weight + data gradient of one convolution (dz: halo-1 NHWC with circular halo columns; din may be NULL),
+ * BatchNorm2d (+identity, ReLU) forward+backward, and one bidirectional LSTM layer's gate gradients. */
+int hn_conv2d_backward(const float* in, int B, int H, int W, int Cin, int in_halo, const float* w_oihw, const float* dz,
+                       int Cout, int kh, int kw, int sh, int sw, int ph, int pw, float* din, float* dw_oihw, void* stream);
+int hn_bn_forward_backward(const float* z, int B, int H, int W, int C, const float* gamma, const float* beta,
+                           float* running_mean, float* running_var, double factor, int train, int relu, const float* res,
+                           float* y, const float* dy, float* dz, float* dres, float* dgamma, float* dbeta, float* bn_scratch,
+                           double* sums, void* stream);
+int hn_lstm_layer_backward(const float* xp, const float* hout, const float* whf, const float* whb, const float* dout, int T,
+                           int B, float* dgates, float* scratch, void* stream);
 
 /* One bidirectional LSTM layer recurrence: xproj [T][B][4096] (input projection + both biases,
  * column = dir*2048 + gate*512 + unit), w_hh_* [2048][512] (PyTorch layout), out [T][B][1024]. */

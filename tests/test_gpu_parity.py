@@ -545,11 +545,12 @@ def test_train_forward_matches_the_real_reference_golden(golden_dir, name, tenso
     g, sd, x, masks, running, frozen = train_golden(golden_dir, name)
     net = _train_net(sd, tensor_cores, frozen, float(g['momentum']) if name == 'frozen1' else None)
     net.dropout_masks_override = masks
-    bon, cor = net(x.to(DEV))
+    with torch.no_grad():                        # no tape: the tensor-core / fp32 inference kernels, each conv twice
+        bon, cor = net(x.to(DEV))
     net.check()
     assert np.abs(bon.cpu().numpy() - g['bon']).max() < 1e-4
     assert np.abs(cor.cpu().numpy() - g['cor']).max() < 1e-4
-    assert not bon.requires_grad                 # forward only: there is no autograd graph behind these outputs
+    assert not bon.requires_grad
     after = net.state_dict()
     for k, v in running.items():
         if k.rsplit('.', 1)[0] in frozen:
@@ -578,7 +579,8 @@ def test_train_forward_with_device_dropout_masks_matches_oracle_and_is_seeded():
     x = synthetic_panoramas(2, seed=31)
     net = _train_net(sd, True)
     torch.manual_seed(77)
-    bon, cor = net(x.to(DEV))
+    with torch.no_grad():
+        bon, cor = net(x.to(DEV))
     seed = net.last_dropout_seed
     m0, m1 = net.dropout_masks(seed, 2, DEV)
     for m in (m0, m1):
@@ -592,17 +594,193 @@ def test_train_forward_with_device_dropout_masks_matches_oracle_and_is_seeded():
     # same torch seed, fresh weights -> same masks -> bit-identical outputs; another seed -> other masks
     net2 = _train_net(sd, True)
     torch.manual_seed(77)
-    bon2, cor2 = net2(x.to(DEV))
-    assert net2.last_dropout_seed == seed and torch.equal(bon2, bon) and torch.equal(cor2, cor)
-    bon3, _ = net2(x.to(DEV))
-    assert net2.last_dropout_seed != seed and not torch.equal(bon3, bon)
+    with torch.no_grad():
+        bon2, cor2 = net2(x.to(DEV))
+        bon3, _ = net2(x.to(DEV))
+    assert net2.last_dropout_seed != seed and torch.equal(bon2, bon) and torch.equal(cor2, cor)
+    assert not torch.equal(bon3, bon)
     # dropout off (p = 0 modules in eval) but BatchNorm in train mode: still the train path, no masks
     net2.bi_rnn.eval(); net2.drop_out.eval()
     assert net2._train_mode_active()
     net3 = _train_net(sd, True)
     net3.bi_rnn.eval(); net3.drop_out.eval()
-    b3, c3 = net3(x.to(DEV))
+    with torch.no_grad():
+        b3, c3 = net3(x.to(DEV))
     tm = horizonnet_ref.TrainMode(p=0.0)
     with torch.no_grad():
         rb, rc = horizonnet_ref.forward(sd, x, train=tm)
     assert (b3.cpu() - rb).abs().max().item() < 1e-4 and (c3.cpu() - rc).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------------------- training step: backward (row f1)
+BWD_CONV_CASES = [
+    # B, Cin, H, W, Cout, k, stride, in_halo, data gradient?
+    (2, 32, 8, 16, 48, 3, (1, 1), 1, True),
+    (2, 64, 8, 16, 64, 1, (1, 1), 1, True),
+    (1, 64, 8, 16, 32, 3, (2, 2), 1, True),        # layer2-4 conv2 of the first block
+    (2, 128, 4, 16, 64, 1, (2, 2), 1, True),       # downsample
+    (2, 64, 8, 16, 32, 3, (2, 1), 1, True),        # height-reduction conv
+    (3, 16, 6, 64, 20, 3, (1, 1), 1, True),        # ragged: Cout % 64 != 0, K % 64 != 0, M not a multiple of 16*slices
+    (1, 3, 16, 32, 64, 7, (2, 2), 3, False),       # stem: weight gradient only, Cin = 3
+]
+
+
+@pytest.mark.parametrize('case', BWD_CONV_CASES)
+def test_conv_backward_vs_autograd(case):
+    """Weight gradient (conv_wgrad_f32) and data gradient (forward conv kernel on the dilated output gradient with
+    flipped weights) of one circular-W convolution against torch.autograd in fp64."""
+    B, Ci, H, W, Co, k, stride, in_halo, want_din = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(B, Ci, H, W, generator=g)
+    w = torch.randn(Co, Ci, k, k, generator=g) / (Ci * k * k) ** 0.5
+    p = k // 2
+    xd = x.double().requires_grad_()
+    wd = w.double().requires_grad_()
+    xp = torch.cat([xd[..., -p:], xd, xd[..., :p]], dim=3) if p else xd
+    y = torch.nn.functional.conv2d(xp, wd, None, stride=stride, padding=(p, 0))
+    dz = torch.randn(y.shape, generator=g)
+    y.backward(dz.double())
+    lib = _lib.lib()
+    xin = gu.to_halo_nhwc(x, in_halo).to(DEV)
+    dzin = gu.to_halo_nhwc(dz, 1).to(DEV)
+    wdev = w.to(DEV)
+    dw = torch.full_like(wdev, float('nan'))
+    din = torch.full((B, H, W + 2, Ci), float('nan'), device=DEV) if want_din else None
+    _lib.check(lib.hn_conv2d_backward(xin.data_ptr(), B, H, W, Ci, in_halo, wdev.data_ptr(), dzin.data_ptr(), Co, k, k,
+                                      stride[0], stride[1], p, p, din.data_ptr() if want_din else None, dw.data_ptr(),
+                                      torch.cuda.current_stream().cuda_stream), 'hn_conv2d_backward')
+    torch.cuda.synchronize()
+    ref_w = wd.grad
+    assert (dw.cpu().double() - ref_w).abs().max().item() <= 2e-5 * ref_w.abs().max().item()
+    if want_din:
+        got = gu.from_halo_nhwc(din, 1).cpu().double()
+        assert (got - xd.grad).abs().max().item() <= 2e-5 * xd.grad.abs().max().item()
+
+
+@pytest.mark.parametrize('train,relu,res', [(1, 1, True), (1, 0, False), (0, 1, True), (1, 1, False)])
+def test_batchnorm_forward_backward_vs_autograd(train, relu, res):
+    B, C, H, W = 3, 32, 5, 8
+    g = torch.Generator().manual_seed(3 + train + 2 * relu)
+    z = torch.randn(B, C, H, W, generator=g) * 2 + 0.5
+    gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    rm, rv = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5
+    r = torch.randn(B, C, H, W, generator=g) if res else None
+    dy = torch.randn(B, C, H, W, generator=g)
+    zd, gd, bd = z.double().requires_grad_(), gamma.double().requires_grad_(), beta.double().requires_grad_()
+    rd = r.double().requires_grad_() if res else None
+    rm2, rv2 = rm.double().clone(), rv.double().clone()
+    y = torch.nn.functional.batch_norm(zd, rm2, rv2, gd, bd, bool(train), 0.1, 1e-5)
+    if res:
+        y = y + rd
+    if relu:
+        y = torch.relu(y)
+    y.backward(dy.double())
+    dev = lambda t: gu.to_halo_nhwc(t, 1).to(DEV)
+    zt, dyt = dev(z), dev(dy)
+    rt = dev(r) if res else None
+    yt, dzt = torch.empty_like(zt), torch.full_like(zt, float('nan'))
+    drt = torch.zeros_like(zt) if res else None
+    gam, bet, rmt, rvt = gamma.to(DEV), beta.to(DEV), rm.to(DEV), rv.to(DEV)
+    dgam, dbet = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    scratch, sums = torch.empty(4 * C, device=DEV), torch.zeros(2 * C, device=DEV, dtype=torch.float64)
+    _lib.check(_lib.lib().hn_bn_forward_backward(
+        zt.data_ptr(), B, H, W, C, gam.data_ptr(), bet.data_ptr(), rmt.data_ptr(), rvt.data_ptr(), 0.1, train, relu,
+        rt.data_ptr() if res else None, yt.data_ptr(), dyt.data_ptr(), dzt.data_ptr(), drt.data_ptr() if res else None,
+        dgam.data_ptr(), dbet.data_ptr(), scratch.data_ptr(), sums.data_ptr(), torch.cuda.current_stream().cuda_stream),
+        'hn_bn_forward_backward')
+    torch.cuda.synchronize()
+    close = lambda a, b, tol=2e-5: (a.cpu().double() - b).abs().max().item() <= tol * max(1.0, b.abs().max().item())
+    assert close(gu.from_halo_nhwc(yt, 1), y.detach())
+    assert torch.equal(yt[:, :, 0], yt[:, :, -2]) and torch.equal(dzt[:, :, -1], dzt[:, :, 1])      # circular halo columns
+    assert close(gu.from_halo_nhwc(dzt, 1), zd.grad)
+    assert close(dgam, gd.grad) and close(dbet, bd.grad)
+    if res:
+        assert close(gu.from_halo_nhwc(drt, 1), rd.grad)
+    if train:
+        assert close(rmt, rm2) and close(rvt, rv2)
+    else:
+        assert torch.equal(rmt.cpu(), rm) and torch.equal(rvt.cpu(), rv)
+
+
+@pytest.mark.parametrize('T,B', [(6, 2), (9, 11)])
+def test_lstm_layer_backward_vs_autograd(T, B):
+    """Gate gradients of one bidirectional layer (recompute of the gates from the saved outputs, cell scan, one launch
+    per time step) against autograd through the oracle's LSTM."""
+    g = torch.Generator().manual_seed(T * 100 + B)
+    x = torch.randn(T, B, 1024, generator=g) * 0.5
+    ws = {}
+    for sfx in ('', '_reverse'):
+        ws['ih' + sfx] = (torch.randn(2048, 1024, generator=g) / 32)
+        ws['hh' + sfx] = (torch.randn(2048, 512, generator=g) / 22)
+        ws['b' + sfx] = torch.randn(2048, generator=g) * 0.1
+    xps, outs = [], []
+    for sfx, rev in (('', False), ('_reverse', True)):
+        xp = (x.double() @ ws['ih' + sfx].double().t() + ws['b' + sfx].double()).requires_grad_()
+        xps.append(xp)
+        # the oracle's recurrence with the input projection made explicit (so that d xp is observable)
+        h = torch.zeros(B, 512, dtype=torch.float64)
+        c = torch.zeros(B, 512, dtype=torch.float64)
+        out = [None] * T
+        for t in (range(T - 1, -1, -1) if rev else range(T)):
+            gt = xp[t] + h @ ws['hh' + sfx].double().t()
+            i, f, gg, o = gt.chunk(4, dim=1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            out[t] = h
+        outs.append(torch.stack(out))
+    hout = torch.cat(outs, dim=2)
+    dout = torch.randn(T, B, 1024, generator=g)
+    hout.backward(dout.double())
+    xp_all = torch.cat([xps[0].detach(), xps[1].detach()], dim=2).float().contiguous().to(DEV)
+    rows = T * B
+    scratch = torch.empty(2 * rows * 512 * 2 + 2 * rows * 2048 + 2 * B * 512 + 2 * 512 * 2048 + 8192, device=DEV)
+    dg = torch.full((2, T, B, 2048), float('nan'), device=DEV)
+    _lib.check(_lib.lib().hn_lstm_layer_backward(
+        xp_all.data_ptr(), hout.detach().float().contiguous().to(DEV).data_ptr(), ws['hh'].to(DEV).data_ptr(),
+        ws['hh_reverse'].to(DEV).data_ptr(), dout.to(DEV).data_ptr(), T, B, dg.data_ptr(), scratch.data_ptr(),
+        torch.cuda.current_stream().cuda_stream), 'hn_lstm_layer_backward')
+    torch.cuda.synchronize()
+    for d in range(2):
+        ref = xps[d].grad
+        assert (dg[d].cpu().double() - ref).abs().max().item() <= 5e-5 * ref.abs().max().item(), d
+
+
+def test_training_step_gradients_match_autograd_of_the_oracle():
+    """BASELINE config 5 (train.py:44-58 + :278) at batch 2: net.train(); loss = L1(bon) + BCE-with-logits(cor);
+    loss.backward() through the library against torch.autograd through the CPU oracle with the same dropout masks,
+    for every one of the reference's parameters."""
+    import torch.nn.functional as F
+    sd = synthetic_state_dict(1, 'random')
+    x = synthetic_panoramas(2, seed=41)
+    gen = torch.Generator().manual_seed(9)
+    y_bon = torch.rand(2, 2, 1024, generator=gen) - 0.5
+    y_cor = torch.rand(2, 1, 1024, generator=gen)
+    net = _train_net(sd, True)
+    torch.manual_seed(11)
+    bon, cor = net(x.to(DEV))
+    assert bon.requires_grad and cor.requires_grad
+    loss = F.l1_loss(bon, y_bon.to(DEV)) + F.binary_cross_entropy_with_logits(cor, y_cor.to(DEV))     # train.py:53-56
+    loss.backward()                                                                                    # train.py:278
+    net.check()
+    masks = [t.cpu() for t in net.dropout_masks(net.last_dropout_seed, 2, DEV)]
+    names = [k for k, _ in net.named_parameters()]
+    psd = {k: (v.clone().requires_grad_() if k in names else v) for k, v in sd.items()}
+    tm = horizonnet_ref.TrainMode(masks=masks)
+    rbon, rcor = horizonnet_ref.forward(psd, x, train=tm)
+    rloss = F.l1_loss(rbon, y_bon) + F.binary_cross_entropy_with_logits(rcor, y_cor)
+    assert (bon.detach().cpu() - rbon.detach()).abs().max().item() < 1e-4
+    assert abs(loss.item() - rloss.item()) < 1e-5
+    ref = dict(zip(names, torch.autograd.grad(rloss, [psd[k] for k in names])))
+    gmax = max(float(v.abs().max()) for v in ref.values())
+    worst = []
+    for k, p in net.named_parameters():
+        assert p.grad is not None and p.grad.shape == p.shape, k
+        err = float((p.grad.cpu() - ref[k]).abs().max())
+        worst.append((err / (float(ref[k].abs().max()) + 1e-5 * gmax), k))
+    worst.sort(reverse=True)
+    assert worst[0][0] < 5e-3, worst[:8]
+    # a second step on the same handle (the tape is rebuilt; gradients accumulate into .grad like torch's do)
+    g0 = net.linear.weight.grad.clone()
+    bon2, cor2 = net(x.to(DEV))
+    (F.l1_loss(bon2, y_bon.to(DEV)) + F.binary_cross_entropy_with_logits(cor2, y_cor.to(DEV))).backward()
+    assert not torch.equal(net.linear.weight.grad, g0)
