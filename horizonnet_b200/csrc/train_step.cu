@@ -7,6 +7,7 @@
 // First correct path, fp32 throughout (CUDA-core kernels; conv_f32.cu for every convolution and its data gradient,
 // bwd_kernels.cu for the rest).  Every convolution output z (pre-BN) and every activation y is kept on a tape; one
 // gradient buffer mirrors every y.  Not built: tcgen05 forward / dgrad / wgrad in the step, loss scaling, DDP.
+#include <cstring>
 #include <memory>
 
 #include "model.cuh"
@@ -363,6 +364,23 @@ int hn_model_get_grad(hn_model* m, const char* key, float* out, long long numel,
     HN_ON_DEVICE(m->device);
     HN_CUDA_OK(cudaMemcpyAsync(out, ts->grads[it->second], (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice,
                                (cudaStream_t)stream));
+    return 0;
+}
+
+// Tape inspection (debugging / tests): unit i of the last hn_train_forward; what = 0 activation y, 1 raw conv output z,
+// 2 gradient of y (after hn_train_backward).  Copies the halo-1 NHWC buffer; dims = {B, H, W, C}.
+int hn_train_debug_unit(hn_model* m, int i, int what, float* out, long long capacity, int dims[4], char* name, int name_cap,
+                        void* stream) {
+    HN_CHECK(m && out && dims, "hn_train_debug_unit: NULL argument");
+    TrainState* ts = state_of(m);
+    HN_CHECK(i >= 0 && i < (int)ts->units.size(), "hn_train_debug_unit: no such unit");
+    const Unit& u = ts->units[i];
+    const Act a = what == 1 ? u.z : (what == 2 ? grad_of(ts, u.y) : u.y);
+    HN_CHECK((long long)a.numel() <= capacity, "hn_train_debug_unit: output buffer too small");
+    dims[0] = a.B; dims[1] = a.H; dims[2] = a.W; dims[3] = a.C;
+    if (name && name_cap > 0) { strncpy(name, u.c->bnprefix.c_str(), name_cap - 1); name[name_cap - 1] = 0; }
+    HN_ON_DEVICE(m->device);
+    HN_CUDA_OK(cudaMemcpyAsync(out, a.p, a.numel() * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return 0;
 }
 

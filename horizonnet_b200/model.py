@@ -344,6 +344,24 @@ class HorizonNet(nn.Module):
         h['tape_keepalive'] = None
         return grads
 
+    def debug_train_unit(self, i, what=0, device=None):
+        """Tape of the last training-step forward (test hook): conv unit i in graph order (stem, blocks, height
+        reduction) -> (BatchNorm2d prefix, NCHW tensor); what = 0 activation, 1 raw conv output, 2 its gradient."""
+        lib = _lib.lib()
+        key = next(iter(self._handles)) if device is None else device
+        h = self._handles[key]
+        dev = torch.device('cuda', key)
+        cap = h['max_batch'] * 130 * 258 * 256
+        out = torch.empty(cap, device=dev, dtype=torch.float32)
+        dims = (ctypes.c_int * 4)()
+        name = ctypes.create_string_buffer(256)
+        with torch.cuda.device(dev):
+            _lib.check(lib.hn_train_debug_unit(h['ptr'], i, what, out.data_ptr(), cap, dims, name, 256,
+                                               torch.cuda.current_stream(dev).cuda_stream), 'hn_train_debug_unit')
+        B, H, W, C = list(dims)
+        t = out[:B * H * (W + 2) * C].view(B, H, W + 2, C)[:, :, 1:-1].permute(0, 3, 1, 2).contiguous()
+        return name.value.decode(), t
+
     def dropout_masks(self, seed, batch, device):
         """The two multiplicative masks ([256, batch, 1024], values 0 or 1/(1-p)) a train forward with this seed applies:
         (between the LSTM layers, before the linear head).  Test hook."""

@@ -620,8 +620,11 @@ BWD_CONV_CASES = [
     (1, 64, 8, 16, 32, 3, (2, 2), 1, True),        # layer2-4 conv2 of the first block
     (2, 128, 4, 16, 64, 1, (2, 2), 1, True),       # downsample
     (2, 64, 8, 16, 32, 3, (2, 1), 1, True),        # height-reduction conv
-    (3, 16, 6, 64, 20, 3, (1, 1), 1, True),        # ragged: Cout % 64 != 0, K % 64 != 0, M not a multiple of 16*slices
+    (3, 16, 6, 62, 48, 3, (1, 1), 1, True),        # ragged: Cout % 64 != 0, K % 64 != 0, M not a multiple of 16*slices
     (1, 3, 16, 32, 64, 7, (2, 2), 3, False),       # stem: weight gradient only, Cin = 3
+    (2, 512, 2, 32, 256, 3, (2, 1), 1, True),      # real height-reduction shapes: H 2 -> 1
+    (2, 64, 16, 256, 32, 3, (2, 1), 1, True),      # ghc_lst.0.layer.3: W = 256, Cout = 32, several pixel slices
+    (2, 1024, 4, 32, 512, 3, (2, 1), 1, True),     # ghc_lst.3.layer.2: K = 9216
 ]
 
 
@@ -735,10 +738,10 @@ def test_lstm_layer_backward_vs_autograd(T, B):
     rows = T * B
     scratch = torch.empty(2 * rows * 512 * 2 + 2 * rows * 2048 + 2 * B * 512 + 2 * 512 * 2048 + 8192, device=DEV)
     dg = torch.full((2, T, B, 2048), float('nan'), device=DEV)
+    hout_d, whf, whb, dout_d = (t.detach().float().contiguous().to(DEV) for t in (hout, ws['hh'], ws['hh_reverse'], dout))
     _lib.check(_lib.lib().hn_lstm_layer_backward(
-        xp_all.data_ptr(), hout.detach().float().contiguous().to(DEV).data_ptr(), ws['hh'].to(DEV).data_ptr(),
-        ws['hh_reverse'].to(DEV).data_ptr(), dout.to(DEV).data_ptr(), T, B, dg.data_ptr(), scratch.data_ptr(),
-        torch.cuda.current_stream().cuda_stream), 'hn_lstm_layer_backward')
+        xp_all.data_ptr(), hout_d.data_ptr(), whf.data_ptr(), whb.data_ptr(), dout_d.data_ptr(), T, B, dg.data_ptr(),
+        scratch.data_ptr(), torch.cuda.current_stream().cuda_stream), 'hn_lstm_layer_backward')
     torch.cuda.synchronize()
     for d in range(2):
         ref = xps[d].grad
@@ -764,21 +767,41 @@ def test_training_step_gradients_match_autograd_of_the_oracle():
     net.check()
     masks = [t.cpu() for t in net.dropout_masks(net.last_dropout_seed, 2, DEV)]
     names = [k for k, _ in net.named_parameters()]
-    psd = {k: (v.clone().requires_grad_() if k in names else v) for k, v in sd.items()}
-    tm = horizonnet_ref.TrainMode(masks=masks)
-    rbon, rcor = horizonnet_ref.forward(psd, x, train=tm)
-    rloss = F.l1_loss(rbon, y_bon) + F.binary_cross_entropy_with_logits(rcor, y_cor)
-    assert (bon.detach().cpu() - rbon.detach()).abs().max().item() < 1e-4
-    assert abs(loss.item() - rloss.item()) < 1e-5
-    ref = dict(zip(names, torch.autograd.grad(rloss, [psd[k] for k in names])))
-    gmax = max(float(v.abs().max()) for v in ref.values())
-    worst = []
-    for k, p in net.named_parameters():
-        assert p.grad is not None and p.grad.shape == p.shape, k
-        err = float((p.grad.cpu() - ref[k]).abs().max())
-        worst.append((err / (float(ref[k].abs().max()) + 1e-5 * gmax), k))
-    worst.sort(reverse=True)
-    assert worst[0][0] < 5e-3, worst[:8]
+
+    def oracle_grads(relu_masks):
+        psd = {k: (v.clone().requires_grad_() if k in names else v) for k, v in sd.items()}
+        tm = horizonnet_ref.TrainMode(masks=masks, relu_masks=relu_masks)
+        rbon, rcor = horizonnet_ref.forward(psd, x, train=tm)
+        rloss = F.l1_loss(rbon, y_bon) + F.binary_cross_entropy_with_logits(rcor, y_cor)
+        return rbon.detach(), rloss.item(), dict(zip(names, torch.autograd.grad(rloss, [psd[k] for k in names])))
+
+    def worst_errors(ref):
+        gmax = max(float(v.abs().max()) for v in ref.values())
+        out = []
+        for k, p in net.named_parameters():
+            assert p.grad is not None and p.grad.shape == p.shape, k
+            err = float((p.grad.cpu() - ref[k]).abs().max())
+            out.append((err / (float(ref[k].abs().max()) + 1e-5 * gmax), k))
+        return sorted(out, reverse=True)
+
+    # (1) the oracle on its own: forward and loss agree; the gradients agree up to ReLU decisions -- the two fp32
+    #     forwards differ by ~1e-4 deep in the net (train-mode BN on 2 panoramas amplifies rounding), which flips the
+    #     sign of ~1 % of the near-zero pre-activations, and each flip moves a gradient element by its full value
+    rbon, rloss, ref = oracle_grads(None)
+    assert (bon.detach().cpu() - rbon).abs().max().item() < 1e-4
+    assert abs(loss.item() - rloss) < 1e-5
+    free = worst_errors(ref)
+    assert free[0][0] < 0.5, free[:8]
+    # (2) the same ReLU decisions on both sides (the device's, read from its tape): every gradient agrees
+    relu_masks = {}
+    for i in range(69):
+        name, y = net.debug_train_unit(i, 0)
+        if not name.endswith('downsample.1'):
+            relu_masks[name] = (y > 0).cpu()
+    _, rloss2, ref2 = oracle_grads(relu_masks)
+    assert abs(loss.item() - rloss2) < 1e-5
+    same = worst_errors(ref2)
+    assert same[0][0] < 5e-3, same[:8]
     # a second step on the same handle (the tape is rebuilt; gradients accumulate into .grad like torch's do)
     g0 = net.linear.weight.grad.clone()
     bon2, cor2 = net(x.to(DEV))
