@@ -2,7 +2,9 @@
 into contiguous shards, one process / GPU / library handle per shard, weights replicated, and the only
 collective is one all-gather of the outputs (393 KB per rank at B_local = 32) over NCCL / NVLink (gloo in the
 CPU tests).  The reference has no multi-GPU inference (inference.py:184-188 is single-device); training uses
-nn.DataParallel (train.py:190-192)."""
+nn.DataParallel (train.py:190-192), i.e. per-GPU BatchNorm statistics and a gradient sum on GPU 0 -- here: one
+process per GPU, per-GPU BatchNorm statistics, and ``average_gradients`` (bucketed all-reduce) between
+``loss.backward()`` and ``optimizer.step()``."""
 import torch
 import torch.distributed as dist
 
@@ -71,3 +73,43 @@ def gather_outputs(bon, cor, group=None, total=None):
     if key not in _default:
         _default[key] = OutputGatherer(group, total)
     return _default[key](bon, cor)
+
+
+def average_gradients(params, group=None, bucket_bytes=64 << 20):
+    """Data-parallel training (replaces nn.DataParallel's gradient reduction, train.py:190-192): averages ``.grad`` of
+    the given parameters over the ranks with all-reduces of flat buckets of about ``bucket_bytes`` (326 MB of fp32
+    gradients for HorizonNet resnet50+rnn => 6 collectives; NCCL rings / NVLS are bandwidth-bound at that size).
+    Every rank must pass the parameters in the same order.  Parameters without a gradient are skipped on the
+    condition that they have none on every rank (frozen blocks, train.py:200-208).  Returns the number of
+    collectives issued."""
+    world = dist.get_world_size(group)
+    grads = [p.grad for p in params if p.grad is not None]
+    if world == 1 or not grads:
+        return 0
+    calls = 0
+    bucket, size = [], 0
+
+    def flush():
+        nonlocal bucket, size, calls
+        if not bucket:
+            return
+        flat = torch.cat([g.reshape(-1) for g in bucket])
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        flat.div_(world)
+        off = 0
+        for g in bucket:
+            n = g.numel()
+            g.copy_(flat[off:off + n].view_as(g))
+            off += n
+        calls += 1
+        bucket, size = [], 0
+
+    for g in grads:
+        if bucket and (g.dtype != bucket[0].dtype or g.device != bucket[0].device):
+            flush()
+        bucket.append(g)
+        size += g.numel() * g.element_size()
+        if size >= bucket_bytes:
+            flush()
+    flush()
+    return calls

@@ -781,7 +781,8 @@ def test_training_step_gradients_match_autograd_of_the_oracle():
         for k, p in net.named_parameters():
             assert p.grad is not None and p.grad.shape == p.shape, k
             err = float((p.grad.cpu() - ref[k]).abs().max())
-            out.append((err / (float(ref[k].abs().max()) + 1e-5 * gmax), k))
+            out.append((err / (float(ref[k].abs().max()) + 1e-4 * gmax), k))    # 1e-4 * gmax: the conv biases in front of a
+            # train-mode BatchNorm have an analytically zero gradient (autograd returns rounding noise there)
         return sorted(out, reverse=True)
 
     # (1) the oracle on its own: forward and loss agree; the gradients agree up to ReLU decisions -- the two fp32
@@ -807,3 +808,86 @@ def test_training_step_gradients_match_autograd_of_the_oracle():
     bon2, cor2 = net(x.to(DEV))
     (F.l1_loss(bon2, y_bon.to(DEV)) + F.binary_cross_entropy_with_logits(cor2, y_cor.to(DEV))).backward()
     assert not torch.equal(net.linear.weight.grad, g0)
+
+
+def test_training_step_with_frozen_blocks_like_freeze_earlier_blocks():
+    """train.py --freeze_earlier_blocks 1 (:200-208 requires_grad = False, :251-256 those blocks in eval mode):
+    frozen BatchNorm2d modules use and keep their running statistics, frozen parameters get no gradient, the rest
+    agree with autograd through the oracle (same ReLU decisions, see the test above)."""
+    import torch.nn.functional as F
+    sd = synthetic_state_dict(2, 'random')
+    x = synthetic_panoramas(2, seed=43)
+    gen = torch.Generator().manual_seed(10)
+    y_bon, y_cor = torch.rand(2, 2, 1024, generator=gen) - 0.5, torch.rand(2, 1, 1024, generator=gen)
+    net = HorizonNet('resnet50', True)
+    net.load_state_dict(sd, strict=True)
+    net = net.to(DEV).train()
+    blocks = net.feature_extractor.list_blocks()
+    for i in range(2):
+        for m in blocks[i]:
+            m.eval()
+            for p in m.parameters():
+                p.requires_grad = False
+    frozen_bn = [n for n, m in net.named_modules() if isinstance(m, torch.nn.BatchNorm2d) and not m.training]
+    assert len(frozen_bn) == 11
+    bon, cor = net(x.to(DEV))
+    loss = F.l1_loss(bon, y_bon.to(DEV)) + F.binary_cross_entropy_with_logits(cor, y_cor.to(DEV))
+    loss.backward()
+    net.check()
+    masks = [t.cpu() for t in net.dropout_masks(net.last_dropout_seed, 2, DEV)]
+    relu_masks = {}
+    for i in range(69):
+        name, y = net.debug_train_unit(i, 0)
+        if not name.endswith('downsample.1'):
+            relu_masks[name] = (y > 0).cpu()
+    live = [k for k, p in net.named_parameters() if p.requires_grad]
+    psd = {k: (v.clone().requires_grad_() if k in live else v) for k, v in sd.items()}
+    tm = horizonnet_ref.TrainMode(masks=masks, frozen=frozen_bn, relu_masks=relu_masks)
+    rbon, rcor = horizonnet_ref.forward(psd, x, train=tm)
+    rloss = F.l1_loss(rbon, y_bon) + F.binary_cross_entropy_with_logits(rcor, y_cor)
+    assert abs(loss.item() - rloss.item()) < 1e-5
+    ref = dict(zip(live, torch.autograd.grad(rloss, [psd[k] for k in live])))
+    gmax = max(float(v.abs().max()) for v in ref.values())
+    worst = []
+    for k, p in net.named_parameters():
+        if k not in ref:
+            assert p.grad is None, k
+            continue
+        worst.append((float((p.grad.cpu() - ref[k]).abs().max()) / (float(ref[k].abs().max()) + 1e-4 * gmax), k))
+    worst.sort(reverse=True)
+    assert worst[0][0] < 5e-3, worst[:8]
+    after = net.state_dict()
+    for n in frozen_bn:
+        assert torch.equal(after[n + '.running_mean'].cpu(), sd[n + '.running_mean'])
+        assert int(after[n + '.num_batches_tracked']) == 0
+
+
+def test_training_loop_like_train_py_reduces_the_loss():
+    """train.py:216-223 (Adam) + :272-281 (zero_grad / backward / step) on one fixed synthetic batch: the loss goes
+    down, every optimizer step is seen by the library (weights re-uploaded), and eval mode afterwards uses the moved
+    running statistics."""
+    import torch.nn.functional as F
+    sd = synthetic_state_dict(3, 'random')
+    x = synthetic_panoramas(2, seed=47).to(DEV)
+    gen = torch.Generator().manual_seed(12)
+    y_bon = (torch.rand(2, 2, 1024, generator=gen) - 0.5).to(DEV)
+    y_cor = torch.rand(2, 1, 1024, generator=gen).to(DEV)
+    net = _train_net(sd, True)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, betas=(0.9, 0.999))
+    losses = []
+    for _ in range(5):
+        torch.manual_seed(0)                    # the same dropout masks every step: the loss curve is not noise
+        opt.zero_grad()
+        bon, cor = net(x)
+        loss = F.l1_loss(bon, y_bon) + F.binary_cross_entropy_with_logits(cor, y_cor)
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    net.check()
+    assert losses[-1] < losses[0] - 0.02, losses
+    assert all(np.isfinite(losses))
+    net.eval()
+    with torch.no_grad():
+        ebon, ecor = net(x)
+        rbon, rcor = horizonnet_ref.forward({k: v.cpu() for k, v in net.state_dict().items()}, x.cpu())
+    assert (ebon.cpu() - rbon).abs().max().item() < 2e-4 and (ecor.cpu() - rcor).abs().max().item() < 2e-4

@@ -6,7 +6,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from horizonnet_b200.parallel import gather_outputs, shard_bounds
+from horizonnet_b200.parallel import average_gradients, gather_outputs, shard_bounds
 
 
 def _free_port():
@@ -68,3 +68,35 @@ def test_shard_bounds_cover_everything_once():
                 seen += list(range(lo, hi))
             assert seen == list(range(total))
     assert shard_bounds(256, 3, 8) == (96, 128)
+
+
+def _worker_grads(rank, world, port):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        shapes = [(64, 3, 7, 7), (64,), (256, 64, 1, 1), (2048, 1024), (12,), (5, 5)]
+        params, expect = [], []
+        for i, shp in enumerate(shapes):
+            p = torch.nn.Parameter(torch.zeros(shp))
+            per_rank = [torch.randn(shp, generator=torch.Generator().manual_seed(100 * r + i)) for r in range(world)]
+            if i != 5:                       # the last parameter is frozen on every rank: no gradient anywhere
+                p.grad = per_rank[rank].clone()
+                expect.append(sum(per_rank) / world)
+            else:
+                expect.append(None)
+            params.append(p)
+        calls = average_gradients(params, bucket_bytes=1 << 20)         # 2048*1024*4 B > 1 MiB: several buckets
+        assert calls >= 2
+        for p, e in zip(params, expect):
+            if e is None:
+                assert p.grad is None
+            else:
+                assert torch.allclose(p.grad, e, rtol=0, atol=1e-6)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_average_gradients_world2():
+    """Data-parallel training step host logic: bucketed gradient all-reduce == mean of the per-rank gradients."""
+    mp.spawn(_worker_grads, args=(2, _free_port()), nprocs=2, join=True)
