@@ -539,6 +539,14 @@ def run_ours(args):
     except Exception as e:
         aux['augment'] = {'error': str(e)}
 
+    # ---- auxiliary: the training step ("next" row f1, BASELINE configs[4] shape per GPU: batch 8, L1 + BCE, Adam)
+    if world == 1:
+        try:
+            aux['train_step'] = train_step_aux(dev)
+        except Exception as e:
+            aux['train_step'] = {'error': '%s: %s' % (type(e).__name__, e)}
+        torch.cuda.empty_cache()
+
     # ---- comparators (N=1 only): stock PyTorch eager on this GPU; the CPU oracle on this host's cores
     cpu = None
     if world == 1 and not args.no_comparators:
@@ -562,6 +570,10 @@ def run_ours(args):
         if t8:
             cpu['bs8_panos_per_s'] = round(8.0 / _median(t8), 4)
             cpu['bs8_reps'] = len(t8)
+        try:
+            cpu['train_step'] = cpu_train_step_baseline()
+        except Exception as e:
+            cpu['train_step'] = {'error': str(e)}
         try:
             cpu['pano_stretch'] = cpu_pano_stretch_baseline()
         except Exception as e:
@@ -595,6 +607,74 @@ def run_ours(args):
     emit_json(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def train_step_aux(dev, batch=8, steps=3):
+    """One optimizer step of train.py (:272-281) through the library's autograd boundary: train-mode forward with tape,
+    L1 + BCE-with-logits (train.py:53-56), loss.backward() (hn_train_backward + one gradient per parameter),
+    Adam (train.py:221-223) and the re-upload of the stepped weights.  Device-timed with CUDA events."""
+    import torch.nn.functional as F
+    from horizonnet_b200.model import HorizonNet
+    from horizonnet_b200.weights import synthetic_state_dict, synthetic_panoramas
+    net = HorizonNet('resnet50', True)
+    net.load_state_dict(synthetic_state_dict(0, 'random'))
+    net = net.to(dev).train()
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, betas=(0.9, 0.999))
+    x = synthetic_panoramas(batch, seed=5).to(dev)
+    g = torch.Generator().manual_seed(6)
+    y_bon = (torch.rand(batch, 2, 1024, generator=g) - 0.5).to(dev)
+    y_cor = torch.rand(batch, 1, 1024, generator=g).to(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    fw = bw = op = 0.0
+    loss = None
+    for it in range(steps + 2):
+        torch.cuda.synchronize(dev)
+        ev[0].record()
+        opt.zero_grad()
+        bon, cor = net(x)
+        loss = F.l1_loss(bon, y_bon) + F.binary_cross_entropy_with_logits(cor, y_cor)
+        ev[1].record()
+        loss.backward()
+        ev[2].record()
+        opt.step()
+        ev[3].record()
+        torch.cuda.synchronize(dev)
+        if it >= 2:
+            fw += ev[0].elapsed_time(ev[1]); bw += ev[1].elapsed_time(ev[2]); op += ev[2].elapsed_time(ev[3])
+    net.check()
+    fw, bw, op = fw / steps, bw / steps, op / steps
+    out = {'batch': batch, 'forward_ms': round(fw, 2), 'backward_ms': round(bw, 2), 'optimizer_ms': round(op, 2),
+           'step_ms': round(fw + bw + op, 2), 'panoramas_per_s': round(batch / (fw + bw + op) * 1e3, 2),
+           'final_loss': round(float(loss), 5), 'dtype': 'f32 (CUDA-core kernels; first correct path of row f1)',
+           'api': 'HorizonNet.train(); net(x); loss.backward(); Adam.step()  (hn_train_forward / hn_train_backward)',
+           'note': 'forward_ms includes the re-upload + re-packing of the weights the optimizer just changed'}
+    del net, opt
+    return out
+
+
+def cpu_train_step_baseline(batch=2):
+    """The same step on the host cores: the CPU oracle (torch CPU fp32, the reference's arithmetic) forward + autograd
+    backward in train mode at batch 2 (bounded: a few seconds)."""
+    import torch.nn.functional as F
+    from oracle import horizonnet_ref
+    from horizonnet_b200.model import HorizonNet
+    from horizonnet_b200.weights import synthetic_state_dict, synthetic_panoramas
+    sd = synthetic_state_dict(0, 'random')
+    names = [k for k, _ in HorizonNet('resnet50', True).named_parameters()]
+    x = synthetic_panoramas(batch, seed=5)
+    g = torch.Generator().manual_seed(6)
+    y_bon, y_cor = torch.rand(batch, 2, 1024, generator=g) - 0.5, torch.rand(batch, 1, 1024, generator=g)
+    times = []
+    for _ in range(2):
+        psd = {k: (v.clone().requires_grad_() if k in names else v) for k, v in sd.items()}
+        t0 = time.perf_counter()
+        bon, cor = horizonnet_ref.forward(psd, x, train=horizonnet_ref.TrainMode())
+        loss = F.l1_loss(bon, y_bon) + F.binary_cross_entropy_with_logits(cor, y_cor)
+        torch.autograd.grad(loss, [psd[k] for k in names])
+        times.append(time.perf_counter() - t0)
+    return {'panoramas_per_s': round(batch / min(times), 4), 'batch': batch, 'step_s': round(min(times), 3),
+            'cores': torch.get_num_threads(), 'kind': 'port', 'sample': 'forward + autograd backward of the CPU oracle in train mode, '
+            'best of 2, no optimizer step'}
 
 
 _JSON_FD = None
