@@ -613,6 +613,7 @@ def train_step_aux(dev, batch=8, steps=3):
     """One optimizer step of train.py (:272-281) through the library's autograd boundary: train-mode forward with tape,
     L1 + BCE-with-logits (train.py:53-56), loss.backward() (hn_train_backward + one gradient per parameter),
     Adam (train.py:221-223) and the re-upload of the stepped weights.  Device-timed with CUDA events."""
+    import torch
     import torch.nn.functional as F
     from horizonnet_b200.model import HorizonNet
     from horizonnet_b200.weights import synthetic_state_dict, synthetic_panoramas
@@ -645,7 +646,7 @@ def train_step_aux(dev, batch=8, steps=3):
     fw, bw, op = fw / steps, bw / steps, op / steps
     out = {'batch': batch, 'forward_ms': round(fw, 2), 'backward_ms': round(bw, 2), 'optimizer_ms': round(op, 2),
            'step_ms': round(fw + bw + op, 2), 'panoramas_per_s': round(batch / (fw + bw + op) * 1e3, 2),
-           'final_loss': round(float(loss), 5), 'dtype': 'f32 (CUDA-core kernels; first correct path of row f1)',
+           'final_loss': round(float(loss), 5), 'dtype': 'convolutions + their data gradients: tcgen05 split-fp16 planes (fp32-equivalent); weight gradients, BatchNorm, LSTM BPTT: fp32 CUDA cores',
            'api': 'HorizonNet.train(); net(x); loss.backward(); Adam.step()  (hn_train_forward / hn_train_backward)',
            'note': 'forward_ms includes the re-upload + re-packing of the weights the optimizer just changed'}
     del net, opt
@@ -655,6 +656,7 @@ def train_step_aux(dev, batch=8, steps=3):
 def cpu_train_step_baseline(batch=2):
     """The same step on the host cores: the CPU oracle (torch CPU fp32, the reference's arithmetic) forward + autograd
     backward in train mode at batch 2 (bounded: a few seconds)."""
+    import torch
     import torch.nn.functional as F
     from oracle import horizonnet_ref
     from horizonnet_b200.model import HorizonNet
@@ -665,7 +667,7 @@ def cpu_train_step_baseline(batch=2):
     g = torch.Generator().manual_seed(6)
     y_bon, y_cor = torch.rand(batch, 2, 1024, generator=g) - 0.5, torch.rand(batch, 1, 1024, generator=g)
     times = []
-    for _ in range(2):
+    for _ in range(1):
         psd = {k: (v.clone().requires_grad_() if k in names else v) for k, v in sd.items()}
         t0 = time.perf_counter()
         bon, cor = horizonnet_ref.forward(psd, x, train=horizonnet_ref.TrainMode())
@@ -674,7 +676,7 @@ def cpu_train_step_baseline(batch=2):
         times.append(time.perf_counter() - t0)
     return {'panoramas_per_s': round(batch / min(times), 4), 'batch': batch, 'step_s': round(min(times), 3),
             'cores': torch.get_num_threads(), 'kind': 'port', 'sample': 'forward + autograd backward of the CPU oracle in train mode, '
-            'best of 2, no optimizer step'}
+            'one run, no optimizer step'}
 
 
 _JSON_FD = None

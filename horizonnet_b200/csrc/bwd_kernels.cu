@@ -8,6 +8,7 @@
 //   maxpool_bwd, ghc_to_sequence_bwd, head_bwd_*, lstm_* (gate recompute scan, one backward launch per time step)
 // Parity target: torch.autograd on the CPU oracle (tests/test_gpu_parity.py, relative tolerance in the tests).
 #include "hn_common.cuh"
+#include "conv_tc.cuh"
 #include "bwd_kernels.cuh"
 
 namespace hn {
@@ -207,8 +208,19 @@ __global__ void bn_finalize_full_kernel(const double* __restrict__ sums, double 
 }
 
 // y = relu?(z*scale + shift (+ res)); interior pixels + the two circular halo columns.  One thread = 4 channels.
+__device__ __forceinline__ void store_planes4(unsigned short* __restrict__ planes, size_t plane, size_t o, const float4 v) {
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    unsigned short h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split_scaled(f[j], h[j], l[j]);
+    *reinterpret_cast<uint2*>(planes + o) = make_uint2((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16));
+    *reinterpret_cast<uint2*>(planes + plane + o) = make_uint2((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16));
+}
+
+// planes != nullptr: also the fp16 hi/lo plane pair of y (the tcgen05 conv kernel's operand format, conv_tc.cuh)
 __global__ void bn_apply_fwd_kernel(const float* __restrict__ z, const float* __restrict__ bn, const float* __restrict__ res,
-                                    float* __restrict__ y, int B, int H, int W, int C, int relu) {
+                                    float* __restrict__ y, unsigned short* __restrict__ planes, int B, int H, int W, int C,
+                                    int relu) {
     const int C4 = C / 4;
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t total = (size_t)B * H * W * C4;
@@ -227,9 +239,16 @@ __global__ void bn_apply_fwd_kernel(const float* __restrict__ z, const float* __
         v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
     }
     if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    const size_t oh1 = (bh * (W + 2) + W + 1) * C + c4 * 4, oh0 = (bh * (W + 2)) * C + c4 * 4;
     *reinterpret_cast<float4*>(y + o) = v;
-    if (w == 0) *reinterpret_cast<float4*>(y + (bh * (W + 2) + W + 1) * C + c4 * 4) = v;
-    if (w == W - 1) *reinterpret_cast<float4*>(y + (bh * (W + 2)) * C + c4 * 4) = v;
+    if (w == 0) *reinterpret_cast<float4*>(y + oh1) = v;
+    if (w == W - 1) *reinterpret_cast<float4*>(y + oh0) = v;
+    if (planes) {
+        const size_t plane = (size_t)B * H * (W + 2) * C;
+        store_planes4(planes, plane, o, v);
+        if (w == 0) store_planes4(planes, plane, oh1, v);
+        if (w == W - 1) store_planes4(planes, plane, oh0, v);
+    }
 }
 
 // sums[c] = sum g, sums[C+c] = sum g * xhat, g = dy * (relu ? y > 0 : 1), xhat = (z - mean) * invstd
@@ -473,70 +492,77 @@ __global__ void lstm_cell_scan_kernel(float* __restrict__ gates, float* __restri
     }
 }
 
-// One backward time step of both directions.  Block = 16 hidden units of one direction: first
-// dh[b][j] = dout[t][b][dir*512+j] + sum_n dG_prev[b][n] * W_hh[n][j], then the gate gradients of step t.
+// One backward time step of both directions.  Block = 16 hidden units of one direction, warp = 2 of them: first
+// dh[b][j] = dout[t][b][dir*512+j] + sum_n dG_prev[b][n] * W_hh[n][j] (W_hh^T rows and dG rows are read as coalesced
+// float4 streams, warp-shuffle reduction), then the gate gradients of step t for those units.
 struct LstmBwdArgs {
     const float* dout;      // [T][B][1024]
     const float* gates;     // [2][T][B][2048] activated
     const float* cell;      // [2][T][B][512]
-    const float* whh[2];    // [2048][512]
+    const float* whh_t[2];  // W_hh^T: [512][2048]
     float* dgates;          // [2][T][B][2048]
     float* dc;              // [2][B][512] carry
     int T, B, step;
 };
 
 __global__ void __launch_bounds__(256) lstm_bwd_step_kernel(const LstmBwdArgs a) {
-    __shared__ float red[16][16 * 8 + 1];
     const int dir = blockIdx.y;
-    const int j0 = blockIdx.x * 16;
-    const int jj = threadIdx.x & 15, ng = threadIdx.x >> 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j0 = blockIdx.x * 16 + warp * 2;
     // reverse of the forward order: forward dir walks t = 0..T-1, so its backward starts at T-1
     const int t = dir == 0 ? a.T - 1 - a.step : a.step;
     const int tprev_bwd = dir == 0 ? t + 1 : t - 1;          // the step processed just before this one
     const int tprev_fwd = dir == 0 ? t - 1 : t + 1;          // c_{t-1} in forward order
-    const float* w = a.whh[dir];
+    const float4* w0 = reinterpret_cast<const float4*>(a.whh_t[dir] + (size_t)j0 * 2048);
+    const float4* w1 = reinterpret_cast<const float4*>(a.whh_t[dir] + (size_t)(j0 + 1) * 2048);
     for (int b0 = 0; b0 < a.B; b0 += 8) {
-        float acc[8];
+        float acc[2][8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+        for (int q = 0; q < 8; ++q) acc[0][q] = acc[1][q] = 0.f;
         if (a.step > 0) {
             const float* dg = a.dgates + (((size_t)dir * a.T + tprev_bwd) * a.B) * 2048;
-            for (int n = ng * 128; n < ng * 128 + 128; ++n) {
-                const float wv = __ldg(w + (size_t)n * 512 + j0 + jj);
+            for (int i = lane; i < 512; i += 32) {              // 512 float4 = 2048 gate rows
+                const float4 wa = __ldg(w0 + i), wb = __ldg(w1 + i);
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (b0 + q < a.B) acc[q] = fmaf(dg[(size_t)(b0 + q) * 2048 + n], wv, acc[q]);
+                for (int q = 0; q < 8; ++q) {
+                    if (b0 + q >= a.B) break;
+                    const float4 g = *reinterpret_cast<const float4*>(dg + (size_t)(b0 + q) * 2048 + i * 4);
+                    acc[0][q] = fmaf(g.x, wa.x, fmaf(g.y, wa.y, fmaf(g.z, wa.z, fmaf(g.w, wa.w, acc[0][q]))));
+                    acc[1][q] = fmaf(g.x, wb.x, fmaf(g.y, wb.y, fmaf(g.z, wb.z, fmaf(g.w, wb.w, acc[1][q]))));
+                }
             }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    acc[0][q] += __shfl_xor_sync(0xffffffffu, acc[0][q], off);
+                    acc[1][q] += __shfl_xor_sync(0xffffffffu, acc[1][q], off);
+                }
         }
-        __syncthreads();
+        // lane = (unit jj, batch q): 16 lanes finish one (b, j) cell each
+        const int jj = lane >> 3, q = lane & 7;
+        const int b = b0 + q;
+        if (jj < 2 && b < a.B) {
+            float dh = 0.f;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) red[ng][jj * 8 + q] = acc[q];
-        __syncthreads();
-        if (threadIdx.x < 128) {
-            const int q = threadIdx.x & 7, j2 = threadIdx.x >> 3;
-            const int b = b0 + q;
-            if (b < a.B) {
-                float dh = 0.f;
-#pragma unroll
-                for (int r = 0; r < 16; ++r) dh += red[r][j2 * 8 + q];
-                const int j = j0 + j2;
-                dh += a.dout[((size_t)t * a.B + b) * 1024 + dir * 512 + j];
-                const float* g = a.gates + (((size_t)dir * a.T + t) * a.B + b) * 2048;
-                const float ig = g[j], fg = g[512 + j], gg = g[1024 + j], og = g[1536 + j];
-                const float c = a.cell[(((size_t)dir * a.T + t) * a.B + b) * 512 + j];
-                const float cprev = (tprev_fwd < 0 || tprev_fwd >= a.T)
-                                        ? 0.f : a.cell[(((size_t)dir * a.T + tprev_fwd) * a.B + b) * 512 + j];
-                const float tc = tanhf(c);
-                float* dcp = a.dc + ((size_t)dir * a.B + b) * 512 + j;
-                const float dcar = a.step > 0 ? *dcp : 0.f;
-                const float dc = dcar + dh * og * (1.f - tc * tc);
-                float* o = a.dgates + (((size_t)dir * a.T + t) * a.B + b) * 2048;
-                o[j] = dc * gg * ig * (1.f - ig);
-                o[512 + j] = dc * cprev * fg * (1.f - fg);
-                o[1024 + j] = dc * ig * (1.f - gg * gg);
-                o[1536 + j] = dh * tc * og * (1.f - og);
-                *dcp = dc * fg;
-            }
+            for (int qq = 0; qq < 8; ++qq) if (qq == q) dh = jj ? acc[1][qq] : acc[0][qq];
+            const int j = j0 + jj;
+            dh += a.dout[((size_t)t * a.B + b) * 1024 + dir * 512 + j];
+            const float* g = a.gates + (((size_t)dir * a.T + t) * a.B + b) * 2048;
+            const float ig = g[j], fg = g[512 + j], gg = g[1024 + j], og = g[1536 + j];
+            const float c = a.cell[(((size_t)dir * a.T + t) * a.B + b) * 512 + j];
+            const float cprev = (tprev_fwd < 0 || tprev_fwd >= a.T)
+                                    ? 0.f : a.cell[(((size_t)dir * a.T + tprev_fwd) * a.B + b) * 512 + j];
+            const float tc = tanhf(c);
+            float* dcp = a.dc + ((size_t)dir * a.B + b) * 512 + j;
+            const float dcar = a.step > 0 ? *dcp : 0.f;
+            const float dc = dcar + dh * og * (1.f - tc * tc);
+            float* o = a.dgates + (((size_t)dir * a.T + t) * a.B + b) * 2048;
+            o[j] = dc * gg * ig * (1.f - ig);
+            o[512 + j] = dc * cprev * fg * (1.f - fg);
+            o[1024 + j] = dc * ig * (1.f - gg * gg);
+            o[1536 + j] = dh * tc * og * (1.f - og);
+            *dcp = dc * fg;
         }
     }
 }
@@ -555,6 +581,63 @@ __global__ void stem_input_kernel(const float* __restrict__ x, int Cx, float* __
     if (w < 0) w += 1024; else if (w >= 1024) w -= 1024;
     const float mean[3] = {0.485f, 0.456f, 0.406f}, stdv[3] = {0.229f, 0.224f, 0.225f};
     out[i] = (__ldg(x + (((size_t)b * Cx + c) * 512 + h) * 1024 + w) - mean[c]) / stdv[c];
+}
+
+// OIHW of the transposed convolution: out[ci][co][dy][dx] = w[co][ci][kh-1-dy][kw-1-dx]
+__global__ void flip_oihw_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int kh, int kw) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)Cout * Cin * kh * kw;
+    if (i >= total) return;
+    const int dx = (int)(i % kw);
+    size_t t = i / kw;
+    const int dy = (int)(t % kh); t /= kh;
+    const int co = (int)(t % Cout);
+    const int ci = (int)(t / Cout);
+    out[i] = w[(((size_t)co * Cin + ci) * kh + (kh - 1 - dy)) * kw + (kw - 1 - dx)];
+}
+
+// Gradients are orders of magnitude smaller than activations, and the fp16 hi/lo planes (conv_tc.cuh: value * 2^-4) only
+// carry ~22 bits for values well above 2^-14: a gradient tensor is therefore multiplied by a power of two that brings its
+// largest magnitude to [2^11, 2^12) before it is split, and the convolution result is divided by it in the epilogue
+// constants (exact: powers of two).
+__device__ __forceinline__ float pow2_factor(float absmax) {
+    if (!(absmax > 0.f) || isinf(absmax)) return 1.f;
+    int e;
+    frexpf(absmax, &e);                      // absmax = m * 2^e, m in [0.5, 1)
+    e = 12 - e;
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    return ldexpf(1.f, e);
+}
+
+__global__ void absmax_f32_kernel(const float* __restrict__ x, size_t n, float* __restrict__ out) {
+    float m = 0.f;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));      // m >= 0: int order = float order
+}
+
+__global__ void split_pow2_kernel(const float* __restrict__ in, unsigned short* __restrict__ out, size_t n,
+                                  const float* __restrict__ absmax) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float s = pow2_factor(*absmax);
+    split_scaled(in[i] * s, out[i], out[n + i]);
+}
+
+__global__ void aux_div_pow2_kernel(float* __restrict__ aux, int C, const float* __restrict__ absmax) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < C) aux[i] /= pow2_factor(*absmax);
+}
+
+__global__ void add_kernel(float* __restrict__ dst, const float* __restrict__ src, size_t n4) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 a = reinterpret_cast<float4*>(dst)[i];
+    const float4 b = reinterpret_cast<const float4*>(src)[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(dst)[i] = a;
 }
 
 __global__ void fill_kernel(float* __restrict__ p, size_t n, float v) {
@@ -578,6 +661,46 @@ inline unsigned blocks_for(size_t n, int per = 256) { return (unsigned)((n + per
 int fill_f32(float* p, size_t n, float v, cudaStream_t st) {
     if (n == 0) return 0;
     fill_kernel<<<blocks_for(n), 256, 0, st>>>(p, n, v);
+    HN_LAUNCH_OK();
+    return 0;
+}
+
+int flip_oihw(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t st) {
+    flip_oihw_kernel<<<blocks_for((size_t)Cout * Cin * kh * kw), 256, 0, st>>>(w_oihw, out, Cout, Cin, kh, kw);
+    HN_LAUNCH_OK();
+    return 0;
+}
+
+int add_inplace(float* dst, const float* src, size_t n, cudaStream_t st) {
+    HN_CHECK(n % 4 == 0, "add_inplace: element count must be a multiple of 4");
+    if (n == 0) return 0;
+    add_kernel<<<blocks_for(n / 4), 256, 0, st>>>(dst, src, n / 4);
+    HN_LAUNCH_OK();
+    return 0;
+}
+
+int split_planes_pow2(const float* in, unsigned short* out, size_t n, float* absmax_scratch, cudaStream_t st) {
+    HN_CUDA_OK(cudaMemsetAsync(absmax_scratch, 0, sizeof(float), st));
+    if (n == 0) return 0;
+    size_t blocks = (n + 256 * 16 - 1) / (256 * 16);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    absmax_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, n, absmax_scratch);
+    HN_LAUNCH_OK();
+    split_pow2_kernel<<<blocks_for(n), 256, 0, st>>>(in, out, n, absmax_scratch);
+    HN_LAUNCH_OK();
+    return 0;
+}
+
+int tc_aux_div_pow2(float* tc_aux, int C, const float* absmax_scratch, cudaStream_t st) {
+    aux_div_pow2_kernel<<<(C + 255) / 256, 256, 0, st>>>(tc_aux, C, absmax_scratch);
+    HN_LAUNCH_OK();
+    return 0;
+}
+
+// zero-dilated copy of dz for the data gradient of a strided conv (see conv_dgrad_f32); out: geometry of din with C = Cout
+int dilate_for_dgrad(const Act& dz, const Act& out, int sh, int sw, cudaStream_t st) {
+    HN_CHECK(out.halo == 1 && out.C == dz.C && out.C % 4 == 0, "dilate_for_dgrad: bad tensors");
+    dilate_kernel<<<blocks_for(out.numel() / 4), 256, 0, st>>>(dz.p, out.p, dz.B, dz.H, dz.W, dz.halo, out.H, out.W, out.C, sh, sw);
     HN_LAUNCH_OK();
     return 0;
 }
@@ -662,10 +785,11 @@ int bn_finalize_full(const double* sums, long long count, const float* gamma, co
     return 0;
 }
 
-int bn_apply_fwd(const Act& z, const float* bn, const float* res, bool relu, const Act& y, cudaStream_t st) {
+int bn_apply_fwd(const Act& z, const float* bn, const float* res, bool relu, const Act& y, unsigned short* y_planes,
+                 cudaStream_t st) {
     HN_CHECK(z.halo == 1 && y.halo == 1 && z.C % 4 == 0 && z.numel() == y.numel(), "bn_apply_fwd: bad tensors");
     const size_t n = (size_t)z.B * z.H * z.W * (z.C / 4);
-    bn_apply_fwd_kernel<<<blocks_for(n), 256, 0, st>>>(z.p, bn, res, y.p, z.B, z.H, z.W, z.C, relu ? 1 : 0);
+    bn_apply_fwd_kernel<<<blocks_for(n), 256, 0, st>>>(z.p, bn, res, y.p, y_planes, z.B, z.H, z.W, z.C, relu ? 1 : 0);
     HN_LAUNCH_OK();
     return 0;
 }
@@ -745,10 +869,10 @@ int lstm_cell_scan(float* gates, float* cell, int T, int B, cudaStream_t st) {
     return 0;
 }
 
-int lstm_bwd_steps(const float* dout, const float* gates, const float* cell, const float* whh_f, const float* whh_b,
+int lstm_bwd_steps(const float* dout, const float* gates, const float* cell, const float* whh_t_f, const float* whh_t_b,
                    float* dgates, float* dc, int T, int B, cudaStream_t st) {
     LstmBwdArgs a;
-    a.dout = dout; a.gates = gates; a.cell = cell; a.whh[0] = whh_f; a.whh[1] = whh_b; a.dgates = dgates; a.dc = dc;
+    a.dout = dout; a.gates = gates; a.cell = cell; a.whh_t[0] = whh_t_f; a.whh_t[1] = whh_t_b; a.dgates = dgates; a.dc = dc;
     a.T = T; a.B = B;
     for (int s = 0; s < T; ++s) {
         a.step = s;

@@ -6,6 +6,13 @@ namespace hn {
 
 int fill_f32(float* p, size_t n, float v, cudaStream_t st);
 int transpose_f32(const float* in, float* out, int rows, int cols, cudaStream_t st);           // out[c][r] = in[r][c]
+int flip_oihw(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t st);   // OIHW of the transposed conv
+int add_inplace(float* dst, const float* src, size_t n, cudaStream_t st);
+// fp32 gradient tensor -> fp16 hi/lo planes of (x * 2^k), k from the tensor's absmax (left in absmax_scratch[0]);
+// tc_aux_div_pow2 folds 2^-k into the first C epilogue constants (accumulator -> true units) of the conv that consumes them
+int split_planes_pow2(const float* in, unsigned short* out, size_t n, float* absmax_scratch, cudaStream_t st);
+int tc_aux_div_pow2(float* tc_aux, int C, const float* absmax_scratch, cudaStream_t st);
+int dilate_for_dgrad(const Act& dz, const Act& out, int sh, int sw, cudaStream_t st);
 
 // dW[Cout][kh][kw][Cin] (zeroed here, then accumulated); in = the conv's forward input, dz = d(raw conv output)
 int conv_wgrad_f32(const ConvDesc& d, const Act& in, const Act& dz, float* dw_ohwi, cudaStream_t st);
@@ -21,7 +28,9 @@ int conv_dgrad_f32(const ConvDesc& d, const float* wd_packed, const Act& dz, con
 // frozen: from the running statistics.
 int bn_finalize_full(const double* sums, long long count, const float* gamma, const float* beta, const float* bias,
                      float* running_mean, float* running_var, double factor, bool train, float* bn, int C, cudaStream_t st);
-int bn_apply_fwd(const Act& z, const float* bn, const float* res, bool relu, const Act& y, cudaStream_t st);
+// y_planes (nullable): also write y as fp16 hi/lo planes, the tcgen05 conv kernel's operand format
+int bn_apply_fwd(const Act& z, const float* bn, const float* res, bool relu, const Act& y, unsigned short* y_planes,
+                 cudaStream_t st);
 // dz (with halo columns), dres += relu-masked dy, parameter gradients; sums: 2*C doubles of scratch
 int bn_bwd(const Act& dy, const Act& y, const Act& z, const float* bn, bool train, bool relu, double* sums, const Act& dz,
            float* dres, float* dgamma, float* dbeta, float* dbias, cudaStream_t st);
@@ -34,7 +43,8 @@ int col_sum(const float* x, size_t rows, int cols, float* out, cudaStream_t st);
 
 int lstm_gather(const float* hout, const float* xp, float* hprev, float* xpd, int T, int B, cudaStream_t st);
 int lstm_cell_scan(float* gates, float* cell, int T, int B, cudaStream_t st);
-int lstm_bwd_steps(const float* dout, const float* gates, const float* cell, const float* whh_f, const float* whh_b,
+// whh_t_*: W_hh transposed, [512][2048] (the same copies the gate GEMM uses)
+int lstm_bwd_steps(const float* dout, const float* gates, const float* cell, const float* whh_t_f, const float* whh_t_b,
                    float* dgates, float* dc, int T, int B, cudaStream_t st);
 int stem_input_nhwc(const float* x, int in_channels, float* out, int B, cudaStream_t st);
 

@@ -4,9 +4,12 @@
 // hn_train_forward and whose backward hands d(bon), d(cor) to hn_train_backward and reads one gradient per
 // parameter back with hn_model_get_grad (horizonnet_b200/model.py).
 //
-// First correct path, fp32 throughout (CUDA-core kernels; conv_f32.cu for every convolution and its data gradient,
-// bwd_kernels.cu for the rest).  Every convolution output z (pre-BN) and every activation y is kept on a tape; one
-// gradient buffer mirrors every y.  Not built: tcgen05 forward / dgrad / wgrad in the step, loss scaling, DDP.
+// Every convolution output z (pre-BN) and every activation y is kept in fp32 on a tape; one gradient buffer mirrors
+// every y.  With the model option tensor_cores (default) the forward convolutions and their data gradients run on the
+// tcgen05 conv kernel (conv_tc.cu: fp16 hi/lo operand planes, fp32 result; a data gradient is the same kernel on the
+// zero-dilated dz with flipped weights); weight gradients, BatchNorm, LSTM BPTT and the rest are fp32 CUDA-core kernels
+// (bwd_kernels.cu).  tensor_cores = 0: conv_f32.cu everywhere.  Not built: a tcgen05 weight-gradient kernel, loss
+// scaling, gradient all-reduce overlapped with the backward.
 #include <cstring>
 #include <memory>
 
@@ -45,6 +48,10 @@ struct TrainState {
     float *yarena = nullptr, *garena = nullptr, *zarena = nullptr, *bnarena = nullptr;
     size_t dz_max = 0, dil_max = 0, w_max = 0;
     float *dz_scratch = nullptr, *dil_scratch = nullptr, *wd_scratch = nullptr, *dw_scratch = nullptr;
+    // tensor-core variant of the step (hn_model option tensor_cores): fp16 hi/lo planes of every activation (same
+    // offsets as yarena), of the current dz / dilated dz, an fp32 landing buffer for data gradients, epilogue constants
+    float *parena = nullptr, *pl_scratch = nullptr, *dtmp = nullptr, *aux_tmp = nullptr;
+    size_t din_max = 0;
     float *ones = nullptr, *zeros = nullptr;
     double* sums = nullptr;
     float* stem_in = nullptr;
@@ -73,6 +80,8 @@ float* grad_buffer(hn_model* m, TrainState* ts, const std::string& key) {
     return ts->grads[i];
 }
 
+unsigned short* planes_of(const TrainState* ts, const Act& y);
+
 // conv + BatchNorm2d (+ identity, ReLU) with tape.  run = false: only lay the buffers out (sizing pass).
 int unit_forward(hn_model* m, TrainState* ts, Bump& Y, Bump& Z, Bump& BN, const ConvLayer& c, const Act& in, const float* res,
                  const TrainCtx& tr, cudaStream_t st, bool run, Act* out) {
@@ -89,18 +98,23 @@ int unit_forward(hn_model* m, TrainState* ts, Bump& Y, Bump& Z, Bump& BN, const 
     ts->dz_max = std::max(ts->dz_max, u.z.numel());
     if (c.d.sh != 1 || c.d.sw != 1) ts->dil_max = std::max(ts->dil_max, (size_t)in.B * in.H * in.Wp() * c.d.Cout);
     ts->w_max = std::max(ts->w_max, (size_t)c.d.Cout * c.d.Cin * c.d.kh * c.d.kw);
+    ts->din_max = std::max(ts->din_max, in.numel());
     if (run) {
         const float* bias = c.biaskey.empty() ? nullptr : m->T(c.biaskey);
         ConvDesc raw = c.d;                       // z = conv + bias, no BN, no ReLU
         raw.relu = 0; raw.scale = ts->ones; raw.shift = bias ? bias : ts->zeros;
-        if (conv_f32(raw, in, u.z, nullptr, st)) return -1;
+        if (m->use_tc && c.wq && conv_tc_supported(raw, in, u.z)) {
+            // tcgen05 kernel, fp32 output: identity epilogue constants for this layer's weight-plane scale
+            if (tc_aux_update(ts->ones, raw.shift, c.tc_scale + 3 * c.d.Cout, ts->aux_tmp, c.d.Cout, st)) return -1;
+            if (conv_tc_planes(raw, c.wq, ts->aux_tmp, in, planes_of(ts, in), u.z, nullptr, u.z.p, nullptr, st)) return -1;
+        } else if (conv_f32(raw, in, u.z, nullptr, st)) return -1;
         if (u.train && bn_batch_stats(u.z, false, ts->sums, st)) return -1;
         if (bn_finalize_full(ts->sums, (long long)in.B * Ho * Wo, m->T(c.bnprefix + ".weight"), m->T(c.bnprefix + ".bias"),
                              bias, const_cast<float*>(m->T(c.bnprefix + ".running_mean")),
                              const_cast<float*>(m->T(c.bnprefix + ".running_var")), tr.bn_factor[c.bn_index], u.train, u.bn,
                              c.d.Cout, st))
             return -1;
-        if (bn_apply_fwd(u.z, u.bn, res, u.relu, u.y, st)) return -1;
+        if (bn_apply_fwd(u.z, u.bn, res, u.relu, u.y, m->use_tc ? planes_of(ts, u.y) : nullptr, st)) return -1;
     }
     ts->units.push_back(u);
     *out = u.y;
@@ -127,20 +141,26 @@ int walk_forward(hn_model* m, TrainState* ts, const float* x, int B, int in_chan
         ts->w_max = std::max(ts->w_max, (size_t)64 * 3 * 49);
         if (run) {
             if (stem_input_nhwc(x, in_channels, ts->stem_in, B, st)) return -1;
-            if (stem_f32(x, B, in_channels, m->stem.w, ts->ones, ts->zeros, u.z, st, false)) return -1;
+            if (m->use_tc && m->stem_tc_on) {
+                if (tc_aux_update(ts->ones, ts->zeros, m->stem_aux + 3 * 64, ts->aux_tmp, 64, st)) return -1;
+                if (stem_tc(x, B, in_channels, m->stem_wq, ts->aux_tmp, ts->zeros, reinterpret_cast<unsigned short*>(m->X[0]),
+                            u.z, st, false))
+                    return -1;
+            } else if (stem_f32(x, B, in_channels, m->stem.w, ts->ones, ts->zeros, u.z, st, false)) return -1;
             if (u.train && bn_batch_stats(u.z, false, ts->sums, st)) return -1;
             const std::string& p = m->stem.bnprefix;
             if (bn_finalize_full(ts->sums, (long long)B * 256 * 512, m->T(p + ".weight"), m->T(p + ".bias"), nullptr,
                                  const_cast<float*>(m->T(p + ".running_mean")), const_cast<float*>(m->T(p + ".running_var")),
                                  tr.bn_factor[m->stem.bn_index], u.train, u.bn, 64, st))
                 return -1;
-            if (bn_apply_fwd(u.z, u.bn, nullptr, true, u.y, st)) return -1;
+            if (bn_apply_fwd(u.z, u.bn, nullptr, true, u.y, nullptr, st)) return -1;
         }
         ts->units.push_back(u);
         ts->stem_y = u.y;
     }
     ts->pool_y = mk(Y.take((size_t)B * 128 * 258 * 64), B, 128, 256, 64);
     if (run && maxpool3x3s2(ts->stem_y, ts->pool_y, st, false)) return -1;
+    if (run && m->use_tc && split_planes(ts->pool_y.p, planes_of(ts, ts->pool_y), ts->pool_y.numel(), st)) return -1;
 
     // ---- layer1..4 (model.py:78-81, torchvision Bottleneck v1.5)
     Act cur = ts->pool_y, feats[4];
@@ -198,13 +218,16 @@ int walk_forward(hn_model* m, TrainState* ts, const float* x, int B, int in_chan
 int ensure_buffers(hn_model* m, TrainState* ts, int B, const TrainCtx& tr) {
     if (ts->sized && ts->B >= B) return 0;
     HN_CHECK(!ts->sized, "hn_train_forward: batch larger than the first training batch of this model handle");
-    ts->dz_max = ts->dil_max = ts->w_max = 0;
+    ts->dz_max = ts->dil_max = ts->w_max = ts->din_max = 0;
     if (walk_forward(m, ts, nullptr, B, 3, nullptr, nullptr, tr, 0, false)) return -1;     // sizing pass
     if (m->alloc_t(&ts->yarena, ts->ysize) || m->alloc_t(&ts->garena, ts->ysize) || m->alloc_t(&ts->zarena, ts->zsize) ||
         m->alloc_t(&ts->bnarena, ts->bnsize))
         return -1;
     if (m->alloc_t(&ts->dz_scratch, ts->dz_max) || m->alloc_t(&ts->dil_scratch, ts->dil_max) ||
         m->alloc_t(&ts->wd_scratch, ts->w_max) || m->alloc_t(&ts->dw_scratch, ts->w_max))
+        return -1;
+    if (m->alloc_t(&ts->parena, ts->ysize) || m->alloc_t(&ts->pl_scratch, std::max(ts->dz_max, ts->dil_max)) ||
+        m->alloc_t(&ts->dtmp, ts->din_max) || m->alloc_t(&ts->aux_tmp, 3 * 4096 + 2))
         return -1;
     if (m->alloc_t(&ts->ones, 4096) || m->alloc_t(&ts->zeros, 4096) || m->alloc_t(&ts->sums, 2 * 4096)) return -1;
     if (fill_f32(ts->ones, 4096, 1.f, 0) || fill_f32(ts->zeros, 4096, 0.f, 0)) return -1;
@@ -222,6 +245,10 @@ int ensure_buffers(hn_model* m, TrainState* ts, int B, const TrainCtx& tr) {
     ts->B = B;
     ts->sized = true;
     return 0;
+}
+
+unsigned short* planes_of(const TrainState* ts, const Act& y) {
+    return reinterpret_cast<unsigned short*>(ts->parena + (y.p - ts->yarena));
 }
 
 Act grad_of(const TrainState* ts, const Act& y) {
@@ -259,7 +286,7 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
             if (conv_f32(g, a, o, o.p, st)) return -1;
         }
         if (lstm_cell_scan(ts->gates, ts->cell, T_STEPS, B, st)) return -1;
-        if (lstm_bwd_steps(dout, ts->gates, ts->cell, m->whh[layer][0], m->whh[layer][1], ts->dgates, ts->dc, T_STEPS, B, st))
+        if (lstm_bwd_steps(dout, ts->gates, ts->cell, ts->whh_t, ts->whh_t + (size_t)512 * 2048, ts->dgates, ts->dc, T_STEPS, B, st))
             return -1;
         for (int dir = 0; dir < 2; ++dir) {
             const std::string sfx = l + (dir ? "_reverse" : "");
@@ -304,9 +331,31 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
         if (conv_wgrad_f32(u.d, u.in, dz, ts->dw_scratch, st)) return -1;
         if (ohwi_to_oihw(ts->dw_scratch, GRAD(c.wkey), u.d.Cout, u.d.Cin, u.d.kh, u.d.kw, st)) return -1;
         if (u.is_stem) continue;                                   // the image needs no gradient
-        if (pack_dgrad_weight(m->T(c.wkey), ts->wd_scratch, u.d.Cout, u.d.Cin, u.d.kh, u.d.kw, st)) return -1;
-        if (conv_dgrad_f32(u.d, ts->wd_scratch, dz, grad_of(ts, u.in), true, ts->dil_scratch, ts->ones, ts->zeros, st))
-            return -1;
+        const Act din = grad_of(ts, u.in);
+        ConvDesc t;                                               // the transposed convolution as a stride-1 conv
+        t.Cin = u.d.Cout; t.Cout = u.d.Cin; t.kh = u.d.kh; t.kw = u.d.kw;
+        t.ph = u.d.kh - 1 - u.d.ph; t.pw = u.d.kw - 1 - u.d.pw; t.shift = ts->zeros;
+        Act src = dz;
+        if (u.d.sh != 1 || u.d.sw != 1) { src = din; src.C = u.d.Cout; src.p = ts->dil_scratch; }
+        Act landing = din; landing.p = ts->dtmp;
+        if (m->use_tc && conv_tc_supported(t, src, landing)) {
+            // tcgen05: planes of the (dilated) dz, flipped weights packed as planes, fp32 result added to the gradient
+            if ((u.d.sh != 1 || u.d.sw != 1) && dilate_for_dgrad(dz, src, u.d.sh, u.d.sw, st)) return -1;
+            unsigned short* sp = reinterpret_cast<unsigned short*>(ts->pl_scratch);
+            unsigned short* wq = reinterpret_cast<unsigned short*>(ts->wd_scratch);
+            float* amax = ts->aux_tmp + 3 * 4096 + 1;            // gradients are tiny: power-of-two scaling around the planes
+            if (split_planes_pow2(src.p, sp, src.numel(), amax, st)) return -1;
+            if (flip_oihw(m->T(c.wkey), ts->dw_scratch, u.d.Cout, u.d.Cin, u.d.kh, u.d.kw, st)) return -1;
+            if (pack_weight_tc(ts->dw_scratch, wq, nullptr, nullptr, ts->aux_tmp, ts->aux_tmp + 3 * t.Cout, t.Cout, t.Cin, t.kh,
+                               t.kw, st))
+                return -1;
+            if (tc_aux_div_pow2(ts->aux_tmp, t.Cout, amax, st)) return -1;
+            if (conv_tc_planes(t, wq, ts->aux_tmp, src, sp, landing, nullptr, landing.p, nullptr, st)) return -1;
+            if (add_inplace(din.p, landing.p, din.numel(), st)) return -1;
+        } else {
+            if (pack_dgrad_weight(m->T(c.wkey), ts->wd_scratch, u.d.Cout, u.d.Cin, u.d.kh, u.d.kw, st)) return -1;
+            if (conv_dgrad_f32(u.d, ts->wd_scratch, dz, din, true, ts->dil_scratch, ts->ones, ts->zeros, st)) return -1;
+        }
     }
 #undef GRAD
     return 0;
@@ -423,7 +472,7 @@ int hn_bn_forward_backward(const float* z, int B, int H, int W, int C, const flo
     if (bn_finalize_full(sums, (long long)B * H * W, gamma, beta, nullptr, running_mean, running_var, factor, train != 0,
                          bn_scratch, C, st))
         return -1;
-    if (bn_apply_fwd(za, bn_scratch, res, relu != 0, ya, st)) return -1;
+    if (bn_apply_fwd(za, bn_scratch, res, relu != 0, ya, nullptr, st)) return -1;
     return bn_bwd(mk(const_cast<float*>(dy), B, H, W, C), ya, za, bn_scratch, train != 0, relu != 0, sums, mk(dz, B, H, W, C),
                   dres, dgamma, dbeta, nullptr, st);
 }
@@ -451,7 +500,7 @@ int hn_lstm_layer_backward(const float* xp, const float* hout, const float* whf,
         if (conv_f32(g, a, o, o.p, st)) return -1;
     }
     if (lstm_cell_scan(gates, cell, T, B, st)) return -1;
-    return lstm_bwd_steps(dout, gates, cell, whf, whb, dgates, dc, T, B, st);
+    return lstm_bwd_steps(dout, gates, cell, wt, wt + (size_t)512 * 2048, dgates, dc, T, B, st);
 }
 
 }  // extern "C"

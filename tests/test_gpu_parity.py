@@ -748,8 +748,10 @@ def test_lstm_layer_backward_vs_autograd(T, B):
         assert (dg[d].cpu().double() - ref).abs().max().item() <= 5e-5 * ref.abs().max().item(), d
 
 
-def test_training_step_gradients_match_autograd_of_the_oracle():
-    """BASELINE config 5 (train.py:44-58 + :278) at batch 2: net.train(); loss = L1(bon) + BCE-with-logits(cor);
+@pytest.mark.parametrize('tensor_cores', [True, False])
+def test_training_step_gradients_match_autograd_of_the_oracle(tensor_cores):
+    """tensor_cores: forward convolutions and data gradients on the tcgen05 kernel (default) / everything on the fp32
+    CUDA-core kernels.  BASELINE config 5 (train.py:44-58 + :278) at batch 2: net.train(); loss = L1(bon) + BCE-with-logits(cor);
     loss.backward() through the library against torch.autograd through the CPU oracle with the same dropout masks,
     for every one of the reference's parameters."""
     import torch.nn.functional as F
@@ -758,7 +760,7 @@ def test_training_step_gradients_match_autograd_of_the_oracle():
     gen = torch.Generator().manual_seed(9)
     y_bon = torch.rand(2, 2, 1024, generator=gen) - 0.5
     y_cor = torch.rand(2, 1, 1024, generator=gen)
-    net = _train_net(sd, True)
+    net = _train_net(sd, tensor_cores)
     torch.manual_seed(11)
     bon, cor = net(x.to(DEV))
     assert bon.requires_grad and cor.requires_grad
