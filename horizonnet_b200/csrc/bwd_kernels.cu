@@ -7,6 +7,8 @@
 //   bn_*                train / frozen BatchNorm2d forward-apply, backward reduce + apply (ReLU and identity fused)
 //   maxpool_bwd, ghc_to_sequence_bwd, head_bwd_*, lstm_* (gate recompute scan, one backward launch per time step)
 // Parity target: torch.autograd on the CPU oracle (tests/test_gpu_parity.py, relative tolerance in the tests).
+#include <cstdlib>
+
 #include "hn_common.cuh"
 #include "conv_tc.cuh"
 #include "bwd_kernels.cuh"
@@ -115,6 +117,99 @@ __global__ void __launch_bounds__(256) conv_wgrad_kernel(const WgradArgs a) {
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int k = k0 + tx * 4 + j;
+            if (k < a.K) atomicAdd(a.dw + (size_t)co * a.K + k, acc[i][j]);
+        }
+    }
+}
+
+// Same product on a 128 x 128 tile with 8 x 8 accumulators per thread and a double-buffered, register-prefetched pixel
+// loop (Cin % 4 == 0, Cout >= 128, K >= 128): 4 LDS.128 per 64 FMAs instead of 2 per 16.  Each thread owns rows
+// {ty*4.., 64+ty*4..} and columns {tx*4.., 64+tx*4..} so that every LDS.128 of a quarter-warp is contiguous.
+__global__ void __launch_bounds__(256, 2) conv_wgrad128_kernel(const WgradArgs a) {
+    __shared__ __align__(16) float Zs[2][16][128];
+    __shared__ __align__(16) float As[2][16][128];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int k0 = blockIdx.x * 128, co0 = blockIdx.y * 128;
+    const int m_begin = blockIdx.z * a.m_per_slice;
+    const int m_end = min(a.M, m_begin + a.m_per_slice);
+    const int lm = tid >> 4, lc = (tid & 15) * 4;
+    int k_ci[2], k_dy[2], k_dx[2];
+    bool k_ok[2];
+#pragma unroll
+    for (int g = 0; g < 2; ++g) {
+        const int k = k0 + lc + 64 * g;
+        k_ok[g] = k < a.K;
+        const int tap = k_ok[g] ? k / a.Cin : 0;
+        k_ci[g] = k_ok[g] ? k - tap * a.Cin : 0;
+        k_dy[g] = tap / a.kw;
+        k_dx[g] = tap - k_dy[g] * a.kw;
+    }
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float4 zr[2], ar[2];
+    auto load = [&](int mc) {
+        const int m = mc + lm;
+        zr[0] = zr[1] = ar[0] = ar[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m >= m_end) return;
+        const int wo = m % a.Wo;
+        const int t = m / a.Wo;
+        const int ho = t % a.Ho;
+        const int b = t / a.Ho;
+        const size_t zrow = (((size_t)b * a.Ho + ho) * a.Wop + wo + a.out_halo) * a.Cout;
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            if (co0 + lc + 64 * g + 3 < a.Cout) zr[g] = __ldg(reinterpret_cast<const float4*>(a.dz + zrow + co0 + lc + 64 * g));
+            if (k_ok[g]) {
+                const int hi = ho * a.sh - a.ph + k_dy[g];
+                if (hi >= 0 && hi < a.H)
+                    ar[g] = __ldg(reinterpret_cast<const float4*>(
+                        a.in + (((size_t)b * a.H + hi) * a.Wp + wo * a.sw + a.woff + k_dx[g]) * a.Cin + k_ci[g]));
+            }
+        }
+    };
+    auto store = [&](int buf) {
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+            *reinterpret_cast<float4*>(&Zs[buf][lm][lc + 64 * g]) = zr[g];
+            *reinterpret_cast<float4*>(&As[buf][lm][lc + 64 * g]) = ar[g];
+        }
+    };
+    load(m_begin);
+    store(0);
+    __syncthreads();
+    int buf = 0;
+    for (int mc = m_begin; mc < m_end; mc += 16, buf ^= 1) {
+        const bool more = mc + 16 < m_end;
+        if (more) load(mc + 16);
+#pragma unroll
+        for (int mm = 0; mm < 16; ++mm) {
+            float zz[8], aa[8];
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                const float4 z4 = *reinterpret_cast<const float4*>(&Zs[buf][mm][ty * 4 + 64 * g]);
+                const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][mm][tx * 4 + 64 * g]);
+                zz[4 * g] = z4.x; zz[4 * g + 1] = z4.y; zz[4 * g + 2] = z4.z; zz[4 * g + 3] = z4.w;
+                aa[4 * g] = a4.x; aa[4 * g + 1] = a4.y; aa[4 * g + 2] = a4.z; aa[4 * g + 3] = a4.w;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(zz[i], aa[j], acc[i][j]);
+        }
+        if (more) store(buf ^ 1);
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int co = co0 + ty * 4 + (i & 3) + 64 * (i >> 2);
+        if (co >= a.Cout) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + tx * 4 + (j & 3) + 64 * (j >> 2);
             if (k < a.K) atomicAdd(a.dw + (size_t)co * a.K + k, acc[i][j]);
         }
     }
@@ -492,7 +587,7 @@ __global__ void lstm_cell_scan_kernel(float* __restrict__ gates, float* __restri
     }
 }
 
-// One backward time step of both directions.  Block = 16 hidden units of one direction, warp = 2 of them: first
+// One backward time step of both directions.  Block = 8 hidden units of one direction, one per warp: first
 // dh[b][j] = dout[t][b][dir*512+j] + sum_n dG_prev[b][n] * W_hh[n][j] (W_hh^T rows and dG rows are read as coalesced
 // float4 streams, warp-shuffle reduction), then the gate gradients of step t for those units.
 struct LstmBwdArgs {
@@ -508,45 +603,40 @@ struct LstmBwdArgs {
 __global__ void __launch_bounds__(256) lstm_bwd_step_kernel(const LstmBwdArgs a) {
     const int dir = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int j0 = blockIdx.x * 16 + warp * 2;
+    const int j = blockIdx.x * 8 + warp;                      // one hidden unit per warp, 8 per block
     // reverse of the forward order: forward dir walks t = 0..T-1, so its backward starts at T-1
     const int t = dir == 0 ? a.T - 1 - a.step : a.step;
     const int tprev_bwd = dir == 0 ? t + 1 : t - 1;          // the step processed just before this one
     const int tprev_fwd = dir == 0 ? t - 1 : t + 1;          // c_{t-1} in forward order
-    const float4* w0 = reinterpret_cast<const float4*>(a.whh_t[dir] + (size_t)j0 * 2048);
-    const float4* w1 = reinterpret_cast<const float4*>(a.whh_t[dir] + (size_t)(j0 + 1) * 2048);
+    const float4* w = reinterpret_cast<const float4*>(a.whh_t[dir] + (size_t)j * 2048);
     for (int b0 = 0; b0 < a.B; b0 += 8) {
-        float acc[2][8];
+        float acc[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) acc[0][q] = acc[1][q] = 0.f;
+        for (int q = 0; q < 8; ++q) acc[q] = 0.f;
         if (a.step > 0) {
             const float* dg = a.dgates + (((size_t)dir * a.T + tprev_bwd) * a.B) * 2048;
+#pragma unroll 4
             for (int i = lane; i < 512; i += 32) {              // 512 float4 = 2048 gate rows
-                const float4 wa = __ldg(w0 + i), wb = __ldg(w1 + i);
+                const float4 wv = __ldg(w + i);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    if (b0 + q >= a.B) break;
-                    const float4 g = *reinterpret_cast<const float4*>(dg + (size_t)(b0 + q) * 2048 + i * 4);
-                    acc[0][q] = fmaf(g.x, wa.x, fmaf(g.y, wa.y, fmaf(g.z, wa.z, fmaf(g.w, wa.w, acc[0][q]))));
-                    acc[1][q] = fmaf(g.x, wb.x, fmaf(g.y, wb.y, fmaf(g.z, wb.z, fmaf(g.w, wb.w, acc[1][q]))));
+                    if (b0 + q < a.B) {
+                        const float4 g = *reinterpret_cast<const float4*>(dg + (size_t)(b0 + q) * 2048 + i * 4);
+                        acc[q] = fmaf(g.x, wv.x, fmaf(g.y, wv.y, fmaf(g.z, wv.z, fmaf(g.w, wv.w, acc[q]))));
+                    }
                 }
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q)
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    acc[0][q] += __shfl_xor_sync(0xffffffffu, acc[0][q], off);
-                    acc[1][q] += __shfl_xor_sync(0xffffffffu, acc[1][q], off);
-                }
+                for (int off = 16; off > 0; off >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
         }
-        // lane = (unit jj, batch q): 16 lanes finish one (b, j) cell each
-        const int jj = lane >> 3, q = lane & 7;
-        const int b = b0 + q;
-        if (jj < 2 && b < a.B) {
+        // lanes 0..7 finish one (b, j) cell each
+        const int b = b0 + lane;
+        if (lane < 8 && b < a.B) {
             float dh = 0.f;
 #pragma unroll
-            for (int qq = 0; qq < 8; ++qq) if (qq == q) dh = jj ? acc[1][qq] : acc[0][qq];
-            const int j = j0 + jj;
+            for (int q = 0; q < 8; ++q) if (q == lane) dh = acc[q];
             dh += a.dout[((size_t)t * a.B + b) * 1024 + dir * 512 + j];
             const float* g = a.gates + (((size_t)dir * a.T + t) * a.B + b) * 2048;
             const float ig = g[j], fg = g[512 + j], gg = g[1024 + j], og = g[1536 + j];
@@ -564,6 +654,87 @@ __global__ void __launch_bounds__(256) lstm_bwd_step_kernel(const LstmBwdArgs a)
             o[1536 + j] = dh * tc * og * (1.f - og);
             *dcp = dc * fg;
         }
+    }
+}
+
+// The same recurrence as ONE cooperative launch: every warp keeps its W_hh^T row in registers for all T steps, the steps
+// are separated by a grid barrier (arrival counter + bounded spin; a time-out raises *error_flag and lets the kernel
+// run out instead of hanging).  dG of the previous step is read with ld.global.cg (written by other CTAs of this launch).
+__global__ void __launch_bounds__(256) lstm_bwd_persistent_kernel(const LstmBwdArgs a, unsigned int* __restrict__ barrier,
+                                                                  int* __restrict__ error_flag) {
+    const int dir = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int j = blockIdx.x * 8 + warp;
+    const unsigned int nblocks = gridDim.x * gridDim.y;
+    float4 wreg[16];
+    {
+        const float4* w = reinterpret_cast<const float4*>((dir == 0 ? a.whh_t[0] : a.whh_t[1]) + (size_t)j * 2048);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) wreg[i] = __ldg(w + lane + 32 * i);
+    }
+    bool dead = false;
+    for (int step = 0; step < a.T; ++step) {
+        const int t = dir == 0 ? a.T - 1 - step : step;
+        const int tprev_bwd = dir == 0 ? t + 1 : t - 1;
+        const int tprev_fwd = dir == 0 ? t - 1 : t + 1;
+        for (int b0 = 0; b0 < a.B; b0 += 8) {
+            float acc[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[q] = 0.f;
+            if (step > 0) {
+                const float* dg = a.dgates + (((size_t)dir * a.T + tprev_bwd) * a.B) * 2048;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        if (b0 + q < a.B) {
+                            const float4 g = __ldcg(reinterpret_cast<const float4*>(dg + (size_t)(b0 + q) * 2048) + lane + 32 * i);
+                            acc[q] = fmaf(g.x, wreg[i].x, fmaf(g.y, wreg[i].y, fmaf(g.z, wreg[i].z, fmaf(g.w, wreg[i].w, acc[q]))));
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+#pragma unroll
+                    for (int off = 16; off > 0; off >>= 1) acc[q] += __shfl_xor_sync(0xffffffffu, acc[q], off);
+            }
+            const int b = b0 + lane;
+            if (lane < 8 && b < a.B) {
+                float dh = 0.f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) if (q == lane) dh = acc[q];
+                dh += a.dout[((size_t)t * a.B + b) * 1024 + dir * 512 + j];
+                const float* g = a.gates + (((size_t)dir * a.T + t) * a.B + b) * 2048;
+                const float ig = g[j], fg = g[512 + j], gg = g[1024 + j], og = g[1536 + j];
+                const float c = a.cell[(((size_t)dir * a.T + t) * a.B + b) * 512 + j];
+                const float cprev = (tprev_fwd < 0 || tprev_fwd >= a.T)
+                                        ? 0.f : a.cell[(((size_t)dir * a.T + tprev_fwd) * a.B + b) * 512 + j];
+                const float tc = tanhf(c);
+                float* dcp = a.dc + ((size_t)dir * a.B + b) * 512 + j;
+                const float dcar = step > 0 ? *dcp : 0.f;
+                const float dc = dcar + dh * og * (1.f - tc * tc);
+                float* o = a.dgates + (((size_t)dir * a.T + t) * a.B + b) * 2048;
+                o[j] = dc * gg * ig * (1.f - ig);
+                o[512 + j] = dc * cprev * fg * (1.f - fg);
+                o[1024 + j] = dc * ig * (1.f - gg * gg);
+                o[1536 + j] = dh * tc * og * (1.f - og);
+                *dcp = dc * fg;
+            }
+        }
+        if (step + 1 == a.T) break;
+        // ---- grid barrier
+        __syncthreads();
+        if (threadIdx.x == 0 && !dead) {
+            __threadfence();
+            atomicAdd(barrier, 1u);
+            const unsigned int target = (unsigned int)(step + 1) * nblocks;
+            unsigned int spins = 0;
+            while (*reinterpret_cast<volatile unsigned int*>(barrier) < target) {
+                if (++spins > (1u << 26)) { atomicExch(error_flag, 1); dead = true; break; }
+            }
+            __threadfence();
+        }
+        __syncthreads();
     }
 }
 
@@ -727,8 +898,10 @@ int conv_wgrad_f32(const ConvDesc& d, const Act& in, const Act& dz, float* dw_oh
     a.M = (int)M; a.K = d.kh * d.kw * d.Cin;
     HN_CUDA_OK(cudaMemsetAsync(dw_ohwi, 0, (size_t)d.Cout * a.K * sizeof(float), st));
     if (a.M == 0) return 0;
-    const int gx = (a.K + 63) / 64, gy = (d.Cout + 63) / 64;
-    long long slices = (148ll * 6 + gx * gy - 1) / (gx * gy);
+    const bool big = d.Cin % 4 == 0 && d.Cout >= 128 && a.K >= 128 && d.Cout % 4 == 0;
+    const int tile = big ? 128 : 64;
+    const int gx = (a.K + tile - 1) / tile, gy = (d.Cout + tile - 1) / tile;
+    long long slices = (148ll * (big ? 2 : 6) + gx * gy - 1) / (gx * gy);
     const long long max_slices = (M + 255) / 256;                  // at least 256 pixels per slice
     if (slices > max_slices) slices = max_slices;
     if (slices < 1) slices = 1;
@@ -736,7 +909,8 @@ int conv_wgrad_f32(const ConvDesc& d, const Act& in, const Act& dz, float* dw_oh
     a.m_per_slice = (int)(((M + slices - 1) / slices + 15) / 16 * 16);
     slices = (M + a.m_per_slice - 1) / a.m_per_slice;
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)slices);
-    if (d.Cin % 4 == 0) conv_wgrad_kernel<true><<<grid, 256, 0, st>>>(a);
+    if (big) conv_wgrad128_kernel<<<grid, 256, 0, st>>>(a);
+    else if (d.Cin % 4 == 0) conv_wgrad_kernel<true><<<grid, 256, 0, st>>>(a);
     else conv_wgrad_kernel<false><<<grid, 256, 0, st>>>(a);
     HN_LAUNCH_OK();
     return 0;
@@ -870,13 +1044,28 @@ int lstm_cell_scan(float* gates, float* cell, int T, int B, cudaStream_t st) {
 }
 
 int lstm_bwd_steps(const float* dout, const float* gates, const float* cell, const float* whh_t_f, const float* whh_t_b,
-                   float* dgates, float* dc, int T, int B, cudaStream_t st) {
+                   float* dgates, float* dc, int T, int B, unsigned int* barrier, int* error_flag, cudaStream_t st) {
     LstmBwdArgs a;
     a.dout = dout; a.gates = gates; a.cell = cell; a.whh_t[0] = whh_t_f; a.whh_t[1] = whh_t_b; a.dgates = dgates; a.dc = dc;
-    a.T = T; a.B = B;
+    a.T = T; a.B = B; a.step = 0;
+    static const bool persistent_on = [] { const char* e = getenv("HN_LSTM_BWD_PERSISTENT"); return !(e && atoi(e) == 0); }();
+    int dev = 0, coop = 0, sms = 0, per_sm = 0;
+    HN_CUDA_OK(cudaGetDevice(&dev));
+    HN_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
+    HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    HN_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_persistent_kernel, 256, 0));
+    if (persistent_on && barrier && error_flag && coop && per_sm * sms >= 128) {
+        // one cooperative launch for the whole sequence (128 co-resident CTAs, grid barrier between the steps)
+        HN_CUDA_OK(cudaMemsetAsync(barrier, 0, sizeof(unsigned int), st));
+        void* args[] = {&a, &barrier, &error_flag};
+        HN_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_bwd_persistent_kernel), dim3(64, 2), dim3(256), args,
+                                               0, st));
+        HN_LAUNCH_OK();
+        return 0;
+    }
     for (int s = 0; s < T; ++s) {
         a.step = s;
-        lstm_bwd_step_kernel<<<dim3(32, 2), 256, 0, st>>>(a);
+        lstm_bwd_step_kernel<<<dim3(64, 2), 256, 0, st>>>(a);
         HN_LAUNCH_OK();
     }
     return 0;

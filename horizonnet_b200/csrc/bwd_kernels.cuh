@@ -44,8 +44,10 @@ int col_sum(const float* x, size_t rows, int cols, float* out, cudaStream_t st);
 int lstm_gather(const float* hout, const float* xp, float* hprev, float* xpd, int T, int B, cudaStream_t st);
 int lstm_cell_scan(float* gates, float* cell, int T, int B, cudaStream_t st);
 // whh_t_*: W_hh transposed, [512][2048] (the same copies the gate GEMM uses)
+// barrier (1 uint) / error_flag (1 int): device scratch of the single cooperative launch (grid barrier between the steps;
+// a barrier time-out sets *error_flag); nullptr or HN_LSTM_BWD_PERSISTENT=0: one launch per time step
 int lstm_bwd_steps(const float* dout, const float* gates, const float* cell, const float* whh_t_f, const float* whh_t_b,
-                   float* dgates, float* dc, int T, int B, cudaStream_t st);
+                   float* dgates, float* dc, int T, int B, unsigned int* barrier, int* error_flag, cudaStream_t st);
 int stem_input_nhwc(const float* x, int in_channels, float* out, int B, cudaStream_t st);
 
 }  // namespace hn

@@ -58,10 +58,15 @@ struct TrainState {
     float *seq = nullptr, *xp[2] = {nullptr, nullptr}, *r[2] = {nullptr, nullptr}, *rm[2] = {nullptr, nullptr};
     float *hprev = nullptr, *gates = nullptr, *cell = nullptr, *dgates = nullptr, *dc = nullptr;
     float *da = nullptr, *db = nullptr, *whh_t = nullptr;
+    unsigned int* barrier = nullptr;
     std::vector<Unit> units;
     Act stem_y, pool_y, gout[4];
     TrainCtx ctx{};
     std::vector<float*> grads;           // per TensorSlot
+    // phase boundaries of the last backward: start, head, lstm, tail, conv units (bn / wgrad / dgrad are summed on the host
+    // from per-unit events only when HN_TRAIN_PROF=1), end
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    bool timed = false;
 };
 
 TrainState* state_of(hn_model* m) {
@@ -239,7 +244,8 @@ int ensure_buffers(hn_model* m, TrainState* ts, int B, const TrainCtx& tr) {
             return -1;
     if (m->alloc_t(&ts->hprev, 2 * rows * 512) || m->alloc_t(&ts->gates, 2 * rows * 2048) ||
         m->alloc_t(&ts->cell, 2 * rows * 512) || m->alloc_t(&ts->dgates, 2 * rows * 2048) ||
-        m->alloc_t(&ts->dc, (size_t)2 * B * 512) || m->alloc_t(&ts->whh_t, (size_t)2 * 512 * 2048))
+        m->alloc_t(&ts->dc, (size_t)2 * B * 512) || m->alloc_t(&ts->whh_t, (size_t)2 * 512 * 2048) ||
+        m->alloc_t(&ts->barrier, 4))
         return -1;
     HN_CUDA_OK(cudaStreamSynchronize(0));
     ts->B = B;
@@ -261,6 +267,8 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
     const int B = ts->units.front().z.B;
     const size_t rows = (size_t)T_STEPS * B, nseq = rows * 1024;
     const TrainCtx& tr = ts->ctx;
+    for (auto& e : ts->ev) if (!e) HN_CUDA_OK(cudaEventCreate(&e));
+    HN_CUDA_OK(cudaEventRecord(ts->ev[0], st));
     HN_CUDA_OK(cudaMemsetAsync(ts->garena, 0, ts->ysize * sizeof(float), st));
 #define GRAD(key) grad_buffer(m, ts, key)
     // ---- linear head (model.py:266) and its dropout (:265)
@@ -271,6 +279,7 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
     if (tr.head_p > 0.0 && (tr.mask[1] ? multiply_inplace(dout, tr.mask[1], nseq, st)
                                        : dropout_inplace(dout, nseq, tr.head_p, tr.seed, 1, false, st)))
         return -1;
+    HN_CUDA_OK(cudaEventRecord(ts->ev[1], st));
     // ---- bi-LSTM, layer 1 then layer 0 (model.py:264)
     for (int layer = 1; layer >= 0; --layer) {
         const std::string l = "_l" + std::to_string(layer);
@@ -286,7 +295,8 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
             if (conv_f32(g, a, o, o.p, st)) return -1;
         }
         if (lstm_cell_scan(ts->gates, ts->cell, T_STEPS, B, st)) return -1;
-        if (lstm_bwd_steps(dout, ts->gates, ts->cell, ts->whh_t, ts->whh_t + (size_t)512 * 2048, ts->dgates, ts->dc, T_STEPS, B, st))
+        if (lstm_bwd_steps(dout, ts->gates, ts->cell, ts->whh_t, ts->whh_t + (size_t)512 * 2048, ts->dgates, ts->dc, T_STEPS, B,
+                           ts->barrier, m->error_flag, st))
             return -1;
         for (int dir = 0; dir < 2; ++dir) {
             const std::string sfx = l + (dir ? "_reverse" : "");
@@ -312,10 +322,12 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
             return -1;
         std::swap(dout, dnext);
     }
+    HN_CUDA_OK(cudaEventRecord(ts->ev[2], st));
     // dout = d(sequence) -> the four height-reduction outputs (model.py:152-155, 175-178, 263)
     Act dg[4];
     for (int s = 0; s < 4; ++s) dg[s] = grad_of(ts, ts->gout[s]);
     if (ghc_to_sequence_bwd(dout, dg, st)) return -1;
+    HN_CUDA_OK(cudaEventRecord(ts->ev[3], st));
 
     // ---- conv units in reverse
     for (size_t ui = ts->units.size(); ui-- > 0;) {
@@ -358,6 +370,8 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
         }
     }
 #undef GRAD
+    HN_CUDA_OK(cudaEventRecord(ts->ev[4], st));
+    ts->timed = true;
     return 0;
 }
 
@@ -413,6 +427,23 @@ int hn_model_get_grad(hn_model* m, const char* key, float* out, long long numel,
     HN_ON_DEVICE(m->device);
     HN_CUDA_OK(cudaMemcpyAsync(out, ts->grads[it->second], (size_t)numel * sizeof(float), cudaMemcpyDeviceToDevice,
                                (cudaStream_t)stream));
+    return 0;
+}
+
+// Device time of the phases of the last hn_train_backward: ms[0] linear head, [1] bi-LSTM BPTT (both layers),
+// [2] sequence -> height-reduction outputs, [3] the 69 conv units (BN backward + weight gradient + data gradient).
+// Synchronises with the backward's stream.
+int hn_train_profile(hn_model* m, double ms[4]) {
+    HN_CHECK(m && ms, "hn_train_profile: NULL argument");
+    TrainState* ts = state_of(m);
+    HN_CHECK(ts->timed, "hn_train_profile: no backward has run");
+    HN_ON_DEVICE(m->device);
+    HN_CUDA_OK(cudaEventSynchronize(ts->ev[4]));
+    for (int i = 0; i < 4; ++i) {
+        float t = 0.f;
+        HN_CUDA_OK(cudaEventElapsedTime(&t, ts->ev[i], ts->ev[i + 1]));
+        ms[i] = t;
+    }
     return 0;
 }
 
@@ -500,7 +531,8 @@ int hn_lstm_layer_backward(const float* xp, const float* hout, const float* whf,
         if (conv_f32(g, a, o, o.p, st)) return -1;
     }
     if (lstm_cell_scan(gates, cell, T, B, st)) return -1;
-    return lstm_bwd_steps(dout, gates, cell, wt, wt + (size_t)512 * 2048, dgates, dc, T, B, st);
+    // the unit test covers the one-launch-per-step kernel; the cooperative one is covered by the whole-step tests
+    return lstm_bwd_steps(dout, gates, cell, wt, wt + (size_t)512 * 2048, dgates, dc, T, B, nullptr, nullptr, st);
 }
 
 }  // extern "C"

@@ -344,6 +344,13 @@ class HorizonNet(nn.Module):
         h['tape_keepalive'] = None
         return grads
 
+    def train_profile(self, device=None):
+        """Device ms of the phases of the last backward: {'head', 'lstm', 'sequence', 'conv_units'}."""
+        key = next(iter(self._handles)) if device is None else device
+        ms = (ctypes.c_double * 4)()
+        _lib.check(_lib.lib().hn_train_profile(self._handles[key]['ptr'], ms), 'hn_train_profile')
+        return dict(zip(('head', 'lstm', 'sequence', 'conv_units'), [round(v, 3) for v in ms]))
+
     def debug_train_unit(self, i, what=0, device=None):
         """Tape of the last training-step forward (test hook): conv unit i in graph order (stem, blocks, height
         reduction) -> (BatchNorm2d prefix, NCHW tensor); what = 0 activation, 1 raw conv output, 2 its gradient."""

@@ -112,6 +112,8 @@ int hn_train_forward(hn_model* m, const float* x_nchw_dev, int batch, int in_cha
                      void* stream);
 int hn_train_backward(hn_model* m, const float* dbon_dev, const float* dcor_dev, void* stream);
 int hn_model_get_grad(hn_model* m, const char* key, float* out_dev, long long numel, void* stream);
+/* Device time (ms) of the phases of the last hn_train_backward: head, bi-LSTM BPTT, sequence adjoint, the 69 conv units. */
+int hn_train_profile(hn_model* m, double ms[4]);
 /* Tape inspection for tests: conv unit i of the last hn_train_forward (graph order: stem, blocks, height reduction);
  * what = 0 activation, 1 raw conv output, 2 gradient of the activation; halo-1 NHWC copy, dims = {B, H, W, C}. */
 int hn_train_debug_unit(hn_model* m, int i, int what, float* out_dev, long long capacity, int dims[4], char* name,

@@ -625,6 +625,8 @@ BWD_CONV_CASES = [
     (2, 512, 2, 32, 256, 3, (2, 1), 1, True),      # real height-reduction shapes: H 2 -> 1
     (2, 64, 16, 256, 32, 3, (2, 1), 1, True),      # ghc_lst.0.layer.3: W = 256, Cout = 32, several pixel slices
     (2, 1024, 4, 32, 512, 3, (2, 1), 1, True),     # ghc_lst.3.layer.2: K = 9216
+    (2, 128, 16, 64, 192, 3, (1, 1), 1, False),    # 128 x 128 weight-gradient tile with a ragged second tile (Cout = 192, K = 1152)
+    (3, 256, 10, 32, 128, 1, (1, 1), 1, True),     # 1x1, K = 256: two full k tiles, M = 960 over several slices
 ]
 
 
