@@ -67,6 +67,22 @@ struct TrainState {
     // from per-unit events only when HN_TRAIN_PROF=1), end
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool timed = false;
+    std::vector<void*> owned;            // batch-sized buffers (freed and laid out again when a larger batch arrives)
+    template <typename T>
+    int alloc_t(T** p, size_t n) {
+        HN_CUDA_OK(cudaMalloc(reinterpret_cast<void**>(p), (n ? n : 1) * sizeof(T)));
+        owned.push_back(*p);
+        return 0;
+    }
+    void release() {
+        for (void* q : owned) cudaFree(q);
+        owned.clear();
+        sized = false; have_tape = false;
+    }
+    ~TrainState() {
+        release();
+        for (auto e : ev) if (e) cudaEventDestroy(e);
+    }
 };
 
 TrainState* state_of(hn_model* m) {
@@ -222,30 +238,33 @@ int walk_forward(hn_model* m, TrainState* ts, const float* x, int B, int in_chan
 
 int ensure_buffers(hn_model* m, TrainState* ts, int B, const TrainCtx& tr) {
     if (ts->sized && ts->B >= B) return 0;
-    HN_CHECK(!ts->sized, "hn_train_forward: batch larger than the first training batch of this model handle");
+    if (ts->sized) {                      // a larger batch than the buffers were laid out for
+        HN_CUDA_OK(cudaDeviceSynchronize());
+        ts->release();
+    }
     ts->dz_max = ts->dil_max = ts->w_max = ts->din_max = 0;
     if (walk_forward(m, ts, nullptr, B, 3, nullptr, nullptr, tr, 0, false)) return -1;     // sizing pass
-    if (m->alloc_t(&ts->yarena, ts->ysize) || m->alloc_t(&ts->garena, ts->ysize) || m->alloc_t(&ts->zarena, ts->zsize) ||
-        m->alloc_t(&ts->bnarena, ts->bnsize))
+    if (ts->alloc_t(&ts->yarena, ts->ysize) || ts->alloc_t(&ts->garena, ts->ysize) || ts->alloc_t(&ts->zarena, ts->zsize) ||
+        ts->alloc_t(&ts->bnarena, ts->bnsize))
         return -1;
-    if (m->alloc_t(&ts->dz_scratch, ts->dz_max) || m->alloc_t(&ts->dil_scratch, ts->dil_max) ||
-        m->alloc_t(&ts->wd_scratch, ts->w_max) || m->alloc_t(&ts->dw_scratch, ts->w_max))
+    if (ts->alloc_t(&ts->dz_scratch, ts->dz_max) || ts->alloc_t(&ts->dil_scratch, ts->dil_max) ||
+        ts->alloc_t(&ts->wd_scratch, ts->w_max) || ts->alloc_t(&ts->dw_scratch, ts->w_max))
         return -1;
-    if (m->alloc_t(&ts->parena, ts->ysize) || m->alloc_t(&ts->pl_scratch, std::max(ts->dz_max, ts->dil_max)) ||
-        m->alloc_t(&ts->dtmp, ts->din_max) || m->alloc_t(&ts->aux_tmp, 3 * 4096 + 2))
+    if (ts->alloc_t(&ts->parena, ts->ysize) || ts->alloc_t(&ts->pl_scratch, std::max(ts->dz_max, ts->dil_max)) ||
+        ts->alloc_t(&ts->dtmp, ts->din_max) || ts->alloc_t(&ts->aux_tmp, 3 * 4096 + 2))
         return -1;
-    if (m->alloc_t(&ts->ones, 4096) || m->alloc_t(&ts->zeros, 4096) || m->alloc_t(&ts->sums, 2 * 4096)) return -1;
+    if (ts->alloc_t(&ts->ones, 4096) || ts->alloc_t(&ts->zeros, 4096) || ts->alloc_t(&ts->sums, 2 * 4096)) return -1;
     if (fill_f32(ts->ones, 4096, 1.f, 0) || fill_f32(ts->zeros, 4096, 0.f, 0)) return -1;
-    if (m->alloc_t(&ts->stem_in, (size_t)B * 512 * 1030 * 3)) return -1;
+    if (ts->alloc_t(&ts->stem_in, (size_t)B * 512 * 1030 * 3)) return -1;
     const size_t rows = (size_t)T_STEPS * B;
-    if (m->alloc_t(&ts->seq, rows * 1024) || m->alloc_t(&ts->da, rows * 1024) || m->alloc_t(&ts->db, rows * 1024)) return -1;
+    if (ts->alloc_t(&ts->seq, rows * 1024) || ts->alloc_t(&ts->da, rows * 1024) || ts->alloc_t(&ts->db, rows * 1024)) return -1;
     for (int l = 0; l < 2; ++l)
-        if (m->alloc_t(&ts->xp[l], rows * 4096) || m->alloc_t(&ts->r[l], rows * 1024) || m->alloc_t(&ts->rm[l], rows * 1024))
+        if (ts->alloc_t(&ts->xp[l], rows * 4096) || ts->alloc_t(&ts->r[l], rows * 1024) || ts->alloc_t(&ts->rm[l], rows * 1024))
             return -1;
-    if (m->alloc_t(&ts->hprev, 2 * rows * 512) || m->alloc_t(&ts->gates, 2 * rows * 2048) ||
-        m->alloc_t(&ts->cell, 2 * rows * 512) || m->alloc_t(&ts->dgates, 2 * rows * 2048) ||
-        m->alloc_t(&ts->dc, (size_t)2 * B * 512) || m->alloc_t(&ts->whh_t, (size_t)2 * 512 * 2048) ||
-        m->alloc_t(&ts->barrier, 4))
+    if (ts->alloc_t(&ts->hprev, 2 * rows * 512) || ts->alloc_t(&ts->gates, 2 * rows * 2048) ||
+        ts->alloc_t(&ts->cell, 2 * rows * 512) || ts->alloc_t(&ts->dgates, 2 * rows * 2048) ||
+        ts->alloc_t(&ts->dc, (size_t)2 * B * 512) || ts->alloc_t(&ts->whh_t, (size_t)2 * 512 * 2048) ||
+        ts->alloc_t(&ts->barrier, 4))
         return -1;
     HN_CUDA_OK(cudaStreamSynchronize(0));
     ts->B = B;

@@ -895,3 +895,35 @@ def test_training_loop_like_train_py_reduces_the_loss():
         ebon, ecor = net(x)
         rbon, rcor = horizonnet_ref.forward({k: v.cpu() for k, v in net.state_dict().items()}, x.cpu())
     assert (ebon.cpu() - rbon).abs().max().item() < 2e-4 and (ecor.cpu() - rcor).abs().max().item() < 2e-4
+
+
+def test_training_batch_growth_on_one_library_handle():
+    """The tape buffers are laid out for the first training batch; a larger one later on the same handle (created by an
+    eval forward of the larger batch) frees and re-lays them out.  The larger step must equal a fresh model's step."""
+    import torch.nn.functional as F
+    sd = synthetic_state_dict(4, 'random')
+    x = synthetic_panoramas(2, seed=51).to(DEV)
+    y_bon, y_cor = torch.zeros(2, 2, 1024, device=DEV), torch.full((2, 1, 1024), 0.5, device=DEV)
+
+    def step(net, xb):
+        torch.manual_seed(3)
+        net.zero_grad()
+        bon, cor = net(xb)
+        n = xb.shape[0]
+        loss = F.l1_loss(bon, y_bon[:n]) + F.binary_cross_entropy_with_logits(cor, y_cor[:n])
+        loss.backward()
+        return loss.item(), net.linear.weight.grad.clone(), net.feature_extractor.encoder.conv1[1].weight.grad.clone()
+
+    net = _train_net(sd, True)
+    net.eval()
+    with torch.no_grad():
+        net(x)                                   # handle with max_batch = 2
+    net.train()
+    step(net, x[:1])                             # tape laid out for batch 1 ...
+    net.load_state_dict(sd)                      # (undo the running-statistics update of that step)
+    l2, g2a, g2b = step(net, x)                  # ... and again for batch 2
+    fresh = _train_net(sd, True)
+    l2f, g2fa, g2fb = step(fresh, x)
+    net.check()
+    assert abs(l2 - l2f) < 1e-6
+    assert torch.allclose(g2a, g2fa, rtol=1e-4, atol=1e-9) and torch.allclose(g2b, g2fb, rtol=1e-3, atol=1e-8)
