@@ -926,4 +926,6 @@ def test_training_batch_growth_on_one_library_handle():
     l2f, g2fa, g2fb = step(fresh, x)
     net.check()
     assert abs(l2 - l2f) < 1e-6
-    assert torch.allclose(g2a, g2fa, rtol=1e-4, atol=1e-9) and torch.allclose(g2b, g2fb, rtol=1e-3, atol=1e-8)
+    # (the weight gradients are fp32 atomic sums: equal up to summation order)
+    for a, b in ((g2a, g2fa), (g2b, g2fb)):
+        assert float((a - b).abs().max()) <= 1e-4 * float(b.abs().max())
