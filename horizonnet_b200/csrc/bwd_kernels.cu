@@ -901,11 +901,18 @@ int conv_wgrad_f32(const ConvDesc& d, const Act& in, const Act& dz, float* dw_oh
     const bool big = d.Cin % 4 == 0 && d.Cout >= 128 && a.K >= 128 && d.Cout % 4 == 0;
     const int tile = big ? 128 : 64;
     const int gx = (a.K + tile - 1) / tile, gy = (d.Cout + tile - 1) / tile;
-    long long slices = (148ll * (big ? 2 : 6) + gx * gy - 1) / (gx * gy);
-    const long long max_slices = (M + 255) / 256;                  // at least 256 pixels per slice
-    if (slices > max_slices) slices = max_slices;
-    if (slices < 1) slices = 1;
-    if (slices > 65535) slices = 65535;
+    // pixel slices: the CTAs of a launch all do the same amount of work, so pick the slice count whose CTA total fills
+    // whole waves of the resident slots best (ncu: 320 CTAs on 296 slots left the SMs idle a third of the time)
+    const long long tiles = (long long)gx * gy, slots = 148ll * (big ? 2 : 4);
+    long long max_slices = (M + 255) / 256;                        // at least 256 pixels per slice
+    if (max_slices > 64) max_slices = 64;
+    long long slices = 1;
+    double best = 0.0;
+    for (long long s = 1; s <= max_slices; ++s) {
+        const long long total = tiles * s, waves = (total + slots - 1) / slots;
+        const double fill = (double)total / (double)(waves * slots);
+        if (fill > best + 0.02) { best = fill; slices = s; }       // more slices only for a real gain (more atomics)
+    }
     a.m_per_slice = (int)(((M + slices - 1) / slices + 15) / 16 * 16);
     slices = (M + a.m_per_slice - 1) / a.m_per_slice;
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)slices);
