@@ -644,10 +644,18 @@ def train_step_aux(dev, batch=8, steps=3):
             fw += ev[0].elapsed_time(ev[1]); bw += ev[1].elapsed_time(ev[2]); op += ev[2].elapsed_time(ev[3])
     net.check()
     phases = net.train_profile()
+    from horizonnet_b200 import _lib
+    wgrad_tc = bool(_lib.lib().hn_wgrad_tc_enabled())
     fw, bw, op = fw / steps, bw / steps, op / steps
     out = {'batch': batch, 'forward_ms': round(fw, 2), 'backward_ms': round(bw, 2), 'optimizer_ms': round(op, 2),
            'step_ms': round(fw + bw + op, 2), 'panoramas_per_s': round(batch / (fw + bw + op) * 1e3, 2),
-           'backward_phases_ms': phases, 'final_loss': round(float(loss), 5), 'dtype': 'convolutions + their data gradients: tcgen05 split-fp16 planes (fp32-equivalent); weight gradients, BatchNorm, LSTM BPTT: fp32 CUDA cores',
+           'backward_phases_ms': phases, 'final_loss': round(float(loss), 5),
+           'dtype': ('convolutions, their data gradients and the weight gradients of the Cin/Cout %% 64 == 0 convolutions: tcgen05 '
+                     'split-fp16 planes (fp32-equivalent); other weight gradients, BatchNorm, LSTM BPTT: fp32 CUDA cores'
+                     if wgrad_tc else
+                     'convolutions + their data gradients: tcgen05 split-fp16 planes (fp32-equivalent); weight gradients, '
+                     'BatchNorm, LSTM BPTT: fp32 CUDA cores'),
+           'wgrad_tc': wgrad_tc,
            'api': 'HorizonNet.train(); net(x); loss.backward(); Adam.step()  (hn_train_forward / hn_train_backward)',
            'note': 'forward_ms includes the re-upload + re-packing of the weights the optimizer just changed'}
     del net, opt

@@ -770,16 +770,7 @@ __global__ void flip_oihw_kernel(const float* __restrict__ w, float* __restrict_
 // Gradients are orders of magnitude smaller than activations, and the fp16 hi/lo planes (conv_tc.cuh: value * 2^-4) only
 // carry ~22 bits for values well above 2^-14: a gradient tensor is therefore multiplied by a power of two that brings its
 // largest magnitude to [2^11, 2^12) before it is split, and the convolution result is divided by it in the epilogue
-// constants (exact: powers of two).
-__device__ __forceinline__ float pow2_factor(float absmax) {
-    if (!(absmax > 0.f) || isinf(absmax)) return 1.f;
-    int e;
-    frexpf(absmax, &e);                      // absmax = m * 2^e, m in [0.5, 1)
-    e = 12 - e;
-    e = e < -100 ? -100 : (e > 100 ? 100 : e);
-    return ldexpf(1.f, e);
-}
-
+// constants (exact: powers of two); pow2_factor lives in conv_tc.cuh (the tcgen05 weight-gradient kernel divides it out too).
 __global__ void absmax_f32_kernel(const float* __restrict__ x, size_t n, float* __restrict__ out) {
     float m = 0.f;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)

@@ -16,6 +16,15 @@ int dilate_for_dgrad(const Act& dz, const Act& out, int sh, int sw, cudaStream_t
 
 // dW[Cout][kh][kw][Cin] (zeroed here, then accumulated); in = the conv's forward input, dz = d(raw conv output)
 int conv_wgrad_f32(const ConvDesc& d, const Act& in, const Act& dz, float* dw_ohwi, cudaStream_t st);
+// The same product on tcgen05 (wgrad_tc.cu) from the split planes of the input and of dz (split_planes_pow2; dz_absmax =
+// the float it left behind): Cin, Cout multiples of 64, halo-1 tensors, strides 1 or 2.  HN_WGRAD_TC=0/1 overrides the default.
+#ifndef HN_WGRAD_TC_DEFAULT
+#define HN_WGRAD_TC_DEFAULT 0
+#endif
+bool wgrad_tc_on();
+bool conv_wgrad_tc_supported(const ConvDesc& d, const Act& in, const Act& dz);
+int conv_wgrad_tc(const ConvDesc& d, const Act& in, const unsigned short* in_planes, const Act& dz,
+                  const unsigned short* dz_planes, const float* dz_absmax, float* dw_ohwi, cudaStream_t st);
 int ohwi_to_oihw(const float* in, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t st);
 // flipped / transposed weights in conv_f32's [K][N] packing, for conv_dgrad_f32
 int pack_dgrad_weight(const float* w_oihw, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t st);

@@ -44,6 +44,17 @@ __device__ __forceinline__ void split2_scaled(float s0, float s1, uint32_t& hi2,
     lo2 = pack_half2_sat(s0 - b.x, s1 - b.y);
 }
 
+// Gradient tensors are split after a multiplication by this power of two (largest magnitude -> [2^11, 2^12)), see
+// split_planes_pow2 in bwd_kernels.cuh; consumers divide it out again (exact).
+__device__ __forceinline__ float pow2_factor(float absmax) {
+    if (!(absmax > 0.f) || isinf(absmax)) return 1.f;
+    int e;
+    frexpf(absmax, &e);                      // absmax = m * 2^e, m in [0.5, 1)
+    e = 12 - e;
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    return ldexpf(1.f, e);
+}
+
 bool conv_tc_supported(const ConvDesc& d, const Act& in, const Act& out);
 // fp32 halo-NHWC in/out convenience wrapper (unit tests): splits, runs the plane kernel, merges.
 int conv_tc(const ConvDesc& d, const Act& in, const Act& out, const float* residual, cudaStream_t st);

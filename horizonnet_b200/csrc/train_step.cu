@@ -7,8 +7,9 @@
 // Every convolution output z (pre-BN) and every activation y is kept in fp32 on a tape; one gradient buffer mirrors
 // every y.  With the model option tensor_cores (default) the forward convolutions and their data gradients run on the
 // tcgen05 conv kernel (conv_tc.cu: fp16 hi/lo operand planes, fp32 result; a data gradient is the same kernel on the
-// zero-dilated dz with flipped weights); weight gradients, BatchNorm, LSTM BPTT and the rest are fp32 CUDA-core kernels
-// (bwd_kernels.cu).  tensor_cores = 0: conv_f32.cu everywhere.  Not built: a tcgen05 weight-gradient kernel, loss
+// zero-dilated dz with flipped weights); the weight gradients of the convolutions with Cin, Cout multiples of 64 can run
+// on the tcgen05 weight-gradient kernel (wgrad_tc.cu, HN_WGRAD_TC); the other weight gradients, BatchNorm, LSTM BPTT and
+// the rest are fp32 CUDA-core kernels (bwd_kernels.cu).  tensor_cores = 0: conv_f32.cu everywhere.  Not built: loss
 // scaling, gradient all-reduce overlapped with the backward.
 #include <cstring>
 #include <memory>
@@ -50,7 +51,7 @@ struct TrainState {
     float *dz_scratch = nullptr, *dil_scratch = nullptr, *wd_scratch = nullptr, *dw_scratch = nullptr;
     // tensor-core variant of the step (hn_model option tensor_cores): fp16 hi/lo planes of every activation (same
     // offsets as yarena), of the current dz / dilated dz, an fp32 landing buffer for data gradients, epilogue constants
-    float *parena = nullptr, *pl_scratch = nullptr, *dtmp = nullptr, *aux_tmp = nullptr;
+    float *parena = nullptr, *pl_scratch = nullptr, *pl2_scratch = nullptr, *dtmp = nullptr, *aux_tmp = nullptr;
     size_t din_max = 0;
     float *ones = nullptr, *zeros = nullptr;
     double* sums = nullptr;
@@ -251,7 +252,8 @@ int ensure_buffers(hn_model* m, TrainState* ts, int B, const TrainCtx& tr) {
         ts->alloc_t(&ts->wd_scratch, ts->w_max) || ts->alloc_t(&ts->dw_scratch, ts->w_max))
         return -1;
     if (ts->alloc_t(&ts->parena, ts->ysize) || ts->alloc_t(&ts->pl_scratch, std::max(ts->dz_max, ts->dil_max)) ||
-        ts->alloc_t(&ts->dtmp, ts->din_max) || ts->alloc_t(&ts->aux_tmp, 3 * 4096 + 2))
+        ts->alloc_t(&ts->pl2_scratch, ts->dz_max) || ts->alloc_t(&ts->dtmp, ts->din_max) ||
+        ts->alloc_t(&ts->aux_tmp, 3 * 4096 + 3))
         return -1;
     if (ts->alloc_t(&ts->ones, 4096) || ts->alloc_t(&ts->zeros, 4096) || ts->alloc_t(&ts->sums, 2 * 4096)) return -1;
     if (fill_f32(ts->ones, 4096, 1.f, 0) || fill_f32(ts->zeros, 4096, 0.f, 0)) return -1;
@@ -359,7 +361,19 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
         if (bn_bwd(grad_of(ts, u.y), u.y, u.z, u.bn, u.train, u.relu, ts->sums, dz, dres, GRAD(c.bnprefix + ".weight"),
                    GRAD(c.bnprefix + ".bias"), c.biaskey.empty() ? nullptr : GRAD(c.biaskey), st))
             return -1;
-        if (conv_wgrad_f32(u.d, u.in, dz, ts->dw_scratch, st)) return -1;
+        // planes of dz (gradients are tiny: power-of-two scaling around the split, see split_planes_pow2); a stride-1 unit
+        // shares them between its weight gradient and its data gradient
+        unsigned short* sp = reinterpret_cast<unsigned short*>(ts->pl_scratch);
+        float* amax = ts->aux_tmp + 3 * 4096 + 1;
+        const bool strided = u.d.sh != 1 || u.d.sw != 1;
+        bool sp_is_dz = false;
+        if (m->use_tc && !u.is_stem && wgrad_tc_on() && conv_wgrad_tc_supported(u.d, u.in, dz)) {
+            unsigned short* zp = strided ? reinterpret_cast<unsigned short*>(ts->pl2_scratch) : sp;
+            float* zmax = strided ? amax + 1 : amax;
+            if (split_planes_pow2(dz.p, zp, dz.numel(), zmax, st)) return -1;
+            if (conv_wgrad_tc(u.d, u.in, planes_of(ts, u.in), dz, zp, zmax, ts->dw_scratch, st)) return -1;
+            sp_is_dz = !strided;
+        } else if (conv_wgrad_f32(u.d, u.in, dz, ts->dw_scratch, st)) return -1;
         if (ohwi_to_oihw(ts->dw_scratch, GRAD(c.wkey), u.d.Cout, u.d.Cin, u.d.kh, u.d.kw, st)) return -1;
         if (u.is_stem) continue;                                   // the image needs no gradient
         const Act din = grad_of(ts, u.in);
@@ -367,15 +381,13 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
         t.Cin = u.d.Cout; t.Cout = u.d.Cin; t.kh = u.d.kh; t.kw = u.d.kw;
         t.ph = u.d.kh - 1 - u.d.ph; t.pw = u.d.kw - 1 - u.d.pw; t.shift = ts->zeros;
         Act src = dz;
-        if (u.d.sh != 1 || u.d.sw != 1) { src = din; src.C = u.d.Cout; src.p = ts->dil_scratch; }
+        if (strided) { src = din; src.C = u.d.Cout; src.p = ts->dil_scratch; }
         Act landing = din; landing.p = ts->dtmp;
         if (m->use_tc && conv_tc_supported(t, src, landing)) {
             // tcgen05: planes of the (dilated) dz, flipped weights packed as planes, fp32 result added to the gradient
-            if ((u.d.sh != 1 || u.d.sw != 1) && dilate_for_dgrad(dz, src, u.d.sh, u.d.sw, st)) return -1;
-            unsigned short* sp = reinterpret_cast<unsigned short*>(ts->pl_scratch);
+            if (strided && dilate_for_dgrad(dz, src, u.d.sh, u.d.sw, st)) return -1;
             unsigned short* wq = reinterpret_cast<unsigned short*>(ts->wd_scratch);
-            float* amax = ts->aux_tmp + 3 * 4096 + 1;            // gradients are tiny: power-of-two scaling around the planes
-            if (split_planes_pow2(src.p, sp, src.numel(), amax, st)) return -1;
+            if (!sp_is_dz && split_planes_pow2(src.p, sp, src.numel(), amax, st)) return -1;
             if (flip_oihw(m->T(c.wkey), ts->dw_scratch, u.d.Cout, u.d.Cin, u.d.kh, u.d.kw, st)) return -1;
             if (pack_weight_tc(ts->dw_scratch, wq, nullptr, nullptr, ts->aux_tmp, ts->aux_tmp + 3 * t.Cout, t.Cout, t.Cin, t.kh,
                                t.kw, st))
@@ -508,6 +520,34 @@ int hn_conv2d_backward(const float* in, int B, int H, int W, int Cin, int in_hal
         cudaFreeAsync(ones, st); cudaFreeAsync(dil, st);
     }
     cudaFreeAsync(tmp, st);
+    return rc;
+}
+
+// 1 when the training step routes the weight gradients the tcgen05 kernel supports through it (HN_WGRAD_TC or the built-in default)
+int hn_wgrad_tc_enabled(void) { return wgrad_tc_on() ? 1 : 0; }
+
+// Weight gradient on the tcgen05 kernel (wgrad_tc.cu) from fp32 halo-1 NHWC tensors: splits both operands into planes
+// (the training step has them already), runs conv_wgrad_tc, returns dW in OIHW.  Fails for shapes the kernel does not take.
+int hn_conv2d_wgrad_tc(const float* in, int B, int H, int W, int Cin, const float* dz, int Cout, int kh, int kw, int sh,
+                       int sw, int ph, int pw, float* dw_oihw, void* stream) {
+    HN_CHECK(in && dz && dw_oihw, "hn_conv2d_wgrad_tc: NULL argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    ConvDesc d;
+    d.Cin = Cin; d.Cout = Cout; d.kh = kh; d.kw = kw; d.sh = sh; d.sw = sw; d.ph = ph; d.pw = pw;
+    Act a = mk(const_cast<float*>(in), B, H, W, Cin, 1);
+    const int Ho = (H + 2 * ph - kh) / sh + 1, Wo = (W + 2 * pw - kw) / sw + 1;
+    Act z = mk(const_cast<float*>(dz), B, Ho, Wo, Cout, 1);
+    HN_CHECK(conv_wgrad_tc_supported(d, a, z), "hn_conv2d_wgrad_tc: shape not supported by the tcgen05 weight-gradient kernel");
+    const size_t nw = (size_t)Cout * Cin * kh * kw;
+    float *tmp = nullptr, *amax = nullptr;
+    unsigned short *ap = nullptr, *zp = nullptr;
+    HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&tmp), nw * sizeof(float), st));
+    HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&amax), sizeof(float), st));
+    HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&ap), a.numel() * 2 * sizeof(unsigned short), st));
+    HN_CUDA_OK(cudaMallocAsync(reinterpret_cast<void**>(&zp), z.numel() * 2 * sizeof(unsigned short), st));
+    int rc = split_planes(a.p, ap, a.numel(), st) || split_planes_pow2(z.p, zp, z.numel(), amax, st) ||
+             conv_wgrad_tc(d, a, ap, z, zp, amax, tmp, st) || ohwi_to_oihw(tmp, dw_oihw, Cout, Cin, kh, kw, st);
+    cudaFreeAsync(tmp, st); cudaFreeAsync(amax, st); cudaFreeAsync(ap, st); cudaFreeAsync(zp, st);
     return rc;
 }
 

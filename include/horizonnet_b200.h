@@ -225,6 +225,11 @@ int hn_conv2d(const float* in_dev, int B, int H, int W, int Cin, int in_halo,
  * BatchNorm2d (+identity, ReLU) forward+backward, and one bidirectional LSTM layer's gate gradients. */
 int hn_conv2d_backward(const float* in, int B, int H, int W, int Cin, int in_halo, const float* w_oihw, const float* dz,
                        int Cout, int kh, int kw, int sh, int sw, int ph, int pw, float* din, float* dw_oihw, void* stream);
+/* The weight gradient alone on the tcgen05 kernel (wgrad_tc.cu; in / dz: halo-1 NHWC fp32, Cin and Cout multiples of 64,
+ * strides 1 or 2): the planes are made inside.  Returns -1 for a shape that kernel does not take. */
+int hn_conv2d_wgrad_tc(const float* in, int B, int H, int W, int Cin, const float* dz, int Cout, int kh, int kw, int sh,
+                       int sw, int ph, int pw, float* dw_oihw, void* stream);
+int hn_wgrad_tc_enabled(void);   /* 1: the training step uses that kernel where it applies (env HN_WGRAD_TC=0/1 overrides the default) */
 int hn_bn_forward_backward(const float* z, int B, int H, int W, int C, const float* gamma, const float* beta,
                            float* running_mean, float* running_var, double factor, int train, int relu, const float* res,
                            float* y, const float* dy, float* dz, float* dres, float* dgamma, float* dbeta, float* bn_scratch,

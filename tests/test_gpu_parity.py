@@ -662,6 +662,100 @@ def test_conv_backward_vs_autograd(case):
         assert (got - xd.grad).abs().max().item() <= 2e-5 * xd.grad.abs().max().item()
 
 
+WGRAD_TC_CASES = [
+    # B, Cin, H, W, Cout, k, stride        (Cin, Cout multiples of 64; the tile shapes of the real units)
+    (2, 64, 8, 256, 64, 3, (1, 1)),        # layer1 conv2: one 64-channel atom on both sides, half rows (W = 256 -> 4 tiles per row)
+    (2, 256, 8, 256, 64, 1, (1, 1)),       # layer1 conv1: two Cin tiles
+    (2, 64, 8, 256, 256, 1, (1, 1)),       # layer1 conv3 / downsample: two Cout tiles
+    (2, 128, 8, 128, 128, 3, (2, 2)),      # layer2.0 conv2: stride 2 both ways (parity view + row traversal stride)
+    (2, 256, 8, 128, 512, 1, (2, 2)),      # layer2.0 downsample
+    (2, 256, 16, 256, 128, 3, (2, 1)),     # ghc_lst.0.layer.0: stride (2, 1), W = 256
+    (2, 128, 4, 64, 128, 3, (1, 1)),       # layer3-like: W = 64, one row per tile
+    (2, 192, 8, 32, 192, 3, (1, 1)),       # W = 32: two rows per tile; second channel tile has one atom on both sides
+    (3, 512, 2, 32, 256, 3, (2, 1)),       # ghc_lst.3.layer.3: H 2 -> 1, two images per tile, ragged last tile (B = 3)
+    (5, 64, 2, 16, 128, 3, (2, 1)),        # W = 16: four images per tile, B = 5
+    (2, 1024, 4, 32, 512, 3, (2, 1)),      # ghc_lst.3.layer.2: 8 x 4 channel tiles, 9 taps
+    (4, 128, 32, 64, 128, 3, (1, 1)),      # 8192 pixels = 128 tiles: more than one pixel slice per work item
+]
+
+
+def _record(name, payload):
+    """Measured errors of the new kernels, kept next to the gpurun logs when that directory exists."""
+    import json
+    d = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    if os.path.isdir(d):
+        with open(os.path.join(d, name), 'a') as f:
+            f.write(json.dumps(payload) + '\n')
+
+
+@pytest.mark.parametrize('case', WGRAD_TC_CASES)
+def test_conv_wgrad_tc_vs_autograd(case):
+    """Weight gradient on the tcgen05 kernel (wgrad_tc.cu: pixel-axis GEMM over MN-major plane tiles) against
+    torch.autograd in fp64, and against the fp32 CUDA-core kernel on the same inputs."""
+    B, Ci, H, W, Co, k, stride = case
+    g = torch.Generator().manual_seed(hash(case) % (2 ** 31))
+    x = torch.randn(B, Ci, H, W, generator=g)
+    p = k // 2
+    wd = (torch.randn(Co, Ci, k, k, generator=g, dtype=torch.float64) / (Ci * k * k) ** 0.5).requires_grad_()
+    xd = x.double()
+    xp = torch.cat([xd[..., -p:], xd, xd[..., :p]], dim=3) if p else xd
+    y = torch.nn.functional.conv2d(xp, wd, None, stride=stride, padding=(p, 0))
+    dz = torch.randn(y.shape, generator=g) * 1e-4          # gradients are small: the planes carry a power-of-two scale
+    y.backward(dz.double())
+    lib = _lib.lib()
+    xin = gu.to_halo_nhwc(x, 1).to(DEV)
+    dzin = gu.to_halo_nhwc(dz, 1).to(DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    dw = torch.full((Co, Ci, k, k), float('nan'), device=DEV)
+    _lib.check(lib.hn_conv2d_wgrad_tc(xin.data_ptr(), B, H, W, Ci, dzin.data_ptr(), Co, k, k, stride[0], stride[1], p, p,
+                                      dw.data_ptr(), st), 'hn_conv2d_wgrad_tc')
+    dw32 = torch.full_like(dw, float('nan'))
+    wdev = wd.detach().float().to(DEV)
+    _lib.check(lib.hn_conv2d_backward(xin.data_ptr(), B, H, W, Ci, 1, wdev.data_ptr(), dzin.data_ptr(), Co, k, k,
+                                      stride[0], stride[1], p, p, None, dw32.data_ptr(), st), 'hn_conv2d_backward')
+    torch.cuda.synchronize()
+    ref = wd.grad
+    scale = ref.abs().max().item()
+    err = (dw.cpu().double() - ref).abs().max().item() / scale
+    err32 = (dw32.cpu().double() - ref).abs().max().item() / scale
+    _record('wgrad_tc_errors.jsonl', {'case': list(case[:6]) + list(stride), 'err_tc': err, 'err_fp32': err32})
+    assert err <= 2e-5, (err, err32)
+
+
+def test_conv_wgrad_tc_rejects_shapes_it_does_not_take():
+    lib = _lib.lib()
+    x = torch.zeros(1, 8, 18, 48, device=DEV)
+    dz = torch.zeros(1, 8, 18, 64, device=DEV)
+    dw = torch.zeros(64, 48, 3, 3, device=DEV)
+    assert lib.hn_conv2d_wgrad_tc(x.data_ptr(), 1, 8, 16, 48, dz.data_ptr(), 64, 3, 3, 1, 1, 1, 1, dw.data_ptr(), None) != 0
+    assert b'not supported' in _lib.lib().hn_last_error()
+
+
+def test_training_step_weight_gradients_tcgen05_vs_fp32_kernels(monkeypatch):
+    """The whole backward of one batch-2 step with the weight gradients on the tcgen05 kernel (HN_WGRAD_TC=1) against the
+    same step with the fp32 CUDA-core weight-gradient kernel (=0): same tape, same dz, so every parameter gradient
+    agrees to rounding."""
+    import torch.nn.functional as F
+    sd = synthetic_state_dict(5, 'random')
+    x = synthetic_panoramas(2, seed=53).to(DEV)
+    y_bon, y_cor = torch.zeros(2, 2, 1024, device=DEV), torch.full((2, 1, 1024), 0.5, device=DEV)
+    grads = {}
+    for mode in ('0', '1'):
+        monkeypatch.setenv('HN_WGRAD_TC', mode)
+        assert _lib.lib().hn_wgrad_tc_enabled() == int(mode)
+        net = _train_net(sd, True)
+        torch.manual_seed(3)
+        bon, cor = net(x)
+        (F.l1_loss(bon, y_bon) + F.binary_cross_entropy_with_logits(cor, y_cor)).backward()
+        net.check()
+        grads[mode] = {k: p.grad.clone() for k, p in net.named_parameters()}
+    gmax = max(float(v.abs().max()) for v in grads['0'].values())
+    worst = sorted(((float((grads['1'][k] - v).abs().max()) / (float(v.abs().max()) + 1e-4 * gmax), k)
+                    for k, v in grads['0'].items()), reverse=True)
+    _record('wgrad_tc_errors.jsonl', {'whole_step_worst': worst[:5]})
+    assert worst[0][0] < 1e-4, worst[:8]
+
+
 @pytest.mark.parametrize('train,relu,res', [(1, 1, True), (1, 0, False), (0, 1, True), (1, 1, False)])
 def test_batchnorm_forward_backward_vs_autograd(train, relu, res):
     B, C, H, W = 3, 32, 5, 8
@@ -750,10 +844,10 @@ def test_lstm_layer_backward_vs_autograd(T, B):
         assert (dg[d].cpu().double() - ref).abs().max().item() <= 5e-5 * ref.abs().max().item(), d
 
 
-@pytest.mark.parametrize('tensor_cores', [True, False])
-def test_training_step_gradients_match_autograd_of_the_oracle(tensor_cores):
+@pytest.mark.parametrize('tensor_cores,wgrad_tc', [(True, '1'), (True, '0'), (False, '0')])
+def test_training_step_gradients_match_autograd_of_the_oracle(tensor_cores, wgrad_tc, monkeypatch):
     """tensor_cores: forward convolutions and data gradients on the tcgen05 kernel (default) / everything on the fp32
-    CUDA-core kernels.  BASELINE config 5 (train.py:44-58 + :278) at batch 2: net.train(); loss = L1(bon) + BCE-with-logits(cor);
+    CUDA-core kernels; wgrad_tc: weight gradients on the tcgen05 kernel where it applies (HN_WGRAD_TC).  BASELINE config 5 (train.py:44-58 + :278) at batch 2: net.train(); loss = L1(bon) + BCE-with-logits(cor);
     loss.backward() through the library against torch.autograd through the CPU oracle with the same dropout masks,
     for every one of the reference's parameters."""
     import torch.nn.functional as F
@@ -762,6 +856,7 @@ def test_training_step_gradients_match_autograd_of_the_oracle(tensor_cores):
     gen = torch.Generator().manual_seed(9)
     y_bon = torch.rand(2, 2, 1024, generator=gen) - 0.5
     y_cor = torch.rand(2, 1, 1024, generator=gen)
+    monkeypatch.setenv('HN_WGRAD_TC', wgrad_tc)
     net = _train_net(sd, tensor_cores)
     torch.manual_seed(11)
     bon, cor = net(x.to(DEV))
