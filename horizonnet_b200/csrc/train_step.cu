@@ -319,16 +319,31 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
         if (lstm_bwd_steps(dout, ts->gates, ts->cell, ts->whh_t, ts->whh_t + (size_t)512 * 2048, ts->dgates, ts->dc, T_STEPS, B,
                            ts->barrier, m->error_flag, st))
             return -1;
+        // weight gradients = 1x1 "convolutions" over the T*B rows: dW_ih = dG^T X, dW_hh = dG^T H_prev
+        const Act xa = mk(const_cast<float*>(X), 1, 1, (int)rows, 1024, 0);
+        ConvDesc wi; wi.Cin = 1024; wi.Cout = 2048;
+        ConvDesc wh; wh.Cin = 512; wh.Cout = 2048;
+        const bool lstm_wg_tc = m->use_tc && wgrad_tc_on() &&
+                                conv_wgrad_tc_supported(wi, xa, mk(ts->dgates, 1, 1, (int)rows, 2048, 0)) &&
+                                conv_wgrad_tc_supported(wh, mk(ts->hprev, 1, 1, (int)rows, 512, 0), mk(ts->dgates, 1, 1, (int)rows, 2048, 0));
+        // tcgen05 kernel: planes of X, of this direction's H_prev and dG in the plane scratch (3584 floats' worth per row)
+        unsigned short* xpl = reinterpret_cast<unsigned short*>(ts->pl_scratch);
+        unsigned short* hpl = reinterpret_cast<unsigned short*>(ts->pl_scratch + rows * 1024);
+        unsigned short* gpl = reinterpret_cast<unsigned short*>(ts->pl_scratch + rows * 1536);
+        float* gmax = ts->aux_tmp + 3 * 4096 + 1;
+        if (lstm_wg_tc && split_planes(X, xpl, rows * 1024, st)) return -1;
         for (int dir = 0; dir < 2; ++dir) {
             const std::string sfx = l + (dir ? "_reverse" : "");
             Act dg = mk(ts->dgates + dir * rows * 2048, 1, 1, (int)rows, 2048, 0);
-            ConvDesc wi; wi.Cin = 1024; wi.Cout = 2048;
-            if (conv_wgrad_f32(wi, mk(const_cast<float*>(X), 1, 1, (int)rows, 1024, 0), dg, GRAD("bi_rnn.weight_ih" + sfx), st))
-                return -1;
-            ConvDesc wh; wh.Cin = 512; wh.Cout = 2048;
-            if (conv_wgrad_f32(wh, mk(ts->hprev + dir * rows * 512, 1, 1, (int)rows, 512, 0), dg,
-                               GRAD("bi_rnn.weight_hh" + sfx), st))
-                return -1;
+            const Act ha = mk(ts->hprev + dir * rows * 512, 1, 1, (int)rows, 512, 0);
+            if (lstm_wg_tc) {
+                if (split_planes(ha.p, hpl, rows * 512, st) || split_planes_pow2(dg.p, gpl, rows * 2048, gmax, st)) return -1;
+                if (conv_wgrad_tc(wi, xa, xpl, dg, gpl, gmax, GRAD("bi_rnn.weight_ih" + sfx), st)) return -1;
+                if (conv_wgrad_tc(wh, ha, hpl, dg, gpl, gmax, GRAD("bi_rnn.weight_hh" + sfx), st)) return -1;
+            } else {
+                if (conv_wgrad_f32(wi, xa, dg, GRAD("bi_rnn.weight_ih" + sfx), st)) return -1;
+                if (conv_wgrad_f32(wh, ha, dg, GRAD("bi_rnn.weight_hh" + sfx), st)) return -1;
+            }
             float* bi = GRAD("bi_rnn.bias_ih" + sfx);
             if (col_sum(dg.p, rows, 2048, bi, st)) return -1;
             HN_CUDA_OK(cudaMemcpyAsync(GRAD("bi_rnn.bias_hh" + sfx), bi, 2048 * sizeof(float), cudaMemcpyDeviceToDevice, st));

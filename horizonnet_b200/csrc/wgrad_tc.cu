@@ -56,15 +56,16 @@ struct WgArgs {
     int out_halo;
     int sh, ph, woff, parity; // woff = in_halo - pw; parity = 1: stride 2 along W through the [Wp/2][2] view
     int num_kt, kt_per_slice, items_per_slice;
+    uint32_t lbo, sbo;        // operand descriptor offsets: ATOM between 64-channel atoms, 1024 between 8-pixel groups
 };
 
 // MN-major, 128-byte swizzle shared-memory operand descriptor: rows of 128 B (64 channels of one pixel), 8-pixel
 // groups 1024 B apart (stride byte offset), 64-channel atoms ATOM bytes apart (leading byte offset)
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);          // start address        bits [0,14)
-    d |= (uint64_t)(ATOM >> 4) << 16;                     // leading byte offset  bits [16,30)
-    d |= (uint64_t)(1024 >> 4) << 32;                     // stride byte offset   bits [32,46)
+    d |= (uint64_t)(lbo >> 4) << 16;                      // leading byte offset  bits [16,30)
+    d |= (uint64_t)(sbo >> 4) << 32;                      // stride byte offset   bits [32,46)
     d |= (uint64_t)1 << 46;                               // descriptor version 1 (sm_100)
     d |= (uint64_t)2 << 61;                               // layout type: SWIZZLE_128B
     return d;
@@ -171,8 +172,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmZh, const __grid_constant_
                 tc_fence_after();
                 const uint32_t sZ = smem_u32(smem + stage * STAGE);
                 const uint32_t sI = sZ + 2 * PLANE;
-                const uint64_t z_hi = umma_desc_mn_sw128(sZ), z_lo = umma_desc_mn_sw128(sZ + PLANE);
-                const uint64_t i_hi = umma_desc_mn_sw128(sI), i_lo = umma_desc_mn_sw128(sI + PLANE);
+                const uint64_t z_hi = umma_desc_mn_sw128(sZ, a.lbo, a.sbo), z_lo = umma_desc_mn_sw128(sZ + PLANE, a.lbo, a.sbo);
+                const uint64_t i_hi = umma_desc_mn_sw128(sI, a.lbo, a.sbo), i_lo = umma_desc_mn_sw128(sI + PLANE, a.lbo, a.sbo);
 #pragma unroll
                 for (int k = 0; k < KT / 16; ++k) {
                     const uint64_t ko = (uint64_t)((k * 16 * 128) >> 4);     // 16 pixel rows of 128 B further on
@@ -253,7 +254,7 @@ bool wgrad_tc_on() {
 
 bool conv_wgrad_tc_supported(const ConvDesc& d, const Act& in, const Act& dz) {
     if (d.Cin % 64 != 0 || d.Cout % 64 != 0) return false;
-    if (in.halo != 1 || dz.halo != 1 || d.pw > in.halo) return false;
+    if (d.pw > in.halo || in.halo > 1 || dz.halo > 1) return false;
     if (in.C != d.Cin || dz.C != d.Cout || in.B != dz.B) return false;
     if (d.sh != 1 && d.sh != 2) return false;
     if (d.sw != 1 && d.sw != 2) return false;
@@ -279,6 +280,15 @@ int conv_wgrad_tc(const ConvDesc& d, const Act& in, const unsigned short* in_pla
     a.tw = g.tw; a.rpt = g.rpt; a.wsegs = g.wsegs; a.Ho = dz.H; a.out_halo = dz.halo;
     a.sh = d.sh; a.ph = d.ph; a.woff = in.halo - d.pw; a.parity = (d.sw == 2);
     a.num_kt = (int)g.num_kt;
+    // Descriptor convention for MN-major 128B-swizzle operands as CUTLASS documents it (cute/atom/mma_traits_sm100.hpp,
+    // make_umma_desc<Major::MN>): leading byte offset = stride between 64-element atoms along M/N, stride byte offset =
+    // stride between 8-row groups along K.  HN_WGRAD_TC_DESC=1 swaps the two (bring-up switch).
+    {
+        const char* e = getenv("HN_WGRAD_TC_DESC");
+        const bool swapped = e && atoi(e) == 1;
+        a.lbo = swapped ? 1024u : (uint32_t)ATOM;
+        a.sbo = swapped ? (uint32_t)ATOM : 1024u;
+    }
     HN_CUDA_OK(cudaMemsetAsync(dw_ohwi, 0, (size_t)d.Cout * a.taps * d.Cin * sizeof(float), st));
 
     // pixel slices: at most 64 tiles (4096 pixels, 256 accumulation steps) and at least 8 tiles per CTA; among those the

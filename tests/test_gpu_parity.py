@@ -718,7 +718,8 @@ def test_conv_wgrad_tc_vs_autograd(case):
     scale = ref.abs().max().item()
     err = (dw.cpu().double() - ref).abs().max().item() / scale
     err32 = (dw32.cpu().double() - ref).abs().max().item() / scale
-    _record('wgrad_tc_errors.jsonl', {'case': list(case[:6]) + list(stride), 'err_tc': err, 'err_fp32': err32})
+    _record('wgrad_tc_errors.jsonl', {'case': list(case[:6]) + list(stride), 'err_tc': err, 'err_fp32': err32,
+                                      'desc': os.environ.get('HN_WGRAD_TC_DESC', '0')})
     assert err <= 2e-5, (err, err32)
 
 
