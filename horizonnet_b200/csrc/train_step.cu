@@ -11,6 +11,7 @@
 // on the tcgen05 weight-gradient kernel (wgrad_tc.cu, HN_WGRAD_TC); the other weight gradients, BatchNorm, LSTM BPTT and
 // the rest are fp32 CUDA-core kernels (bwd_kernels.cu).  tensor_cores = 0: conv_f32.cu everywhere.  Not built: loss
 // scaling, gradient all-reduce overlapped with the backward.
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -64,10 +65,11 @@ struct TrainState {
     Act stem_y, pool_y, gout[4];
     TrainCtx ctx{};
     std::vector<float*> grads;           // per TensorSlot
-    // phase boundaries of the last backward: start, head, lstm, tail, conv units (bn / wgrad / dgrad are summed on the host
-    // from per-unit events only when HN_TRAIN_PROF=1), end
+    // phase boundaries of the last backward: start, head, lstm, tail, conv units, end
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     bool timed = false;
+    std::vector<cudaEvent_t> uev;        // HN_TRAIN_PROF=1: 4 events per conv unit (start, BN backward, weight gradient, data gradient)
+    bool units_timed = false;
     std::vector<void*> owned;            // batch-sized buffers (freed and laid out again when a larger batch arrives)
     template <typename T>
     int alloc_t(T** p, size_t n) {
@@ -83,6 +85,7 @@ struct TrainState {
     ~TrainState() {
         release();
         for (auto e : ev) if (e) cudaEventDestroy(e);
+        for (auto e : uev) if (e) cudaEventDestroy(e);
     }
 };
 
@@ -366,9 +369,18 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
     HN_CUDA_OK(cudaEventRecord(ts->ev[3], st));
 
     // ---- conv units in reverse
+    const bool prof = [] { const char* e = getenv("HN_TRAIN_PROF"); return e && atoi(e) != 0; }();
+    if (prof && ts->uev.size() != 4 * ts->units.size()) {
+        for (auto e : ts->uev) cudaEventDestroy(e);
+        ts->uev.assign(4 * ts->units.size(), nullptr);
+        for (auto& e : ts->uev) HN_CUDA_OK(cudaEventCreate(&e));
+    }
+    ts->units_timed = prof;
+#define MARK(k) do { if (prof) HN_CUDA_OK(cudaEventRecord(ts->uev[4 * ui + (k)], st)); } while (0)
     for (size_t ui = ts->units.size(); ui-- > 0;) {
         const Unit& u = ts->units[ui];
         const ConvLayer& c = *u.c;
+        MARK(0);
         if (u.is_stem && maxpool_bwd(ts->stem_y, grad_of(ts, ts->pool_y), grad_of(ts, ts->stem_y).p, st)) return -1;
         Act dz = u.z; dz.p = ts->dz_scratch;
         float* dres = nullptr;
@@ -376,6 +388,7 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
         if (bn_bwd(grad_of(ts, u.y), u.y, u.z, u.bn, u.train, u.relu, ts->sums, dz, dres, GRAD(c.bnprefix + ".weight"),
                    GRAD(c.bnprefix + ".bias"), c.biaskey.empty() ? nullptr : GRAD(c.biaskey), st))
             return -1;
+        MARK(1);
         // planes of dz (gradients are tiny: power-of-two scaling around the split, see split_planes_pow2); a stride-1 unit
         // shares them between its weight gradient and its data gradient
         unsigned short* sp = reinterpret_cast<unsigned short*>(ts->pl_scratch);
@@ -390,7 +403,8 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
             sp_is_dz = !strided;
         } else if (conv_wgrad_f32(u.d, u.in, dz, ts->dw_scratch, st)) return -1;
         if (ohwi_to_oihw(ts->dw_scratch, GRAD(c.wkey), u.d.Cout, u.d.Cin, u.d.kh, u.d.kw, st)) return -1;
-        if (u.is_stem) continue;                                   // the image needs no gradient
+        MARK(2);
+        if (u.is_stem) { MARK(3); continue; }                      // the image needs no gradient
         const Act din = grad_of(ts, u.in);
         ConvDesc t;                                               // the transposed convolution as a stride-1 conv
         t.Cin = u.d.Cout; t.Cout = u.d.Cin; t.kh = u.d.kh; t.kw = u.d.kw;
@@ -414,7 +428,9 @@ int walk_backward(hn_model* m, TrainState* ts, const float* dbon, const float* d
             if (pack_dgrad_weight(m->T(c.wkey), ts->wd_scratch, u.d.Cout, u.d.Cin, u.d.kh, u.d.kw, st)) return -1;
             if (conv_dgrad_f32(u.d, ts->wd_scratch, dz, din, true, ts->dil_scratch, ts->ones, ts->zeros, st)) return -1;
         }
+        MARK(3);
     }
+#undef MARK
 #undef GRAD
     HN_CUDA_OK(cudaEventRecord(ts->ev[4], st));
     ts->timed = true;
@@ -490,6 +506,26 @@ int hn_train_profile(hn_model* m, double ms[4]) {
         HN_CUDA_OK(cudaEventElapsedTime(&t, ts->ev[i], ts->ev[i + 1]));
         ms[i] = t;
     }
+    return 0;
+}
+
+// With HN_TRAIN_PROF=1 set during the last hn_train_backward: the conv-unit phase split into ms[0] BatchNorm backward,
+// ms[1] weight gradients (incl. the dz plane split of the tcgen05 kernel and the OHWI -> OIHW pass), ms[2] data gradients,
+// summed over the units.  Returns -1 when that backward was not profiled.
+int hn_train_profile_units(hn_model* m, double ms[3]) {
+    HN_CHECK(m && ms, "hn_train_profile_units: NULL argument");
+    TrainState* ts = state_of(m);
+    HN_CHECK(ts->timed && ts->units_timed && ts->uev.size() == 4 * ts->units.size(),
+             "hn_train_profile_units: the last backward ran without HN_TRAIN_PROF=1");
+    HN_ON_DEVICE(m->device);
+    HN_CUDA_OK(cudaEventSynchronize(ts->ev[4]));
+    ms[0] = ms[1] = ms[2] = 0.0;
+    for (size_t ui = 0; ui < ts->units.size(); ++ui)
+        for (int k = 0; k < 3; ++k) {
+            float t = 0.f;
+            HN_CUDA_OK(cudaEventElapsedTime(&t, ts->uev[4 * ui + k], ts->uev[4 * ui + k + 1]));
+            ms[k] += t;
+        }
     return 0;
 }
 

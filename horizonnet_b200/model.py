@@ -16,6 +16,7 @@ their torch ``forward`` methods is ever called -- all arithmetic runs in the CUD
 is no CPU fallback: a CPU tensor or a missing library raises.
 """
 import ctypes
+import os
 import threading
 
 import numpy as np
@@ -349,7 +350,12 @@ class HorizonNet(nn.Module):
         key = next(iter(self._handles)) if device is None else device
         ms = (ctypes.c_double * 4)()
         _lib.check(_lib.lib().hn_train_profile(self._handles[key]['ptr'], ms), 'hn_train_profile')
-        return dict(zip(('head', 'lstm', 'sequence', 'conv_units'), [round(v, 3) for v in ms]))
+        out = dict(zip(('head', 'lstm', 'sequence', 'conv_units'), [round(v, 3) for v in ms]))
+        if os.environ.get('HN_TRAIN_PROF', '0') not in ('', '0'):      # per-unit events were recorded: split the conv units
+            us = (ctypes.c_double * 3)()
+            if _lib.lib().hn_train_profile_units(self._handles[key]['ptr'], us) == 0:
+                out.update(zip(('units_bn_backward', 'units_weight_gradient', 'units_data_gradient'), [round(v, 3) for v in us]))
+        return out
 
     def debug_train_unit(self, i, what=0, device=None):
         """Tape of the last training-step forward (test hook): conv unit i in graph order (stem, blocks, height

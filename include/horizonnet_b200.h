@@ -114,6 +114,9 @@ int hn_train_backward(hn_model* m, const float* dbon_dev, const float* dcor_dev,
 int hn_model_get_grad(hn_model* m, const char* key, float* out_dev, long long numel, void* stream);
 /* Device time (ms) of the phases of the last hn_train_backward: head, bi-LSTM BPTT, sequence adjoint, the 69 conv units. */
 int hn_train_profile(hn_model* m, double ms[4]);
+/* HN_TRAIN_PROF=1 during the last hn_train_backward: the conv-unit phase split into ms[0] BatchNorm backward, ms[1] weight
+ * gradients, ms[2] data gradients (device ms, summed over the units); -1 when that backward was not profiled. */
+int hn_train_profile_units(hn_model* m, double ms[3]);
 /* Tape inspection for tests: conv unit i of the last hn_train_forward (graph order: stem, blocks, height reduction);
  * what = 0 activation, 1 raw conv output, 2 gradient of the activation; halo-1 NHWC copy, dims = {B, H, W, C}. */
 int hn_train_debug_unit(hn_model* m, int i, int what, float* out_dev, long long capacity, int dims[4], char* name,
