@@ -347,54 +347,86 @@ __global__ void bn_apply_fwd_kernel(const float* __restrict__ z, const float* __
 }
 
 // sums[c] = sum g, sums[C+c] = sum g * xhat, g = dy * (relu ? y > 0 : 1), xhat = (z - mean) * invstd
+// Block = CL4 channel-quad lanes x (256 / CL4) pixel lanes, rows walked with 32-bit arithmetic, 16-byte loads (same
+// layout as bn_stats_kernel in train_fwd.cu; the sums stay fp64 per element).
 __global__ void __launch_bounds__(256)
 bn_bwd_reduce_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ z,
-                     const float* __restrict__ bn, int B, int H, int W, int C, int relu, int CL, double* __restrict__ sums) {
-    __shared__ double sh[2][256];
-    const int cl = threadIdx.x % CL, pl = threadIdx.x / CL, PL = 256 / CL;
-    const int c = blockIdx.x * CL + cl;
-    const size_t npix = (size_t)B * H * W;
-    double s1 = 0.0, s2 = 0.0;
-    if (c < C) {
-        const float mean = bn[2 * C + c], invstd = bn[3 * C + c];
-        for (size_t p = (size_t)blockIdx.y * PL + pl; p < npix; p += (size_t)gridDim.y * PL) {
-            const int w = (int)(p % W);
-            const size_t i = ((p / W) * (W + 2) + w + 1) * C + c;
-            float g = dy[i];
-            if (relu && !(y[i] > 0.f)) g = 0.f;
-            s1 += (double)g;
-            s2 += (double)g * (double)((z[i] - mean) * invstd);
+                     const float* __restrict__ bn, int rows, int W, int C, int relu, int CL4, double* __restrict__ sums) {
+    __shared__ double sh[256][8];
+    const int cl = threadIdx.x % CL4, pl = threadIdx.x / CL4, PL = 256 / CL4;
+    const int c4 = blockIdx.x * CL4 + cl;
+    const bool active = c4 * 4 < C;
+    double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (active) {
+        const float4 mean = __ldg(reinterpret_cast<const float4*>(bn + 2 * C) + c4);
+        const float4 invstd = __ldg(reinterpret_cast<const float4*>(bn + 3 * C) + c4);
+        const float mm[4] = {mean.x, mean.y, mean.z, mean.w}, iv[4] = {invstd.x, invstd.y, invstd.z, invstd.w};
+        for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+            const size_t base = ((size_t)row * (W + 2) + 1) * C + (size_t)c4 * 4;
+            for (int w = pl; w < W; w += PL) {
+                const size_t i = base + (size_t)w * C;
+                const float4 dv = *reinterpret_cast<const float4*>(dy + i);
+                const float4 zv = *reinterpret_cast<const float4*>(z + i);
+                float g[4] = {dv.x, dv.y, dv.z, dv.w};
+                const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
+                if (relu) {
+                    const float4 yv = *reinterpret_cast<const float4*>(y + i);
+                    const float yy[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) if (!(yy[j] > 0.f)) g[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    a[j] += (double)g[j];
+                    a[4 + j] += (double)g[j] * (double)((zz[j] - mm[j]) * iv[j]);
+                }
+            }
         }
     }
-    sh[0][threadIdx.x] = s1;
-    sh[1][threadIdx.x] = s2;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = a[j];
     __syncthreads();
-    if (pl == 0 && c < C) {
-        for (int j = 1; j < PL; ++j) { s1 += sh[0][j * CL + cl]; s2 += sh[1][j * CL + cl]; }
-        atomicAdd(sums + c, s1);
-        atomicAdd(sums + C + c, s2);
+    if (pl == 0 && active) {
+        for (int k = 1; k < PL; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] += sh[k * CL4 + cl][j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(sums + c4 * 4 + j, a[j]);
+            atomicAdd(sums + C + c4 * 4 + j, a[4 + j]);
+        }
     }
 }
 
+// Per channel, once: the two means the apply pass subtracts (as floats: mf[c] = s1/N, mf[C+c] = s2/N) and the
+// parameter gradients dgamma = s2, dbeta = s1, dbias = (frozen) scale * s1 | (train) 0.  (The first version divided
+// the fp64 sums in every thread of the apply pass: 8 double divisions per 4 outputs.)
+__global__ void bn_bwd_means_kernel(const double* __restrict__ sums, double count, const float* __restrict__ bn, int train,
+                                    float* __restrict__ mf, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                    float* __restrict__ dbias, int C) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    mf[c] = (float)(sums[c] / count);
+    mf[C + c] = (float)(sums[C + c] / count);
+    if (dgamma) dgamma[c] = (float)sums[C + c];
+    if (dbeta) dbeta[c] = (float)sums[c];
+    if (dbias) dbias[c] = train ? 0.f : (float)((double)bn[c] * sums[c]);
+}
+
 // dz = scale * (g - s1/N - xhat * s2/N)  (train)   |   scale * g  (frozen);  dres += g;  dz gets circular halo columns.
-// Parameter gradients (thread of pixel 0): dgamma = s2, dbeta = s1, dbias = sum dz.
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ y, const float* __restrict__ z,
-                                    const float* __restrict__ bn, const double* __restrict__ sums, double count, int train,
-                                    int relu, float* __restrict__ dz, float* __restrict__ dres, float* __restrict__ dgamma,
-                                    float* __restrict__ dbeta, float* __restrict__ dbias, int B, int H, int W, int C) {
-    const int C4 = C / 4;
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const size_t total = (size_t)B * H * W * C4;
+                                    const float* __restrict__ bn, const float* __restrict__ mf, int train, int relu,
+                                    float* __restrict__ dz, float* __restrict__ dres, unsigned total, int W, int C) {
+    const unsigned C4 = (unsigned)C / 4;
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
-    const int c4 = (int)(i % C4);
-    size_t t = i / C4;
-    const int w = (int)(t % W);
-    const size_t bh = t / W;
+    const unsigned c4 = i % C4;
+    const unsigned t = i / C4;
+    const unsigned w = t % (unsigned)W;
+    const size_t bh = t / (unsigned)W;
     const size_t o = (bh * (W + 2) + w + 1) * C + c4 * 4;
     const float4 dv = *reinterpret_cast<const float4*>(dy + o);
-    const float4 zv = *reinterpret_cast<const float4*>(z + o);
     float g[4] = {dv.x, dv.y, dv.z, dv.w};
-    const float zz[4] = {zv.x, zv.y, zv.z, zv.w};
     if (relu) {
         const float4 yv = *reinterpret_cast<const float4*>(y + o);
         const float yy[4] = {yv.x, yv.y, yv.z, yv.w};
@@ -406,28 +438,31 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* _
         r.x += g[0]; r.y += g[1]; r.z += g[2]; r.w += g[3];
         *reinterpret_cast<float4*>(dres + o) = r;
     }
+    const float4 sc4 = __ldg(reinterpret_cast<const float4*>(bn) + c4);
+    const float sc[4] = {sc4.x, sc4.y, sc4.z, sc4.w};
     float out[4];
+    if (train) {
+        const float4 zv = *reinterpret_cast<const float4*>(z + o);
+        const float4 mean4 = __ldg(reinterpret_cast<const float4*>(bn + 2 * C) + c4);
+        const float4 inv4 = __ldg(reinterpret_cast<const float4*>(bn + 3 * C) + c4);
+        const float4 m14 = __ldg(reinterpret_cast<const float4*>(mf) + c4);
+        const float4 m24 = __ldg(reinterpret_cast<const float4*>(mf + C) + c4);
+        const float zz[4] = {zv.x, zv.y, zv.z, zv.w}, mm[4] = {mean4.x, mean4.y, mean4.z, mean4.w};
+        const float iv[4] = {inv4.x, inv4.y, inv4.z, inv4.w};
+        const float m1[4] = {m14.x, m14.y, m14.z, m14.w}, m2[4] = {m24.x, m24.y, m24.z, m24.w};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int c = c4 * 4 + j;
-        const float scale = bn[c];
-        if (train) {
-            const float xhat = (zz[j] - bn[2 * C + c]) * bn[3 * C + c];
-            const float m1 = (float)(sums[c] / count), m2 = (float)(sums[C + c] / count);
-            out[j] = scale * (g[j] - m1 - xhat * m2);
-        } else {
-            out[j] = scale * g[j];
+        for (int j = 0; j < 4; ++j) {
+            const float xhat = (zz[j] - mm[j]) * iv[j];
+            out[j] = sc[j] * (g[j] - m1[j] - xhat * m2[j]);
         }
-        if (i < (size_t)C4) {        // pixel 0 writes the parameter gradients of its 4 channels
-            if (dgamma) dgamma[c] = (float)sums[C + c];
-            if (dbeta) dbeta[c] = (float)sums[c];
-            if (dbias) dbias[c] = train ? 0.f : (float)((double)scale * sums[c]);
-        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) out[j] = sc[j] * g[j];
     }
     const float4 ov = make_float4(out[0], out[1], out[2], out[3]);
     *reinterpret_cast<float4*>(dz + o) = ov;
     if (w == 0) *reinterpret_cast<float4*>(dz + (bh * (W + 2) + W + 1) * C + c4 * 4) = ov;
-    if (w == W - 1) *reinterpret_cast<float4*>(dz + (bh * (W + 2)) * C + c4 * 4) = ov;
+    if (w == (unsigned)W - 1) *reinterpret_cast<float4*>(dz + (bh * (W + 2)) * C + c4 * 4) = ov;
 }
 
 // ------------------------------------------------------------------------------------------------ pooling / tail / head
@@ -516,21 +551,24 @@ __global__ void head_bwd_input_kernel(const float* __restrict__ dbon, const floa
     drnn[i] = acc;
 }
 
-// dW[o][j] = sum_{t,b} d[t][b][o] * rnn[t][b][j];  db[o] = sum d     (grid: (4, 12), 256 threads = 256 j)
+// dW[o][j] += sum_{t,b} d[t][b][o] * rnn[t][b][j];  db[o] += sum d   (grid: (4, 12, row splits), 256 threads = 256 j;
+// every block sums its rows in fp64 and adds the partial sum to the zeroed outputs)
 __global__ void head_bwd_weight_kernel(const float* __restrict__ dbon, const float* __restrict__ dcor,
                                        const float* __restrict__ rnn, float* __restrict__ dw, float* __restrict__ db, int T,
                                        int B) {
     const int o = blockIdx.y;
     const int j = blockIdx.x * 256 + threadIdx.x;
+    const int rows = T * B, per = (rows + gridDim.z - 1) / gridDim.z;
+    const int r0 = blockIdx.z * per, r1 = min(rows, r0 + per);
     double acc = 0.0, accb = 0.0;
-    for (int row = 0; row < T * B; ++row) {
+    for (int row = r0; row < r1; ++row) {
         const int t = row / B, b = row - t * B;
         const float d = head_grad(dbon, dcor, t, b, o);
         acc += (double)d * (double)rnn[(size_t)row * 1024 + j];
         accb += (double)d;
     }
-    dw[o * 1024 + j] = (float)acc;
-    if (j == 0) db[o] = (float)accb;
+    atomicAdd(dw + o * 1024 + j, (float)acc);
+    if (j == 0) atomicAdd(db + o, (float)accb);
 }
 
 // out[c] = sum_r x[r][c]      (grid over column chunks of 256 x row splits; atomics)
@@ -660,8 +698,12 @@ __global__ void __launch_bounds__(256) lstm_bwd_step_kernel(const LstmBwdArgs a)
 // The same recurrence as ONE cooperative launch: every warp keeps its W_hh^T row in registers for all T steps, the steps
 // are separated by a grid barrier (arrival counter + bounded spin; a time-out raises *error_flag and lets the kernel
 // run out instead of hanging).  dG of the previous step is read with ld.global.cg (written by other CTAs of this launch).
+// STAGED (B <= 16): the block copies that step's dG [B][2048] of its direction into shared memory once and its 8 warps
+// read it from there (ncu launch list: the eight warps each streaming the same 64 KB from L2 made a step cost 12 us).
+template <bool STAGED>
 __global__ void __launch_bounds__(256) lstm_bwd_persistent_kernel(const LstmBwdArgs a, unsigned int* __restrict__ barrier,
                                                                   int* __restrict__ error_flag) {
+    extern __shared__ float4 sdg[];                        // STAGED: [B][512] float4
     const int dir = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int j = blockIdx.x * 8 + warp;
@@ -677,6 +719,11 @@ __global__ void __launch_bounds__(256) lstm_bwd_persistent_kernel(const LstmBwdA
         const int t = dir == 0 ? a.T - 1 - step : step;
         const int tprev_bwd = dir == 0 ? t + 1 : t - 1;
         const int tprev_fwd = dir == 0 ? t - 1 : t + 1;
+        if (STAGED && step > 0) {
+            const float4* dg4 = reinterpret_cast<const float4*>(a.dgates + (((size_t)dir * a.T + tprev_bwd) * a.B) * 2048);
+            for (int i = threadIdx.x; i < a.B * 512; i += 256) sdg[i] = __ldcg(dg4 + i);
+            __syncthreads();                               // (the grid barrier's __syncthreads separates this from the last reads)
+        }
         for (int b0 = 0; b0 < a.B; b0 += 8) {
             float acc[8];
 #pragma unroll
@@ -688,7 +735,8 @@ __global__ void __launch_bounds__(256) lstm_bwd_persistent_kernel(const LstmBwdA
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         if (b0 + q < a.B) {
-                            const float4 g = __ldcg(reinterpret_cast<const float4*>(dg + (size_t)(b0 + q) * 2048) + lane + 32 * i);
+                            const float4 g = STAGED ? sdg[(b0 + q) * 512 + lane + 32 * i]
+                                                    : __ldcg(reinterpret_cast<const float4*>(dg + (size_t)(b0 + q) * 2048) + lane + 32 * i);
                             acc[q] = fmaf(g.x, wreg[i].x, fmaf(g.y, wreg[i].y, fmaf(g.z, wreg[i].z, fmaf(g.w, wreg[i].w, acc[q]))));
                         }
                     }
@@ -771,21 +819,44 @@ __global__ void flip_oihw_kernel(const float* __restrict__ w, float* __restrict_
 // carry ~22 bits for values well above 2^-14: a gradient tensor is therefore multiplied by a power of two that brings its
 // largest magnitude to [2^11, 2^12) before it is split, and the convolution result is divided by it in the epilogue
 // constants (exact: powers of two); pow2_factor lives in conv_tc.cuh (the tcgen05 weight-gradient kernel divides it out too).
+// 16-byte loads, grid-stride; the tail (n % 4) goes to the first threads
 __global__ void absmax_f32_kernel(const float* __restrict__ x, size_t n, float* __restrict__ out) {
     float m = 0.f;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        m = fmaxf(m, fabsf(x[i]));
+    const size_t n4 = n / 4, stride = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (size_t i = t; i < n4; i += stride) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(x) + i);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(v.x), fabsf(v.y))), fmaxf(fabsf(v.z), fabsf(v.w)));
+    }
+    if (t < n - n4 * 4) m = fmaxf(m, fabsf(x[n4 * 4 + t]));
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, off));
     if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<int*>(out), __float_as_int(m));      // m >= 0: int order = float order
 }
 
+__global__ void split_pow2_scalar_kernel(const float* __restrict__ in, unsigned short* __restrict__ out, size_t n,
+                                         const float* __restrict__ absmax) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    split_scaled(in[i] * pow2_factor(*absmax), out[i], out[n + i]);
+}
+
+// n % 8 == 0 (both planes 16-byte aligned): 8 elements per thread, two 16-byte loads, one 16-byte store per plane
 __global__ void split_pow2_kernel(const float* __restrict__ in, unsigned short* __restrict__ out, size_t n,
                                   const float* __restrict__ absmax) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    const size_t n8 = n / 8;
     const float s = pow2_factor(*absmax);
-    split_scaled(in[i] * s, out[i], out[n + i]);
+    if (i < n8) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        unsigned short h[8], l[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) split_scaled(v[j] * s, h[j], l[j]);
+        *reinterpret_cast<uint4*>(out + 8 * i) = make_uint4((unsigned)h[0] | ((unsigned)h[1] << 16), (unsigned)h[2] | ((unsigned)h[3] << 16),
+                                                            (unsigned)h[4] | ((unsigned)h[5] << 16), (unsigned)h[6] | ((unsigned)h[7] << 16));
+        *reinterpret_cast<uint4*>(out + n + 8 * i) = make_uint4((unsigned)l[0] | ((unsigned)l[1] << 16), (unsigned)l[2] | ((unsigned)l[3] << 16),
+                                                                (unsigned)l[4] | ((unsigned)l[5] << 16), (unsigned)l[6] | ((unsigned)l[7] << 16));
+    }
 }
 
 __global__ void aux_div_pow2_kernel(float* __restrict__ aux, int C, const float* __restrict__ absmax) {
@@ -844,11 +915,16 @@ int add_inplace(float* dst, const float* src, size_t n, cudaStream_t st) {
 int split_planes_pow2(const float* in, unsigned short* out, size_t n, float* absmax_scratch, cudaStream_t st) {
     HN_CUDA_OK(cudaMemsetAsync(absmax_scratch, 0, sizeof(float), st));
     if (n == 0) return 0;
-    size_t blocks = (n + 256 * 16 - 1) / (256 * 16);
+    size_t blocks = (n / 4 + 256 * 4 - 1) / (256 * 4);                                  // >= 4 float4 per thread
     if (blocks > 148 * 8) blocks = 148 * 8;
+    if (blocks < 1) blocks = 1;
+    HN_CHECK((reinterpret_cast<uintptr_t>(in) & 15) == 0, "split_planes_pow2: input must be 16-byte aligned");
     absmax_f32_kernel<<<(unsigned)blocks, 256, 0, st>>>(in, n, absmax_scratch);
     HN_LAUNCH_OK();
-    split_pow2_kernel<<<blocks_for(n), 256, 0, st>>>(in, out, n, absmax_scratch);
+    if (n % 8 == 0 && (reinterpret_cast<uintptr_t>(in) & 15) == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0)
+        split_pow2_kernel<<<blocks_for(n / 8), 256, 0, st>>>(in, out, n, absmax_scratch);
+    else
+        split_pow2_scalar_kernel<<<blocks_for(n), 256, 0, st>>>(in, out, n, absmax_scratch);
     HN_LAUNCH_OK();
     return 0;
 }
@@ -969,23 +1045,26 @@ int bn_apply_fwd(const Act& z, const float* bn, const float* res, bool relu, con
 int bn_bwd(const Act& dy, const Act& y, const Act& z, const float* bn, bool train, bool relu, double* sums, const Act& dz,
            float* dres, float* dgamma, float* dbeta, float* dbias, cudaStream_t st) {
     HN_CHECK(dy.halo == 1 && z.halo == 1 && dz.halo == 1 && z.C % 4 == 0, "bn_bwd: bad tensors");
-    const int C = z.C;
+    const int C = z.C, C4 = C / 4;
     HN_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * (size_t)C * sizeof(double), st));
-    int CL = 32;
-    while (CL < C && CL < 128) CL *= 2;
-    const int cblocks = (C + CL - 1) / CL;
-    const size_t npix = (size_t)z.B * z.H * z.W;
-    const size_t per_block = (size_t)(256 / CL) * 64;
-    size_t psplit = (npix + per_block - 1) / per_block;
-    const size_t want = (size_t)(148 * 8 + cblocks - 1) / cblocks;
-    if (psplit > want) psplit = want;
-    if (psplit < 1) psplit = 1;
-    bn_bwd_reduce_kernel<<<dim3((unsigned)cblocks, (unsigned)psplit), 256, 0, st>>>(dy.p, y.p, z.p, bn, z.B, z.H, z.W, C,
-                                                                                     relu ? 1 : 0, CL, sums);
+    int CL4 = 1;
+    while (CL4 * 2 <= C4 && CL4 * 2 <= 64) CL4 *= 2;
+    const int cblocks = (C4 + CL4 - 1) / CL4;
+    const long long rows = (long long)z.B * z.H;
+    const size_t npix = (size_t)rows * z.W;
+    HN_CHECK(rows < (1ll << 31) && npix * C4 < (1ull << 32), "bn_bwd: tensor too large for 32-bit indexing");
+    long long ysplit = (148 * 8 + cblocks - 1) / cblocks;
+    if (ysplit > rows) ysplit = rows;
+    if (ysplit > 65535) ysplit = 65535;
+    bn_bwd_reduce_kernel<<<dim3((unsigned)cblocks, (unsigned)ysplit), 256, 0, st>>>(dy.p, y.p, z.p, bn, (int)rows, z.W, C,
+                                                                                     relu ? 1 : 0, CL4, sums);
     HN_LAUNCH_OK();
-    const size_t n = npix * (C / 4);
-    bn_bwd_apply_kernel<<<blocks_for(n), 256, 0, st>>>(dy.p, y.p, z.p, bn, sums, (double)npix, train ? 1 : 0, relu ? 1 : 0,
-                                                       dz.p, dres, dgamma, dbeta, dbias, z.B, z.H, z.W, C);
+    float* mf = reinterpret_cast<float*>(sums + 2 * (size_t)C);            // 2*C floats behind the 2*C sums
+    bn_bwd_means_kernel<<<(C + 255) / 256, 256, 0, st>>>(sums, (double)npix, bn, train ? 1 : 0, mf, dgamma, dbeta, dbias, C);
+    HN_LAUNCH_OK();
+    const size_t n = npix * C4;
+    bn_bwd_apply_kernel<<<blocks_for(n), 256, 0, st>>>(dy.p, y.p, z.p, bn, mf, train ? 1 : 0, relu ? 1 : 0, dz.p, dres,
+                                                       (unsigned)n, z.W, C);
     HN_LAUNCH_OK();
     return 0;
 }
@@ -1015,7 +1094,9 @@ int head_bwd(const float* dbon, const float* dcor, const float* rnn, const float
              int B, cudaStream_t st) {
     head_bwd_input_kernel<<<blocks_for((size_t)T * B * 1024), 256, 0, st>>>(dbon, dcor, w, drnn, T, B);
     HN_LAUNCH_OK();
-    head_bwd_weight_kernel<<<dim3(4, 12), 256, 0, st>>>(dbon, dcor, rnn, dw, db, T, B);
+    HN_CUDA_OK(cudaMemsetAsync(dw, 0, 12 * 1024 * sizeof(float), st));
+    HN_CUDA_OK(cudaMemsetAsync(db, 0, 12 * sizeof(float), st));
+    head_bwd_weight_kernel<<<dim3(4, 12, 16), 256, 0, st>>>(dbon, dcor, rnn, dw, db, T, B);
     HN_LAUNCH_OK();
     return 0;
 }
@@ -1051,13 +1132,19 @@ int lstm_bwd_steps(const float* dout, const float* gates, const float* cell, con
     HN_CUDA_OK(cudaGetDevice(&dev));
     HN_CUDA_OK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev));
     HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    HN_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_persistent_kernel, 256, 0));
+    static const bool staged_on = [] { const char* e = getenv("HN_LSTM_BWD_STAGED"); return !(e && atoi(e) == 0); }();
+    const bool staged = staged_on && B <= 16;
+    const size_t smem = staged ? (size_t)B * 2048 * sizeof(float) : 0;
+    void* kernel = staged ? reinterpret_cast<void*>(lstm_bwd_persistent_kernel<true>)
+                          : reinterpret_cast<void*>(lstm_bwd_persistent_kernel<false>);
+    if (staged) HN_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HN_CUDA_OK(staged ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_persistent_kernel<true>, 256, smem)
+                      : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lstm_bwd_persistent_kernel<false>, 256, 0));
     if (persistent_on && barrier && error_flag && coop && per_sm * sms >= 128) {
         // one cooperative launch for the whole sequence (128 co-resident CTAs, grid barrier between the steps)
         HN_CUDA_OK(cudaMemsetAsync(barrier, 0, sizeof(unsigned int), st));
         void* args[] = {&a, &barrier, &error_flag};
-        HN_CUDA_OK(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lstm_bwd_persistent_kernel), dim3(64, 2), dim3(256), args,
-                                               0, st));
+        HN_CUDA_OK(cudaLaunchCooperativeKernel(kernel, dim3(64, 2), dim3(256), args, smem, st));
         HN_LAUNCH_OK();
         return 0;
     }

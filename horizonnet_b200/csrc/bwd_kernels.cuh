@@ -40,7 +40,7 @@ int bn_finalize_full(const double* sums, long long count, const float* gamma, co
 // y_planes (nullable): also write y as fp16 hi/lo planes, the tcgen05 conv kernel's operand format
 int bn_apply_fwd(const Act& z, const float* bn, const float* res, bool relu, const Act& y, unsigned short* y_planes,
                  cudaStream_t st);
-// dz (with halo columns), dres += relu-masked dy, parameter gradients; sums: 2*C doubles of scratch
+// dz (with halo columns), dres += relu-masked dy, parameter gradients; sums: 3*C doubles of scratch
 int bn_bwd(const Act& dy, const Act& y, const Act& z, const float* bn, bool train, bool relu, double* sums, const Act& dz,
            float* dres, float* dgamma, float* dbeta, float* dbias, cudaStream_t st);
 

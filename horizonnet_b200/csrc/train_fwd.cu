@@ -23,39 +23,54 @@ __device__ __forceinline__ float plane_value(const unsigned short* __restrict__ 
 }
 
 // sums[c] += sum z, sums[C + c] += sum z^2 over the interior pixels of a halo-NHWC tensor (fp32, or fp16 hi/lo planes).
-// Block = CL channel lanes x (256 / CL) pixel lanes; consecutive threads read consecutive channels.
+// Block = CL4 channel-quad lanes x (256 / CL4) pixel lanes: a thread owns 4 consecutive channels (one 16-byte load per
+// pixel) and walks its rows with 32-bit index arithmetic (round 2: the first version spent its time in 64-bit
+// divisions of a flat pixel index and scalar loads: 5.3 ms per batch-8 training step for 3.4 GB of input); the sums
+// stay fp64 per element, so the statistics are unchanged.
 template <bool PLANES>
 __global__ void __launch_bounds__(ST_THREADS)
-bn_stats_kernel(const void* __restrict__ z, int B, int H, int W, int C, int halo, int CL, double* __restrict__ sums) {
-    __shared__ double sh[2][ST_THREADS];
-    const int cl = threadIdx.x % CL, pl = threadIdx.x / CL, PL = ST_THREADS / CL;
-    const int c = blockIdx.x * CL + cl;
-    const size_t npix = (size_t)B * H * W;
-    const size_t plane = (size_t)B * H * (W + 2 * halo) * C;
-    double s = 0.0, ss = 0.0;
-    if (c < C) {
-        for (size_t p = (size_t)blockIdx.y * PL + pl; p < npix; p += (size_t)gridDim.y * PL) {
-            const int w = (int)(p % W);
-            const size_t bh = p / W;
-            const size_t i = (bh * (W + 2 * halo) + w + halo) * C + c;
-            float v;
-            if (PLANES) {
-                const unsigned short* q = static_cast<const unsigned short*>(z);
-                v = plane_value(q, q + plane, i);
-            } else {
-                v = static_cast<const float*>(z)[i];
+bn_stats_kernel(const void* __restrict__ z, int rows, int W, int C, int halo, int CL4, double* __restrict__ sums) {
+    __shared__ double sh[ST_THREADS][8];
+    const int cl = threadIdx.x % CL4, pl = threadIdx.x / CL4, PL = ST_THREADS / CL4;
+    const int c4 = blockIdx.x * CL4 + cl;
+    const bool active = c4 * 4 < C;
+    const int Wp = W + 2 * halo;
+    const size_t plane = (size_t)rows * Wp * C;
+    double a[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    if (active) {
+        for (int row = blockIdx.y; row < rows; row += gridDim.y) {
+            const size_t base = ((size_t)row * Wp + halo) * C + (size_t)c4 * 4;
+            for (int w = pl; w < W; w += PL) {
+                const size_t i = base + (size_t)w * C;
+                float v[4];
+                if (PLANES) {
+                    const unsigned short* q = static_cast<const unsigned short*>(z);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) v[j] = plane_value(q, q + plane, i + j);
+                } else {
+                    const float4 f = *reinterpret_cast<const float4*>(static_cast<const float*>(z) + i);
+                    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    a[j] += (double)v[j];
+                    a[4 + j] += (double)v[j] * (double)v[j];
+                }
             }
-            s += (double)v;
-            ss += (double)v * (double)v;
         }
     }
-    sh[0][threadIdx.x] = s;
-    sh[1][threadIdx.x] = ss;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) sh[threadIdx.x][j] = a[j];
     __syncthreads();
-    if (pl == 0 && c < C) {
-        for (int j = 1; j < PL; ++j) { s += sh[0][j * CL + cl]; ss += sh[1][j * CL + cl]; }
-        atomicAdd(sums + c, s);
-        atomicAdd(sums + C + c, ss);
+    if (pl == 0 && active) {
+        for (int k = 1; k < PL; ++k)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] += sh[k * CL4 + cl][j];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            atomicAdd(sums + c4 * 4 + j, a[j]);
+            atomicAdd(sums + C + c4 * 4 + j, a[4 + j]);
+        }
     }
 }
 
@@ -140,20 +155,20 @@ int multiply_inplace(float* x, const float* mask, size_t n, cudaStream_t st) {
 }
 
 int bn_batch_stats(const Act& z, bool planes, double* sums, cudaStream_t st) {
-    HN_CHECK(z.C >= 1 && z.C <= 4096 && z.B >= 1, "bn_batch_stats: bad tensor");
+    HN_CHECK(z.C >= 4 && z.C <= 4096 && z.C % 4 == 0 && z.B >= 1, "bn_batch_stats: bad tensor (C must be a multiple of 4)");
     HN_CUDA_OK(cudaMemsetAsync(sums, 0, 2 * (size_t)z.C * sizeof(double), st));
-    int CL = 32;
-    while (CL < z.C && CL < 128) CL *= 2;
-    const int cblocks = (z.C + CL - 1) / CL;
-    const size_t npix = (size_t)z.B * z.H * z.W;
-    const size_t per_block = (size_t)(ST_THREADS / CL) * 64;               // >= 64 pixels per thread
-    size_t psplit = (npix + per_block - 1) / per_block;
-    const size_t want = (size_t)(148 * 8 + cblocks - 1) / cblocks;
-    if (psplit > want) psplit = want;
-    if (psplit < 1) psplit = 1;
-    dim3 grid((unsigned)cblocks, (unsigned)psplit);
-    if (planes) bn_stats_kernel<true><<<grid, ST_THREADS, 0, st>>>(z.p, z.B, z.H, z.W, z.C, z.halo, CL, sums);
-    else bn_stats_kernel<false><<<grid, ST_THREADS, 0, st>>>(z.p, z.B, z.H, z.W, z.C, z.halo, CL, sums);
+    const int C4 = z.C / 4;
+    int CL4 = 1;
+    while (CL4 * 2 <= C4 && CL4 * 2 <= 64) CL4 *= 2;
+    const int cblocks = (C4 + CL4 - 1) / CL4;
+    const long long rows = (long long)z.B * z.H;
+    HN_CHECK(rows < (1ll << 31), "bn_batch_stats: too many rows");
+    long long ysplit = (148 * 8 + cblocks - 1) / cblocks;                  // ~8 resident blocks per SM
+    if (ysplit > rows) ysplit = rows;
+    if (ysplit > 65535) ysplit = 65535;
+    dim3 grid((unsigned)cblocks, (unsigned)ysplit);
+    if (planes) bn_stats_kernel<true><<<grid, ST_THREADS, 0, st>>>(z.p, (int)rows, z.W, z.C, z.halo, CL4, sums);
+    else bn_stats_kernel<false><<<grid, ST_THREADS, 0, st>>>(z.p, (int)rows, z.W, z.C, z.halo, CL4, sums);
     HN_LAUNCH_OK();
     return 0;
 }

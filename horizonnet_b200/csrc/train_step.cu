@@ -602,7 +602,7 @@ int hn_conv2d_wgrad_tc(const float* in, int B, int H, int W, int Cin, const floa
     return rc;
 }
 
-// BatchNorm2d (+ identity, ReLU) forward and backward on halo-1 NHWC tensors; bn_scratch: 4*C floats, sums: 2*C doubles
+// BatchNorm2d (+ identity, ReLU) forward and backward on halo-1 NHWC tensors; bn_scratch: 4*C floats, sums: 3*C doubles
 int hn_bn_forward_backward(const float* z, int B, int H, int W, int C, const float* gamma, const float* beta,
                            float* running_mean, float* running_var, double factor, int train, int relu, const float* res,
                            float* y, const float* dy, float* dz, float* dres, float* dgamma, float* dbeta, float* bn_scratch,

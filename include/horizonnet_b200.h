@@ -225,7 +225,8 @@ int hn_conv2d(const float* in_dev, int B, int H, int W, int Cin, int in_halo,
               int relu, float* out_dev, int out_halo, int impl, void* stream);
 /* Backward building blocks of the training step, for unit tests against torch.autograd (train_step.cu):
  * weight + data gradient of one convolution (dz: halo-1 NHWC with circular halo columns; din may be NULL),
- * BatchNorm2d (+identity, ReLU) forward+backward, and one bidirectional LSTM layer's gate gradients. */
+ * BatchNorm2d (+identity, ReLU) forward+backward (bn_scratch: 4*C floats, sums: 3*C doubles, C a multiple of 4), and one
+ * bidirectional LSTM layer's gate gradients. */
 int hn_conv2d_backward(const float* in, int B, int H, int W, int Cin, int in_halo, const float* w_oihw, const float* dz,
                        int Cout, int kh, int kw, int sh, int sw, int ph, int pw, float* din, float* dw_oihw, void* stream);
 /* The weight gradient alone on the tcgen05 kernel (wgrad_tc.cu; in / dz: halo-1 NHWC fp32, Cin and Cout multiples of 64,

@@ -757,9 +757,10 @@ def test_training_step_weight_gradients_tcgen05_vs_fp32_kernels(monkeypatch):
     assert worst[0][0] < 1e-4, worst[:8]
 
 
+@pytest.mark.parametrize('shape', [(3, 32, 5, 8), (2, 256, 4, 70), (2, 96, 3, 33)])
 @pytest.mark.parametrize('train,relu,res', [(1, 1, True), (1, 0, False), (0, 1, True), (1, 1, False)])
-def test_batchnorm_forward_backward_vs_autograd(train, relu, res):
-    B, C, H, W = 3, 32, 5, 8
+def test_batchnorm_forward_backward_vs_autograd(train, relu, res, shape):
+    B, C, H, W = shape          # channel-quad lanes x pixel lanes of the reduction kernels: 8 x 32, 64 x 4, 16 x 16 (24 quads)
     g = torch.Generator().manual_seed(3 + train + 2 * relu)
     z = torch.randn(B, C, H, W, generator=g) * 2 + 0.5
     gamma, beta = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
@@ -782,7 +783,7 @@ def test_batchnorm_forward_backward_vs_autograd(train, relu, res):
     drt = torch.zeros_like(zt) if res else None
     gam, bet, rmt, rvt = gamma.to(DEV), beta.to(DEV), rm.to(DEV), rv.to(DEV)
     dgam, dbet = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
-    scratch, sums = torch.empty(4 * C, device=DEV), torch.zeros(2 * C, device=DEV, dtype=torch.float64)
+    scratch, sums = torch.empty(4 * C, device=DEV), torch.zeros(3 * C, device=DEV, dtype=torch.float64)
     _lib.check(_lib.lib().hn_bn_forward_backward(
         zt.data_ptr(), B, H, W, C, gam.data_ptr(), bet.data_ptr(), rmt.data_ptr(), rvt.data_ptr(), 0.1, train, relu,
         rt.data_ptr() if res else None, yt.data_ptr(), dyt.data_ptr(), dzt.data_ptr(), drt.data_ptr() if res else None,
