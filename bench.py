@@ -649,8 +649,8 @@ def train_step_aux(dev, batch=8, steps=3):
     fw, bw, op = fw / steps, bw / steps, op / steps
     out = {'batch': batch, 'forward_ms': round(fw, 2), 'backward_ms': round(bw, 2), 'optimizer_ms': round(op, 2),
            'step_ms': round(fw + bw + op, 2), 'panoramas_per_s': round(batch / (fw + bw + op) * 1e3, 2),
-           'backward_phases_ms': phases, 'final_loss': round(float(loss), 5),
-           'dtype': ('convolutions, their data gradients and the weight gradients of the Cin/Cout %% 64 == 0 convolutions: tcgen05 '
+           'backward_phases_ms': phases, 'final_loss': round(float(loss.detach()), 5),
+           'dtype': ('convolutions, their data gradients and the weight gradients of the Cin/Cout % 64 == 0 convolutions + the LSTM weights: tcgen05 '
                      'split-fp16 planes (fp32-equivalent); other weight gradients, BatchNorm, LSTM BPTT: fp32 CUDA cores'
                      if wgrad_tc else
                      'convolutions + their data gradients: tcgen05 split-fp16 planes (fp32-equivalent); weight gradients, '
