@@ -23,6 +23,7 @@ int conv_wgrad_f32(const ConvDesc& d, const Act& in, const Act& dz, float* dw_oh
 #endif
 bool wgrad_tc_on();
 bool conv_wgrad_tc_supported(const ConvDesc& d, const Act& in, const Act& dz);
+int conv_wgrad_tc_plan(const ConvDesc& d, const Act& in, const Act& dz, int sms, int plan[10]);      // host-only (tests)
 int conv_wgrad_tc(const ConvDesc& d, const Act& in, const unsigned short* in_planes, const Act& dz,
                   const unsigned short* dz_planes, const float* dz_absmax, float* dw_ohwi, cudaStream_t st);
 int ohwi_to_oihw(const float* in, float* out, int Cout, int Cin, int kh, int kw, cudaStream_t st);

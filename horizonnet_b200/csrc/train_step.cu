@@ -574,6 +574,19 @@ int hn_conv2d_backward(const float* in, int B, int H, int W, int Cin, int in_hal
     return rc;
 }
 
+// Host-side plan of the tcgen05 weight-gradient kernel for one convolution shape (halo-1 tensors; no GPU needed): plan[10] =
+// tile columns, rows per tile, tiles per row, box rows, images per tile, pixel tiles, tiles per slice, slices, work items
+// per slice, CTAs.  -1 for a shape the kernel does not take.
+int hn_wgrad_tc_plan(int B, int H, int W, int Cin, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int sms, int plan[10]) {
+    HN_CHECK(plan, "hn_wgrad_tc_plan: NULL argument");
+    ConvDesc d;
+    d.Cin = Cin; d.Cout = Cout; d.kh = kh; d.kw = kw; d.sh = sh; d.sw = sw; d.ph = ph; d.pw = pw;
+    HN_CHECK(B >= 1 && H >= 1 && W >= 1 && kh >= 1 && kw >= 1 && sh >= 1 && sw >= 1, "hn_wgrad_tc_plan: bad geometry");
+    const Act a = mk(nullptr, B, H, W, Cin, 1);
+    const Act z = mk(nullptr, B, (H + 2 * ph - kh) / sh + 1, (W + 2 * pw - kw) / sw + 1, Cout, 1);
+    return conv_wgrad_tc_plan(d, a, z, sms, plan);
+}
+
 // 1 when the training step routes the weight gradients the tcgen05 kernel supports through it (HN_WGRAD_TC or the built-in default)
 int hn_wgrad_tc_enabled(void) { return wgrad_tc_on() ? 1 : 0; }
 

@@ -244,6 +244,26 @@ bool tile_geometry(const Act& dz, Geometry* g) {
     return true;
 }
 
+// pixel slices: at most 64 tiles (4096 pixels, 256 accumulation steps) and at least 8 tiles per CTA; among those the
+// slice count whose CTA total fills whole waves of the SMs best (one CTA per SM), fewer slices on a tie (fewer reductions).
+// Returns the tiles per slice, *slices_out = the slice count that follows from it.
+int choose_slices(long long num_kt, long long items, int sms, long long* slices_out) {
+    const long long smin = (num_kt + 63) / 64;
+    long long smax = num_kt / 8;
+    if (smax < smin) smax = smin;
+    long long slices = smin;
+    double best = 0.0;
+    for (long long s = smin; s <= smax; ++s) {
+        const long long total = items * s, waves = (total + sms - 1) / sms;
+        const double fill = (double)total / (double)(waves * sms);
+        if (fill > best + 0.02) { best = fill; slices = s; }
+        if (total >= 16ll * sms) break;
+    }
+    const int kt_per_slice = (int)((num_kt + slices - 1) / slices);
+    *slices_out = (num_kt + kt_per_slice - 1) / kt_per_slice;
+    return kt_per_slice;
+}
+
 }  // namespace
 
 bool wgrad_tc_on() {
@@ -264,6 +284,23 @@ bool conv_wgrad_tc_supported(const ConvDesc& d, const Act& in, const Act& dz) {
     if (!tile_geometry(dz, &g)) return false;
     if (g.box_rows * d.sh > 256 || g.imgs > 256) return false;
     return g.num_kt > 0 && g.num_kt < (1ll << 24);
+}
+
+// The host-side plan of conv_wgrad_tc for a shape (no device work; `sms` = SM count to plan for):
+// plan[0..9] = tw, rows per tile, tiles per row, box rows, images per tile, pixel tiles, tiles per slice, slices,
+// work items per slice (Cout tiles x Cin tiles x taps), CTAs.
+int conv_wgrad_tc_plan(const ConvDesc& d, const Act& in, const Act& dz, int sms, int plan[10]) {
+    HN_CHECK(conv_wgrad_tc_supported(d, in, dz), "conv_wgrad_tc: unsupported shape");
+    HN_CHECK(sms >= 1, "conv_wgrad_tc_plan: sms must be positive");
+    Geometry g;
+    tile_geometry(dz, &g);
+    const long long items = (long long)((d.Cout + 127) / 128) * ((d.Cin + 127) / 128) * d.kh * d.kw;
+    long long slices = 0;
+    const int kps = choose_slices(g.num_kt, items, sms, &slices);
+    HN_CHECK(items * slices < (1ll << 31), "conv_wgrad_tc: too many work items");
+    const int v[10] = {g.tw, g.rpt, g.wsegs, g.box_rows, g.imgs, (int)g.num_kt, kps, (int)slices, (int)items, (int)(items * slices)};
+    for (int i = 0; i < 10; ++i) plan[i] = v[i];
+    return 0;
 }
 
 int conv_wgrad_tc(const ConvDesc& d, const Act& in, const unsigned short* in_planes, const Act& dz,
@@ -291,25 +328,12 @@ int conv_wgrad_tc(const ConvDesc& d, const Act& in, const unsigned short* in_pla
     }
     HN_CUDA_OK(cudaMemsetAsync(dw_ohwi, 0, (size_t)d.Cout * a.taps * d.Cin * sizeof(float), st));
 
-    // pixel slices: at most 64 tiles (4096 pixels, 256 accumulation steps) and at least 8 tiles per CTA; among those the
-    // slice count whose CTA total fills whole waves of the SMs best (one CTA per SM), fewer slices on a tie (fewer reductions)
     int dev = 0, sms = 0;
     HN_CUDA_OK(cudaGetDevice(&dev));
     HN_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     const long long items = (long long)m_tiles * a.n_tiles * a.taps;
-    const long long smin = (g.num_kt + 63) / 64;
-    long long smax = g.num_kt / 8;
-    if (smax < smin) smax = smin;
-    long long slices = smin;
-    double best = 0.0;
-    for (long long s = smin; s <= smax; ++s) {
-        const long long total = items * s, waves = (total + sms - 1) / sms;
-        const double fill = (double)total / (double)(waves * sms);
-        if (fill > best + 0.02) { best = fill; slices = s; }
-        if (total >= 16ll * sms) break;
-    }
-    a.kt_per_slice = (int)((g.num_kt + slices - 1) / slices);
-    slices = (g.num_kt + a.kt_per_slice - 1) / a.kt_per_slice;
+    long long slices = 0;
+    a.kt_per_slice = choose_slices(g.num_kt, items, sms, &slices);
     a.items_per_slice = (int)items;
     HN_CHECK(items * slices < (1ll << 31), "conv_wgrad_tc: too many work items");
 

@@ -233,6 +233,10 @@ int hn_conv2d_backward(const float* in, int B, int H, int W, int Cin, int in_hal
  * strides 1 or 2): the planes are made inside.  Returns -1 for a shape that kernel does not take. */
 int hn_conv2d_wgrad_tc(const float* in, int B, int H, int W, int Cin, const float* dz, int Cout, int kh, int kw, int sh,
                        int sw, int ph, int pw, float* dw_oihw, void* stream);
+/* Host-side plan of that kernel for one shape (no GPU work; sms = SM count to plan for): plan[10] = tile columns, rows per
+ * tile, tiles per row, box rows, images per tile, pixel tiles (64 pixels each), tiles per slice, slices, work items per slice,
+ * CTAs.  -1 for a shape the kernel does not take. */
+int hn_wgrad_tc_plan(int B, int H, int W, int Cin, int Cout, int kh, int kw, int sh, int sw, int ph, int pw, int sms, int plan[10]);
 int hn_wgrad_tc_enabled(void);   /* 1: the training step uses that kernel where it applies (env HN_WGRAD_TC=0/1 overrides the default) */
 int hn_bn_forward_backward(const float* z, int B, int H, int W, int C, const float* gamma, const float* beta,
                            float* running_mean, float* running_var, double factor, int train, int relu, const float* res,
