@@ -171,3 +171,35 @@ def test_augmentation_draws_and_corner_bookkeeping_replay_the_reference(golden_d
         assert np.abs(cor - g[f'c{c}_cor_out']).max() < 1e-3
     off = augment.draw_params(g['c0_cor_in'], 128, stretch=False, flip=False, rotate=False, gamma=False)
     assert off == dict(kx=None, ky=None, flip=False, dx=0, p=None)
+
+
+def test_tracked_bench_line_carries_every_contract_key():
+    """The last default `bench.py` line of the round (profiles/r02_bench_n1.json, copied from the GPU box) has every key
+    the bench contract names, consistent with each other -- guards the JSON layout without needing a GPU."""
+    import json
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = json.load(open(os.path.join(root, 'profiles', 'r02_bench_n1.json')))
+    base = json.load(open(os.path.join(root, 'BASELINE.json')))
+    for k in ('metric', 'value', 'unit', 'n_gpus', 'steps', 'warmup', 'ms_per_step', 'higher_is_better', 'scaling', 'vs_baseline',
+              'dtype', 'data', 'config', 'clocks', 'e2e', 'gpu_launches', 'roofline', 'cpu_baseline'):
+        assert k in d, k
+    assert base['metric'].startswith(d['metric']) and d['higher_is_better'] is True and d['scaling'] == 'weak' and d['data'] == 'synthetic'
+    assert d['n_gpus'] == 1 and d['warmup'] >= 3 and d['gpu_launches'] > 0 and d['vs_baseline'] is None
+    assert 'workload' in d['config'] and 'l2' in d['config'] and 'model' not in d['config']
+    assert abs(d['value'] - d['config']['global_batch'] / d['ms_per_step'] * 1e3) < 1e-2 * d['value']
+    for k in ('sm_mhz', 'sm_max_mhz', 'reasons'):
+        assert k in d['clocks'], k
+    assert not set(d['clocks']['reasons']) & {'hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown'}
+    e = d['e2e']
+    assert e['unit'] == d['unit'] and e['h2d_bytes_per_step'] == 32 * 3 * 512 * 1024 * 4 and e['d2h_bytes_per_step'] == 32 * 3 * 1024 * 4
+    assert e['value'] != d['value']                                   # measured separately, not a copy of the device-timed value
+    r = d['roofline']
+    for k in ('bound', 'achieved', 'peak', 'unit', 'frac', 'traffic'):
+        assert k in r, k
+    assert r['bound'] in ('hbm', 'tensor') and abs(r['frac'] - r['achieved'] / r['peak']) < 1e-3
+    c = d['cpu_baseline']
+    for k in ('value', 'unit', 'cores', 'kind', 'sample'):
+        assert k in c, k
+    assert c['kind'] in ('reference', 'port') and c['unit'] == d['unit']
+    t = d['aux']['train_step']
+    assert t['wgrad_tc'] is True and abs(t['step_ms'] - (t['forward_ms'] + t['backward_ms'] + t['optimizer_ms'])) < 0.05
