@@ -175,3 +175,35 @@ def test_train_mode_oracle_draws_the_reference_masks_from_torchs_generator(golde
         bon, cor = horizonnet_ref.forward(sd, x, train=horizonnet_ref.TrainMode())
     assert np.abs(bon.numpy() - g['bon']).max() < 2e-5 and np.abs(cor.numpy() - g['cor']).max() < 2e-5
     assert 0.49 < float((masks[0] > 0).float().mean()) < 0.51
+
+
+def test_oracle_backward_matches_the_real_reference(golden_dir):
+    """Row f1, backward: torch.autograd through the oracle's train-mode forward (the checker of the GPU whole-step tests)
+    against the gradients the REAL reference's `loss.backward()` produced (train.py:53-56, :278; fixture minted by
+    tests/golden/make_golden.py golden_train_backward): loss and, for all 241 parameters, strided samples and |grad| max."""
+    import torch.nn.functional as F
+    from horizonnet_b200.weights import synthetic_state_dict, synthetic_panoramas
+    g = np.load(os.path.join(golden_dir, 'train_backward.npz'))
+    batch, n = int(g['batch']), int(g['n'])
+    sd = synthetic_state_dict(int(g['wseed']), 'random')
+    x = synthetic_panoramas(batch, seed=int(g['x_seed']))
+    gen = torch.Generator().manual_seed(int(g['y_seed']))
+    y_bon, y_cor = torch.rand(batch, 2, 1024, generator=gen) - 0.5, torch.rand(batch, 1, 1024, generator=gen)
+    torch.manual_seed(int(g['train_seed']))                  # the two dropout masks, in the reference's draw order
+    masks = [torch.empty(256, batch, 1024).bernoulli_(0.5).div_(0.5) for _ in range(2)]
+    names = [str(k) for k in g['names']]
+    assert len(names) == 241
+    psd = {k: (v.clone().requires_grad_() if k in names else v) for k, v in sd.items()}
+    bon, cor = horizonnet_ref.forward(psd, x, train=horizonnet_ref.TrainMode(masks=masks))
+    loss = F.l1_loss(bon, y_bon) + F.binary_cross_entropy_with_logits(cor, y_cor)
+    assert abs(loss.item() - float(g['loss'])) < 1e-6
+    grads = torch.autograd.grad(loss, [psd[k] for k in names])
+    gmax = float(g['absmax'].max())
+    worst = 0.0
+    for i, (k, gr) in enumerate(zip(names, grads)):
+        flat = gr.reshape(-1)
+        got = flat[::max(1, flat.numel() // n)][:n].numpy()
+        scale = float(g['absmax'][i]) + 1e-4 * gmax          # conv biases in front of a train-mode BN: analytically zero gradient
+        worst = max(worst, float(np.abs(got - g['samples'][i][:got.size]).max()) / scale,
+                    abs(float(flat.abs().max()) - float(g['absmax'][i])) / scale)
+    assert worst < 2e-4, worst                               # measured at mint time: 2.3e-5
