@@ -4,7 +4,7 @@ Run in the build container only (the GPU box has no /root/reference):
     python tests/golden/make_golden.py
 Outputs (committed): tests/golden/forward_identity.npz, forward_randombn.npz,
 panostretch_small.npz, panostretch_rows.npz, tta_randombn.npz, augment.npz (row f3), rotate.npz (row f4),
-train_all.npz / train_frozen1.npz (row f1, train-mode forward), train_backward.npz (row f1, loss.backward()).  The two shims are the ones SURVEY.md section 8c
+train_all.npz / train_frozen1.npz (row f1, train-mode forward), train_backward.npz / train_backward_frozen1.npz (row f1, loss.backward()).  The two shims are the ones SURVEY.md section 8c
 describes: torchvision.resnet50 is forced to weights=None (no network), nothing else is patched.
 Weights/inputs come from horizonnet_b200.weights (numpy RandomState => reproducible on any box).
 """
@@ -289,7 +289,7 @@ def golden_train(name, freeze_earlier_blocks, bn_momentum=None, batch=2, wseed=1
     print('train golden', name, 'oracle-vs-reference', err, 'frozen BN modules:', len(frozen), 'bon', float(bon.abs().max()), 'cor', float(cor.abs().max()))
 
 
-def golden_train_backward(batch=2, wseed=1, n=256):
+def golden_train_backward(name='backward', freeze_earlier_blocks=-1, batch=2, wseed=1, n=256):
     """Row f1, backward: the REAL reference's `loss.backward()` exactly as train.py drives it (:249 net.train(); :52 forward;
     :53-56 loss = L1(bon) + BCE-with-logits(cor); :278 backward), in fp32 without autocast.  Stores the loss and, for each
     of the 241 parameters, |grad| max, |grad| mean and `n` strided samples; the mint asserts that torch.autograd through the
@@ -301,6 +301,15 @@ def golden_train_backward(batch=2, wseed=1, n=256):
     sd = synthetic_state_dict(wseed, 'random')
     net.load_state_dict(sd, strict=True)
     net.train()
+    frozen = []
+    if freeze_earlier_blocks != -1:                                          # train.py:200-208 and :251-256
+        blocks = net.feature_extractor.list_blocks()
+        for i in range(freeze_earlier_blocks + 1):
+            for m in blocks[i]:
+                m.eval()
+                for p in m.parameters():
+                    p.requires_grad = False
+        frozen = [nm for nm, m in net.named_modules() if isinstance(m, torch.nn.BatchNorm2d) and not m.training]
     x = synthetic_panoramas(batch, seed=200 + wseed)
     g = torch.Generator().manual_seed(77)
     y_bon, y_cor = torch.rand(batch, 2, 1024, generator=g) - 0.5, torch.rand(batch, 1, 1024, generator=g)
@@ -308,13 +317,14 @@ def golden_train_backward(batch=2, wseed=1, n=256):
     bon, cor = net(x)
     loss = F.l1_loss(bon, y_bon) + F.binary_cross_entropy_with_logits(cor, y_cor)
     loss.backward()
-    names = [k for k, _ in net.named_parameters()]
-    grads = {k: p.grad for k, p in net.named_parameters()}
-    assert len(names) == 241 and all(v is not None for v in grads.values())
+    names = [k for k, p in net.named_parameters() if p.requires_grad]
+    grads = {k: p.grad for k, p in net.named_parameters() if p.requires_grad}
+    assert len(names) == (241 if not frozen else 241 - 33) and all(v is not None for v in grads.values())
+    assert all(p.grad is None for p in net.parameters() if not p.requires_grad)
     # the oracle's autograd with the masks the reference consumed
     masks = replay_dropout_masks(TRAIN_SEED, batch)
     psd = {k: (v.clone().requires_grad_() if k in grads else v) for k, v in sd.items()}
-    o_bon, o_cor = oracle.forward(psd, x, train=oracle.TrainMode(masks=masks))
+    o_bon, o_cor = oracle.forward(psd, x, train=oracle.TrainMode(masks=masks, frozen=frozen))
     o_loss = F.l1_loss(o_bon, y_bon) + F.binary_cross_entropy_with_logits(o_cor, y_cor)
     o_grads = dict(zip(names, torch.autograd.grad(o_loss, [psd[k] for k in names])))
     gmax = max(float(v.abs().max()) for v in grads.values())
@@ -328,17 +338,19 @@ def golden_train_backward(batch=2, wseed=1, n=256):
         v = flat[::stride][:n].numpy()
         out[:v.size] = v
         return out
-    np.savez_compressed(os.path.join(HERE, 'train_backward.npz'), names=np.array(names, dtype='U'), loss=np.float64(loss.item()),
+    np.savez_compressed(os.path.join(HERE, f'train_{name}.npz'), names=np.array(names, dtype='U'), loss=np.float64(loss.item()),
+                        frozen=np.array(frozen, dtype='U'),
                         absmax=np.array([float(grads[k].abs().max()) for k in names]),
                         absmean=np.array([float(grads[k].abs().double().mean()) for k in names]),
                         samples=np.stack([strided(grads[k]) for k in names]), n=n, wseed=wseed, x_seed=200 + wseed, y_seed=77,
                         batch=batch, train_seed=TRAIN_SEED)
-    print('train backward golden: loss', loss.item(), 'oracle autograd vs reference, worst tensor (rel. to its max):', worst)
+    print('train backward golden', name, ': loss', loss.item(), 'parameters with a gradient:', len(names), 'oracle autograd vs reference, worst tensor (rel. to its max):', worst)
 
 
 if __name__ == '__main__':
-    if len(sys.argv) > 1 and sys.argv[1] == 'backward':    # only the backward fixture of row f1
+    if len(sys.argv) > 1 and sys.argv[1] == 'backward':    # only the backward fixtures of row f1
         golden_train_backward()
+        golden_train_backward('backward_frozen1', 1)
         sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == 'next':        # only the fixtures of the "next" rows f3 / f4
         golden_augment()
@@ -357,3 +369,4 @@ if __name__ == '__main__':
     golden_train('all', -1)
     golden_train('frozen1', 1, bn_momentum=0.01)
     golden_train_backward()
+    golden_train_backward('backward_frozen1', 1)
