@@ -203,3 +203,18 @@ def test_tracked_bench_line_carries_every_contract_key():
     assert c['kind'] in ('reference', 'port') and c['unit'] == d['unit']
     t = d['aux']['train_step']
     assert t['wgrad_tc'] is True and abs(t['step_ms'] - (t['forward_ms'] + t['backward_ms'] + t['optimizer_ms'])) < 0.05
+
+
+def test_every_environment_switch_of_the_library_is_documented():
+    """Every HN_* variable the CUDA sources or the Python package read appears in INTEGRATION.md's switch table."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for f in glob.glob(os.path.join(root, 'horizonnet_b200', 'csrc', '*.cu*')) + glob.glob(os.path.join(root, 'horizonnet_b200', '*.py')):
+        src = open(f).read()
+        names |= set(re.findall(r'getenv\("(HN_[A-Z0-9_]+)"\)', src)) | set(re.findall(r"environ\.get\('(HN_[A-Z0-9_]+)'", src))
+    doc = open(os.path.join(root, 'INTEGRATION.md')).read()
+    assert len(names) >= 15
+    missing = sorted(n for n in names if n not in doc)
+    assert not missing, missing
